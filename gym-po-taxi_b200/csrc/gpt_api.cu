@@ -1,0 +1,420 @@
+// gpt_api.cu — the extern "C" surface declared in include/gpt_b200.h.
+#include <cstdio>
+#include <cstring>
+#include <new>
+
+#include "gpt_internal.h"
+
+// Minimal DLPack (v0.x ABI) definitions — only what gpt_bind_dlpack / gpt_step_dlpack read.
+extern "C" {
+typedef struct {
+  int32_t device_type;
+  int32_t device_id;
+} GptDLDevice;
+typedef struct {
+  uint8_t code;
+  uint8_t bits;
+  uint16_t lanes;
+} GptDLDataType;
+typedef struct {
+  void* data;
+  GptDLDevice device;
+  int32_t ndim;
+  GptDLDataType dtype;
+  int64_t* shape;
+  int64_t* strides;
+  uint64_t byte_offset;
+} GptDLTensor;
+typedef struct GptDLManagedTensor {
+  GptDLTensor dl_tensor;
+  void* manager_ctx;
+  void (*deleter)(struct GptDLManagedTensor*);
+} GptDLManagedTensor;
+}
+enum { kDLCUDA = 2, kDLCUDAManaged = 13, kDLInt = 0, kDLUInt = 1, kDLFloat = 2, kDLBool = 6 };
+
+namespace gpt {
+
+static thread_local std::string g_error;
+void set_error(const std::string& msg) { g_error = msg; }
+int fail(int code, const std::string& msg) {
+  g_error = msg;
+  return code;
+}
+int cuda_fail(cudaError_t e, const char* what) {
+  g_error = std::string(what) + ": " + cudaGetErrorString(e);
+  return GPT_E_CUDA;
+}
+
+static int elem_size(int dtype) {
+  switch (dtype) {
+    case GPT_DT_U8:
+    case GPT_DT_I8: return 1;
+    case GPT_DT_U16: return 2;
+    case GPT_DT_I32:
+    case GPT_DT_F32: return 4;
+    case GPT_DT_F64: return 8;
+  }
+  return 0;
+}
+
+void add_array(gpt_env* env, const char* name, int role, int dtype, int cols) {
+  ArraySlot s;
+  memset(&s.desc, 0, sizeof(s.desc));
+  snprintf(s.desc.name, sizeof(s.desc.name), "%s", name);
+  s.desc.role = role;
+  s.desc.dtype = dtype;
+  s.desc.cols = cols;
+  s.desc.elem_size = elem_size(dtype);
+  env->arrays.push_back(s);
+}
+
+int upload_blob(gpt_env* env, const std::vector<uint8_t>& blob) {
+  env->blob_bytes = align16((uint32_t)blob.size());
+  if (env->blob_bytes > 200 * 1024) return fail(GPT_E_ARG, "static tables exceed 200 KB of shared memory");
+  cudaError_t e = cudaMalloc((void**)&env->d_blob, env->blob_bytes);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc(blob)");
+  std::vector<uint8_t> padded(env->blob_bytes, 0);
+  memcpy(padded.data(), blob.data(), blob.size());
+  e = cudaMemcpy(env->d_blob, padded.data(), env->blob_bytes, cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaMemcpy(blob)");
+  return GPT_OK;
+}
+
+static int launch(gpt_env* env, const LaunchArgs& a) {
+  switch (env->cfg.family) {
+    case GPT_FAMILY_TAXI: return taxi_launch(env, a);
+    case GPT_FAMILY_ROOMS: return rooms_launch(env, a);
+    case GPT_FAMILY_CROOMS: return crooms_launch(env, a);
+    case GPT_FAMILY_TAG: return tag_launch(env, a);
+  }
+  return fail(GPT_E_ARG, "unknown family");
+}
+
+static int check_dlpack(const gpt_env* env, const GptDLManagedTensor* m, int dtype, int cols, int64_t min_rows, void** out,
+                        int64_t* rows_out) {
+  if (!m) return fail(GPT_E_DLPACK, "dlpack: NULL tensor");
+  const GptDLTensor& t = m->dl_tensor;
+  if (t.device.device_type != kDLCUDA && t.device.device_type != kDLCUDAManaged)
+    return fail(GPT_E_DLPACK, "dlpack: tensor is not on a CUDA device");
+  if (t.device.device_id != env->cfg.device) return fail(GPT_E_DLPACK, "dlpack: tensor is on a different CUDA device than the env");
+  int code = -1, bits = elem_size(dtype) * 8;
+  switch (dtype) {
+    case GPT_DT_U8: code = kDLUInt; break;
+    case GPT_DT_I8: code = kDLInt; break;
+    case GPT_DT_U16: code = kDLUInt; break;
+    case GPT_DT_I32: code = kDLInt; break;
+    case GPT_DT_F32:
+    case GPT_DT_F64: code = kDLFloat; break;
+  }
+  const bool bool_as_u8 = dtype == GPT_DT_U8 && t.dtype.code == kDLBool && t.dtype.bits == 8;
+  // int16 storage is accepted for uint16 arrays (torch has no general uint16 support)
+  const bool i16_as_u16 = dtype == GPT_DT_U16 && t.dtype.code == kDLInt && t.dtype.bits == 16;
+  if (!bool_as_u8 && !i16_as_u16 && (t.dtype.code != code || t.dtype.bits != bits || t.dtype.lanes != 1))
+    return fail(GPT_E_DLPACK, "dlpack: dtype mismatch");
+  if (t.ndim < 1 || t.ndim > 3) return fail(GPT_E_DLPACK, "dlpack: expected 1 to 3 dimensions");
+  int64_t inner = 1;
+  for (int i = 1; i < t.ndim; ++i) inner *= t.shape[i];
+  if (inner != cols) return fail(GPT_E_DLPACK, "dlpack: trailing dimensions do not match the array's columns");
+  if (t.shape[0] < min_rows) return fail(GPT_E_DLPACK, "dlpack: fewer rows than the env capacity");
+  if (t.strides) {  // must be row-major contiguous
+    int64_t expect = 1;
+    for (int i = t.ndim - 1; i >= 0; --i) {
+      if (t.shape[i] != 1 && t.strides[i] != expect) return fail(GPT_E_DLPACK, "dlpack: tensor is not contiguous");
+      expect *= t.shape[i];
+    }
+  }
+  char* p = (char*)t.data + t.byte_offset;
+  if (((uintptr_t)p & 15u) != 0) return fail(GPT_E_DLPACK, "dlpack: data pointer is not 16-byte aligned");
+  *out = p;
+  if (rows_out) *rows_out = t.shape[0];
+  return GPT_OK;
+}
+
+static int host_path_init(gpt_env* env) {
+  HostPath& h = env->host;
+  if (h.ready) return GPT_OK;
+  for (int i = 0; i < HostPath::kStreams; ++i) {
+    cudaError_t e = cudaStreamCreateWithFlags(&h.streams[i], cudaStreamNonBlocking);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaStreamCreate(host path)");
+    e = cudaEventCreateWithFlags(&h.done[i], cudaEventDisableTiming);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaEventCreate(host path)");
+  }
+  const size_t abytes = (size_t)env->capacity * env->action_cols * elem_size(env->action_dtype);
+  cudaError_t e = cudaMalloc(&h.d_actions, abytes);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc(host path actions)");
+  e = cudaMemset(h.d_actions, 0, abytes);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaMemset(host path actions)");
+  h.ready = true;
+  return GPT_OK;
+}
+
+}  // namespace gpt
+
+using namespace gpt;
+
+int gpt_env::find(const char* name) const {
+  for (size_t i = 0; i < arrays.size(); ++i)
+    if (strncmp(arrays[i].desc.name, name, sizeof(arrays[i].desc.name)) == 0) return (int)i;
+  return -1;
+}
+void* gpt_env::ptr(const char* name) const {
+  int i = find(name);
+  return i < 0 ? nullptr : arrays[i].ptr;
+}
+
+extern "C" {
+
+int gpt_abi_version(void) { return GPT_ABI_VERSION; }
+const char* gpt_last_error(void) { return g_error.c_str(); }
+
+int gpt_create(const gpt_config* cfg, gpt_env** out) {
+  if (!cfg || !out) return fail(GPT_E_ARG, "gpt_create: NULL argument");
+  *out = nullptr;
+  if (cfg->abi_version != GPT_ABI_VERSION) return fail(GPT_E_ARG, "gpt_create: abi_version mismatch");
+  if (cfg->num_envs < 1) return fail(GPT_E_ARG, "gpt_create: num_envs must be >= 1");
+  if (cfg->rng_mode != GPT_RNG_PHILOX && cfg->rng_mode != GPT_RNG_REPLAY) return fail(GPT_E_ARG, "gpt_create: bad rng_mode");
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    return fail(GPT_E_CUDA, std::string("gpt_create: no CUDA device (there is no CPU fallback): ") + cudaGetErrorString(e));
+  if (cfg->device < 0 || cfg->device >= ndev) return fail(GPT_E_ARG, "gpt_create: bad device ordinal");
+  e = cudaSetDevice(cfg->device);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaSetDevice");
+
+  gpt_env* env = new (std::nothrow) gpt_env();
+  if (!env) return fail(GPT_E_ARG, "gpt_create: out of host memory");
+  env->cfg = *cfg;
+  env->capacity = (cfg->num_envs + GPT_ENV_ALIGN - 1) / GPT_ENV_ALIGN * GPT_ENV_ALIGN;
+  if (env->capacity / GPT_ENV_ALIGN > 0x7FFFFFF0LL) {
+    delete env;
+    return fail(GPT_E_ARG, "gpt_create: num_envs too large");
+  }
+  env->n_tiles = (int32_t)(env->capacity / GPT_ENV_ALIGN);
+  int rc;
+  switch (cfg->family) {
+    case GPT_FAMILY_TAXI: rc = taxi_create(env, cfg); break;
+    case GPT_FAMILY_ROOMS: rc = rooms_create(env, cfg); break;
+    case GPT_FAMILY_CROOMS: rc = crooms_create(env, cfg); break;
+    case GPT_FAMILY_TAG: rc = tag_create(env, cfg); break;
+    default: rc = fail(GPT_E_ARG, "gpt_create: unknown family");
+  }
+  if (rc == GPT_OK) {
+    e = cudaMalloc((void**)&env->d_stats, 8 * sizeof(double));
+    if (e == cudaSuccess) e = cudaMemset(env->d_stats, 0, 8 * sizeof(double));
+    if (e != cudaSuccess) rc = cuda_fail(e, "cudaMalloc(stats)");
+  }
+  if (rc != GPT_OK) {
+    std::string keep = g_error;
+    gpt_destroy(env);
+    g_error = keep;
+    return rc;
+  }
+  // host pointers in the copied config must not be dereferenced after create
+  env->cfg.taxi_wall_bits = nullptr;
+  env->cfg.taxi_loc_cell = nullptr;
+  env->cfg.taxi_valid_states = nullptr;
+  env->cfg.taxi_reset_cdf = nullptr;
+  env->cfg.rooms_grid = nullptr;
+  env->cfg.rooms_slip_cumsum = nullptr;
+  *out = env;
+  return GPT_OK;
+}
+
+int gpt_destroy(gpt_env* env) {
+  if (!env) return GPT_OK;
+  cudaSetDevice(env->cfg.device);
+  if (env->d_blob) cudaFree(env->d_blob);
+  if (env->d_stats) cudaFree(env->d_stats);
+  if (env->host.ready) {
+    for (int i = 0; i < HostPath::kStreams; ++i) {
+      if (env->host.done[i]) cudaEventDestroy(env->host.done[i]);
+      if (env->host.streams[i]) cudaStreamDestroy(env->host.streams[i]);
+    }
+    if (env->host.d_actions) cudaFree(env->host.d_actions);
+  }
+  delete env;
+  return GPT_OK;
+}
+
+int64_t gpt_capacity(const gpt_env* env) { return env ? env->capacity : 0; }
+int gpt_array_count(const gpt_env* env) { return env ? (int)env->arrays.size() : 0; }
+
+int gpt_array_info(const gpt_env* env, int index, gpt_array_desc* out) {
+  if (!env || !out || index < 0 || index >= (int)env->arrays.size()) return fail(GPT_E_ARG, "gpt_array_info: bad index");
+  *out = env->arrays[index].desc;
+  return GPT_OK;
+}
+
+int gpt_find_array(const gpt_env* env, const char* name) {
+  if (!env || !name) return fail(GPT_E_ARG, "gpt_find_array: NULL argument");
+  int i = env->find(name);
+  return i < 0 ? fail(GPT_E_ARG, std::string("gpt_find_array: no array named ") + name) : i;
+}
+
+int gpt_bind(gpt_env* env, int index, void* device_ptr, int64_t capacity_rows) {
+  if (!env || index < 0 || index >= (int)env->arrays.size()) return fail(GPT_E_ARG, "gpt_bind: bad index");
+  ArraySlot& s = env->arrays[index];
+  if (s.desc.role == GPT_ROLE_ACTION) return fail(GPT_E_ARG, "gpt_bind: the action array is passed to gpt_step, not bound");
+  if (!device_ptr) return fail(GPT_E_ARG, "gpt_bind: NULL pointer");
+  if (capacity_rows < env->capacity) return fail(GPT_E_ARG, "gpt_bind: array has fewer rows than gpt_capacity()");
+  if (((uintptr_t)device_ptr & 15u) != 0) return fail(GPT_E_ARG, "gpt_bind: pointer must be 16-byte aligned");
+  s.ptr = device_ptr;
+  s.rows = capacity_rows;
+  return GPT_OK;
+}
+
+int gpt_bind_dlpack(gpt_env* env, int index, void* managed) {
+  if (!env || index < 0 || index >= (int)env->arrays.size()) return fail(GPT_E_ARG, "gpt_bind_dlpack: bad index");
+  const ArraySlot& s = env->arrays[index];
+  void* p = nullptr;
+  int64_t rows = 0;
+  if (int rc = check_dlpack(env, (const GptDLManagedTensor*)managed, s.desc.dtype, s.desc.cols, env->capacity, &p, &rows)) return rc;
+  return gpt_bind(env, index, p, rows);
+}
+
+int gpt_reset(gpt_env* env, int has_seed, uint64_t seed, void* stream) {
+  if (!env) return fail(GPT_E_ARG, "gpt_reset: NULL env");
+  if (has_seed) {
+    env->cfg.seed = seed;
+    env->counter = 0;
+  }
+  LaunchArgs a;
+  a.mode = kModeReset;
+  a.n_tiles = env->n_tiles;
+  a.stream = (cudaStream_t)stream;
+  int rc = launch(env, a);
+  env->counter += 1;
+  return rc;
+}
+
+int gpt_step(gpt_env* env, const void* actions, void* stream) {
+  if (!env) return fail(GPT_E_ARG, "gpt_step: NULL env");
+  LaunchArgs a;
+  a.mode = kModeStep;
+  a.actions = actions;
+  a.n_tiles = env->n_tiles;
+  a.stream = (cudaStream_t)stream;
+  int rc = launch(env, a);
+  env->counter += 1;
+  return rc;
+}
+
+int gpt_step_dlpack(gpt_env* env, void* managed_actions, void* stream) {
+  if (!env) return fail(GPT_E_ARG, "gpt_step_dlpack: NULL env");
+  void* p = nullptr;
+  if (int rc = check_dlpack(env, (const GptDLManagedTensor*)managed_actions, env->action_dtype, env->action_cols, env->capacity,
+                            &p, nullptr))
+    return rc;
+  return gpt_step(env, p, stream);
+}
+
+int gpt_step_many(gpt_env* env, const void* actions, int32_t n_steps, int64_t out_stride_rows, void* stream) {
+  if (!env) return fail(GPT_E_ARG, "gpt_step_many: NULL env");
+  if (n_steps < 0 || out_stride_rows < 0) return fail(GPT_E_ARG, "gpt_step_many: negative argument");
+  if (out_stride_rows != 0 && out_stride_rows < env->capacity) return fail(GPT_E_ARG, "gpt_step_many: out_stride_rows < capacity");
+  const size_t arow = (size_t)env->action_cols * elem_size(env->action_dtype);
+  for (int32_t t = 0; t < n_steps; ++t) {
+    LaunchArgs a;
+    a.mode = kModeStep;
+    a.actions = (const char*)actions + (size_t)t * env->capacity * arow;
+    a.out_row = t * out_stride_rows;
+    a.n_tiles = env->n_tiles;
+    a.stream = (cudaStream_t)stream;
+    // outputs at row offsets need (t+1)*stride rows in every bound OUTPUT array
+    if (out_stride_rows) {
+      for (const ArraySlot& s : env->arrays)
+        if (s.desc.role == GPT_ROLE_OUTPUT && s.rows < a.out_row + env->capacity)
+          return fail(GPT_E_ARG, "gpt_step_many: bound output arrays are too small for n_steps*out_stride_rows");
+    }
+    int rc = launch(env, a);
+    env->counter += 1;
+    if (rc) return rc;
+  }
+  return GPT_OK;
+}
+
+int gpt_step_host(gpt_env* env, const gpt_host_io* io) {
+  if (!env || !io || !io->actions || !io->obs || !io->reward || !io->terminated || !io->truncated)
+    return fail(GPT_E_ARG, "gpt_step_host: NULL argument");
+  cudaError_t e = cudaSetDevice(env->cfg.device);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaSetDevice");
+  if (int rc = host_path_init(env)) return rc;
+  HostPath& h = env->host;
+  const int obs_i = env->find("obs");
+  char* d_obs = (char*)env->ptr("obs");
+  float* d_rew = (float*)env->ptr("reward");
+  uint8_t* d_term = (uint8_t*)env->ptr("terminated");
+  uint8_t* d_trunc = (uint8_t*)env->ptr("truncated");
+  if (obs_i < 0 || !d_obs || !d_rew || !d_term || !d_trunc) return fail(GPT_E_UNBOUND, "gpt_step_host: output arrays must be bound");
+  const size_t obs_row = (size_t)env->arrays[obs_i].desc.cols * env->arrays[obs_i].desc.elem_size;
+  const size_t act_row = (size_t)env->action_cols * elem_size(env->action_dtype);
+  const int64_t B = env->cfg.num_envs;
+
+  // chunk the tile range over the internal streams so H2D, compute and D2H overlap
+  const int n_chunks = env->n_tiles < HostPath::kStreams * 2 ? 1 : HostPath::kStreams * 2;
+  const int32_t per = (env->n_tiles + n_chunks - 1) / n_chunks;
+  int rc = GPT_OK;
+  for (int c = 0; c < n_chunks && rc == GPT_OK; ++c) {
+    const int32_t t0 = c * per;
+    const int32_t nt = (t0 + per <= env->n_tiles) ? per : env->n_tiles - t0;
+    if (nt <= 0) break;
+    cudaStream_t st = h.streams[c % HostPath::kStreams];
+    const int64_t r0 = (int64_t)t0 * GPT_ENV_ALIGN;
+    int64_t r1 = r0 + (int64_t)nt * GPT_ENV_ALIGN;
+    if (r1 > B) r1 = B;
+    if (r1 <= r0) break;
+    const size_t rows = (size_t)(r1 - r0);
+    e = cudaMemcpyAsync((char*)h.d_actions + r0 * act_row, (const char*)io->actions + r0 * act_row, rows * act_row,
+                        cudaMemcpyHostToDevice, st);
+    if (e != cudaSuccess) { rc = cuda_fail(e, "H2D actions"); break; }
+    LaunchArgs a;
+    a.mode = kModeStep;
+    a.actions = h.d_actions;
+    a.first_tile = t0;
+    a.n_tiles = nt;
+    a.stream = st;
+    rc = launch(env, a);
+    if (rc) break;
+    e = cudaMemcpyAsync((char*)io->obs + r0 * obs_row, d_obs + r0 * obs_row, rows * obs_row, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(io->reward + r0, d_rew + r0, rows * sizeof(float), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(io->terminated + r0, d_term + r0, rows, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(io->truncated + r0, d_trunc + r0, rows, cudaMemcpyDeviceToHost, st);
+    if (e != cudaSuccess) { rc = cuda_fail(e, "D2H outputs"); break; }
+  }
+  env->counter += 1;
+  for (int i = 0; i < HostPath::kStreams; ++i) {
+    e = cudaStreamSynchronize(h.streams[i]);
+    if (e != cudaSuccess && rc == GPT_OK) rc = cuda_fail(e, "cudaStreamSynchronize(host path)");
+  }
+  return rc;
+}
+
+int gpt_get_counter(const gpt_env* env, uint64_t* counter) {
+  if (!env || !counter) return fail(GPT_E_ARG, "gpt_get_counter: NULL argument");
+  *counter = env->counter;
+  return GPT_OK;
+}
+int gpt_set_counter(gpt_env* env, uint64_t counter) {
+  if (!env) return fail(GPT_E_ARG, "gpt_set_counter: NULL env");
+  env->counter = counter;
+  return GPT_OK;
+}
+int gpt_set_env_offset(gpt_env* env, int64_t env_offset) {
+  if (!env || env_offset < 0) return fail(GPT_E_ARG, "gpt_set_env_offset: bad argument");
+  env->cfg.env_offset = env_offset;
+  return GPT_OK;
+}
+int gpt_stats_ptr(gpt_env* env, void** device_ptr) {
+  if (!env || !device_ptr) return fail(GPT_E_ARG, "gpt_stats_ptr: NULL argument");
+  *device_ptr = env->d_stats;
+  return GPT_OK;
+}
+int gpt_stats_reset(gpt_env* env, void* stream) {
+  if (!env) return fail(GPT_E_ARG, "gpt_stats_reset: NULL env");
+  cudaError_t e = cudaMemsetAsync(env->d_stats, 0, 8 * sizeof(double), (cudaStream_t)stream);
+  return e == cudaSuccess ? GPT_OK : cuda_fail(e, "cudaMemsetAsync(stats)");
+}
+int64_t gpt_launch_count(const gpt_env* env) { return env ? env->launches : 0; }
+
+}  // extern "C"

@@ -1,0 +1,121 @@
+// gpt_common.cuh — device helpers shared by the fused env-step kernels (sm_100a).
+//
+//   * Philox4x32-10 counter RNG (no RNG state in HBM: key = seed, counter = (global env id, step, stream))
+//   * streaming 128/64/32-bit global loads / stores (every per-env byte is touched once per step)
+//   * TMA bulk copy (cp.async.bulk + mbarrier) that stages the packed static tables into shared memory
+//   * exact division of small integers by run-time constants via multiply-high
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace gpt {
+
+constexpr int kWarp = 32;
+constexpr int kQuad = 4;                       // consecutive envs handled as one vector
+constexpr int kQuadsPerThread = 4;             // -> 16 envs per thread
+constexpr int kEnvsPerThread = kQuad * kQuadsPerThread;
+constexpr int kTileEnvs = kWarp * kEnvsPerThread;  // 512 == GPT_ENV_ALIGN
+constexpr int kQuadStride = kWarp * kQuad;     // 128 envs between a thread's consecutive quads
+
+// ------------------------------------------------------------------------------------------
+// Philox4x32-10 (Salmon et al., SC'11).  ctr = {env_lo, env_hi, step_lo, step_hi^stream}, key = seed.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
+  constexpr uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(M0, c.x), lo0 = M0 * c.x;
+    const uint32_t hi1 = __umulhi(M1, c.z), lo1 = M1 * c.z;
+    c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
+    k.x += W0;
+    k.y += W1;
+  }
+  return c;
+}
+
+struct RngKey {
+  uint32_t seed_lo, seed_hi;   // Philox key
+  uint32_t step_lo, step_hi;   // step counter (incremented by the host once per launch / per step)
+};
+
+// one Philox block for (global env id, step, stream)
+__device__ __forceinline__ uint4 env_random(const RngKey& k, uint64_t env, uint32_t stream) {
+  return philox4x32_10(make_uint4((uint32_t)env, (uint32_t)(env >> 32), k.step_lo, k.step_hi ^ (stream << 24)),
+                       make_uint2(k.seed_lo, k.seed_hi));
+}
+
+// unbiased-enough bounded integer: floor(u * n / 2^32); bias <= n * 2^-32
+__device__ __forceinline__ uint32_t bounded(uint32_t u, uint32_t n) { return __umulhi(u, n); }
+
+// ------------------------------------------------------------------------------------------
+// exact n / d for 0 <= n < 2^16, 1 <= d < 2^16:  q = (n * ceil(2^32/d)) >> 32
+// ------------------------------------------------------------------------------------------
+struct FastDiv {
+  uint32_t magic, d;
+};
+__host__ __device__ inline FastDiv make_fastdiv(uint32_t d) {
+  FastDiv f;
+  f.d = d;
+  f.magic = d <= 1 ? 0u : (uint32_t)(((1ull << 32) + d - 1) / d);
+  return f;
+}
+__device__ __forceinline__ uint32_t fdiv(uint32_t n, const FastDiv& f) { return f.d <= 1 ? n : __umulhi(n, f.magic); }
+
+// ------------------------------------------------------------------------------------------
+// streaming global access (evict-first: nothing is re-read within a step)
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ int4 ld_stream(const int4* p) { return __ldcs(p); }
+__device__ __forceinline__ uint2 ld_stream(const uint2* p) { return __ldcs(p); }
+__device__ __forceinline__ uint32_t ld_stream(const uint32_t* p) { return __ldcs(p); }
+__device__ __forceinline__ void st_stream(int4* p, int4 v) { __stcs(p, v); }
+__device__ __forceinline__ void st_stream(uint2* p, uint2 v) { __stcs(p, v); }
+__device__ __forceinline__ void st_stream(uint32_t* p, uint32_t v) { __stcs(p, v); }
+__device__ __forceinline__ void st_stream(float4* p, float4 v) { __stcs(p, v); }
+
+// ------------------------------------------------------------------------------------------
+// TMA bulk copy of the static-table blob: global -> shared, completion on an mbarrier.
+// SASS: UBLKCP + SYNCS.  `bytes` must be a multiple of 16, both addresses 16-byte aligned.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(smem_dst)),
+               "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+// Called by every thread of the CTA.  Thread 0 arms the barrier and issues one bulk copy; the
+// caller overlaps its first global loads with the copy and calls stage_wait() before the first
+// table lookup.
+__device__ __forceinline__ void stage_tables_begin(void* smem_dst, const void* gmem_blob, uint32_t bytes, uint64_t* bar) {
+  if (threadIdx.x == 0) mbar_init(bar, 1);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    mbar_expect_tx(bar, bytes);
+    tma_bulk_g2s(smem_dst, gmem_blob, bytes, bar);
+  }
+}
+__device__ __forceinline__ void stage_tables_wait(uint64_t* bar) { mbar_wait(bar, 0); }
+
+}  // namespace gpt

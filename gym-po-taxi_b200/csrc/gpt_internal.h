@@ -1,0 +1,109 @@
+// gpt_internal.h — host-side handle shared by the C ABI (gpt_api.cu) and the per-family launchers.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/gpt_b200.h"
+#include "gpt_common.cuh"
+
+namespace gpt {
+
+struct ArraySlot {
+  gpt_array_desc desc;
+  void* ptr = nullptr;
+  int64_t rows = 0;
+};
+
+enum LaunchMode { kModeStep = 0, kModeReset = 1 };
+
+struct HostPath {  // gpt_step_host(): chunked H2D -> step -> D2H pipeline
+  static constexpr int kStreams = 4;
+  cudaStream_t streams[kStreams] = {};
+  cudaEvent_t done[kStreams] = {};
+  void* d_actions = nullptr;  // device staging for the host actions (capacity rows)
+  bool ready = false;
+};
+
+}  // namespace gpt
+
+struct gpt_env {
+  gpt_config cfg{};
+  int64_t capacity = 0;
+  int32_t n_tiles = 0;
+  std::vector<gpt::ArraySlot> arrays;
+  // packed static tables (device) — staged into shared memory by every CTA with one TMA bulk copy
+  uint8_t* d_blob = nullptr;
+  uint32_t blob_bytes = 0;
+  double* d_stats = nullptr;
+  uint64_t counter = 0;  // Philox step counter
+  int64_t launches = 0;
+  gpt::HostPath host;
+
+  // ---- taxi ----
+  uint32_t taxi_cdf_off = 0, taxi_vs_off = 0, taxi_rep_shift = 0;
+  // ---- rooms / crooms ----
+  struct RoomsLayout {
+    uint32_t nb8_off = 0, yx_off = 0, room_off = 0, sid_off = 0, valid_off = 0, thr32_off = 0, thr64_off = 0,
+             rows_off = 0, dirs_off = 0;
+    int32_t n_valid = 0, n_rooms = 0, n_cells = 0;
+  } rl;
+  int32_t action_dtype = GPT_DT_I8, action_cols = 1;
+
+  int find(const char* name) const;
+  void* ptr(const char* name) const;  // nullptr if unbound / missing
+};
+
+namespace gpt {
+
+void set_error(const std::string& msg);
+int fail(int code, const std::string& msg);
+int cuda_fail(cudaError_t e, const char* what);
+
+void add_array(gpt_env* env, const char* name, int role, int dtype, int cols);
+int upload_blob(gpt_env* env, const std::vector<uint8_t>& blob);
+
+// per-family: validate the config, build the blob, declare the array schema
+int taxi_create(gpt_env* env, const gpt_config* cfg);
+int rooms_create(gpt_env* env, const gpt_config* cfg);
+int crooms_create(gpt_env* env, const gpt_config* cfg);
+int tag_create(gpt_env* env, const gpt_config* cfg);
+
+// per-family: launch one fused kernel.  `out_row` offsets the OUTPUT arrays (gpt_step_many);
+// `first_tile`/`n_tiles` restrict the launch to a tile range (gpt_step_host chunks); when
+// `actions` is non-null it points at row 0 of the action array.
+struct LaunchArgs {
+  int mode = kModeStep;
+  const void* actions = nullptr;
+  int64_t out_row = 0;
+  int32_t first_tile = 0;
+  int32_t n_tiles = 0;
+  cudaStream_t stream = nullptr;
+};
+int taxi_launch(gpt_env* env, const LaunchArgs& a);
+int rooms_launch(gpt_env* env, const LaunchArgs& a);
+int crooms_launch(gpt_env* env, const LaunchArgs& a);
+int tag_launch(gpt_env* env, const LaunchArgs& a);
+
+inline uint32_t align16(uint32_t x) { return (x + 15u) & ~15u; }
+
+template <typename T>
+inline uint32_t blob_append(std::vector<uint8_t>& blob, const std::vector<T>& v) {
+  uint32_t off = align16((uint32_t)blob.size());
+  blob.resize(off + align16((uint32_t)(v.size() * sizeof(T))), 0);
+  if (!v.empty()) memcpy(blob.data() + off, v.data(), v.size() * sizeof(T));
+  return off;
+}
+
+inline RngKey make_rng_key(const gpt_env* env) {
+  RngKey k;
+  k.seed_lo = (uint32_t)env->cfg.seed;
+  k.seed_hi = (uint32_t)(env->cfg.seed >> 32);
+  k.step_lo = (uint32_t)env->counter;
+  k.step_hi = (uint32_t)(env->counter >> 32) & 0x00FFFFFFu;
+  return k;
+}
+
+}  // namespace gpt

@@ -1,0 +1,316 @@
+// gpt_taxi.cu — fused Taxi POMDP step for sm_100a.
+//
+// One kernel = the whole of TaxiVecEnv.step (reference gym_po/envs/extended_taxi.py:244-287):
+// ++elapsed, decode, move / pickup / dropoff, reward, terminated, truncated, passenger respawn
+// (:354-364), full autoreset (:344-352) and the observation of the post-reset state (:366-372).
+//
+// Data layout in HBM (SoA, `capacity` rows, one stream per field):
+//     s int32 | elapsed int32 | ndrop uint8 | action int8  ->  s, elapsed, ndrop, obs int32,
+//     reward float32, terminated uint8, truncated uint8                       (29 B per env-step)
+// Thread mapping: a warp owns a tile of 512 consecutive envs; lane l handles four "quads" of four
+// consecutive envs at tile + j*128 + 4*l (j = 0..3), so every warp-wide access is one fully used
+// 512 B (int32/float32 streams) or 128 B (byte streams) contiguous segment.
+//
+// Static tables (<= 8 KB) are packed on the host into one blob and staged into shared memory by
+// one TMA bulk copy per CTA:
+//     celltab uint16[cells x REP]: bits 0-3 = wall bits N,S,W,E around the cell (1 = blocked; this is
+//         hansen_encodings, extended_taxi.py:102-114, which also decides motion — SURVEY.md A.1),
+//         bits 8-15 = index of the named location on that cell (0xFF none).  Replicated per lane
+//         (REP = 32) when small so that the data-dependent lookups are bank-conflict free.
+//     reset_cdf uint32[n_valid], valid_states uint16[n_valid]: Philox-mode autoreset sampler.
+#include "gpt_internal.h"
+
+namespace gpt {
+
+struct TaxiParams {
+  int32_t* s;
+  int32_t* elapsed;
+  uint8_t* ndrop;
+  const int8_t* actions;
+  int32_t* obs;
+  float* reward;
+  uint8_t* terminated;
+  uint8_t* truncated;
+  const int32_t* rp_reset_state;
+  const int8_t* rp_new_p;
+  const int8_t* rp_new_d;
+  const uint8_t* blob;
+  uint32_t blob_bytes, cdf_off, vs_off, rep_shift;
+  int64_t env_offset;
+  int32_t first_tile, n_tiles;
+  int32_t cols, nlocs, n_dropoffs, time_limit, n_valid, mode;
+  FastDiv div_nlocs, div_nlocs1;
+  float r_goal, r_bad, r_any;
+  RngKey rng;
+};
+
+struct TaxiTables {
+  const uint16_t* cell;
+  const uint32_t* cdf;
+  const uint16_t* valid;
+  uint32_t rep_shift, rep_lane;
+  __device__ __forceinline__ uint32_t lookup(uint32_t c) const { return cell[(c << rep_shift) | rep_lane]; }
+};
+
+template <bool HANSEN, bool REPLAY>
+__device__ __forceinline__ void taxi_env(const TaxiParams& P, const TaxiTables& T, int64_t env, bool reset_all,
+                                         int32_t& s, int32_t& e, uint32_t& nd, uint32_t a, int32_t& obs, float& rew,
+                                         uint32_t& term, uint32_t& trunc) {
+  const uint32_t nlocs = (uint32_t)P.nlocs;
+  uint32_t cell, p, d;
+  bool full_reset = reset_all;
+  bool respawn = false;
+  rew = 0.f;
+  term = trunc = 0u;
+  uint32_t ent = 0;
+  if (!reset_all) {
+    e += 1;
+    // decode s = ((cell*(nlocs+1)) + p)*nlocs + d           (extended_taxi.py:84-94)
+    const uint32_t t = fdiv((uint32_t)s, P.div_nlocs);
+    d = (uint32_t)s - t * nlocs;
+    cell = fdiv(t, P.div_nlocs1);
+    p = t - cell * (nlocs + 1);
+    // move N/S/W/E unless the wall bit of that side is set    (:248-260)
+    ent = T.lookup(cell);
+    if (a < 4u && !((ent >> a) & 1u)) {
+      const int32_t step = (a & 2u) ? 1 : P.cols;
+      cell = (uint32_t)((int32_t)cell + ((a & 1u) ? step : -step));
+      ent = T.lookup(cell);
+    }
+    // pickup / dropoff                                       (:262-275)
+    const uint32_t here = ent >> 8;  // named location on this cell, 0xFF if none
+    const bool act = a == 4u;
+    const bool goal = act && p == nlocs && here == d;
+    nd += goal ? 1u : 0u;
+    const bool pickup = act && p < nlocs && here == p;
+    p = pickup ? nlocs : p;
+    const bool bad = act && !goal && !pickup;
+    rew = goal ? P.r_goal : (bad ? P.r_bad : P.r_any);
+    term = nd == (uint32_t)P.n_dropoffs;   // (:276-279)
+    trunc = e > P.time_limit;
+    full_reset = term | trunc;
+    respawn = goal && !full_reset;         // (:283-285)
+  }
+  if (respawn | full_reset) {  // rare, divergent
+    uint4 rnd = make_uint4(0, 0, 0, 0);
+    if (!REPLAY) rnd = env_random(P.rng, (uint64_t)(P.env_offset + env), 0u);
+    if (full_reset) {  // _reset_mask (:344-352)
+      uint32_t fresh;
+      if (REPLAY) {
+        fresh = (uint32_t)P.rp_reset_state[env];
+      } else {  // inverse CDF of the law of argmax(multinomial(ns, uniform over valid states))
+        int lo = 0, hi = P.n_valid - 1;
+        while (lo < hi) {
+          const int mid = (lo + hi) >> 1;
+          if (rnd.x <= T.cdf[mid]) hi = mid; else lo = mid + 1;
+        }
+        fresh = T.valid[lo];
+      }
+      const uint32_t t = fdiv(fresh, P.div_nlocs);
+      d = fresh - t * nlocs;
+      cell = fdiv(t, P.div_nlocs1);
+      p = t - cell * (nlocs + 1);
+      e = 0;
+      nd = 0;
+      if (HANSEN) ent = T.lookup(cell);
+    } else {  // _reset_passenger_and_destination (:354-364): p uniform, d uniform over the others
+      if (REPLAY) {
+        p = (uint32_t)P.rp_new_p[env];
+        d = (uint32_t)P.rp_new_d[env];
+      } else {
+        p = bounded(rnd.y, nlocs);
+        d = bounded(rnd.z, nlocs - 1);
+        d += d >= p ? 1u : 0u;
+      }
+    }
+  }
+  s = (int32_t)((cell * (nlocs + 1) + p) * nlocs + d);   // encode (:97-99)
+  obs = HANSEN ? (int32_t)(((ent & 15u) * (nlocs + 1) + p) * nlocs + d) : s;   // (:366-372)
+}
+
+template <bool HANSEN, bool REPLAY>
+__global__ void __launch_bounds__(256) taxi_step_kernel(const __grid_constant__ TaxiParams P) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  __shared__ uint64_t bar;
+  stage_tables_begin(smem, P.blob, P.blob_bytes, &bar);
+
+  const uint32_t lane = threadIdx.x & 31u;
+  const int32_t tile = P.first_tile + (int32_t)(blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5));
+  if (tile >= P.first_tile + P.n_tiles) return;
+  const int64_t base = (int64_t)tile * kTileEnvs + lane * kQuad;
+  const bool reset_all = P.mode == kModeReset;
+
+  int4 s4[kQuadsPerThread], e4[kQuadsPerThread];
+  uint32_t nd4[kQuadsPerThread], a4[kQuadsPerThread];
+#pragma unroll
+  for (int j = 0; j < kQuadsPerThread; ++j) {
+    const int64_t q = base + j * kQuadStride;
+    if (!reset_all) {
+      s4[j] = ld_stream(reinterpret_cast<const int4*>(P.s + q));
+      e4[j] = ld_stream(reinterpret_cast<const int4*>(P.elapsed + q));
+      nd4[j] = ld_stream(reinterpret_cast<const uint32_t*>(P.ndrop + q));
+      a4[j] = ld_stream(reinterpret_cast<const uint32_t*>(P.actions + q));
+    } else {
+      s4[j] = e4[j] = make_int4(0, 0, 0, 0);
+      nd4[j] = a4[j] = 0u;
+    }
+  }
+
+  stage_tables_wait(&bar);
+  TaxiTables T;
+  T.cell = reinterpret_cast<const uint16_t*>(smem);
+  T.cdf = reinterpret_cast<const uint32_t*>(smem + P.cdf_off);
+  T.valid = reinterpret_cast<const uint16_t*>(smem + P.vs_off);
+  T.rep_shift = P.rep_shift;
+  T.rep_lane = P.rep_shift ? lane : 0u;
+
+#pragma unroll
+  for (int j = 0; j < kQuadsPerThread; ++j) {
+    const int64_t q = base + j * kQuadStride;
+    int32_t sv[4] = {s4[j].x, s4[j].y, s4[j].z, s4[j].w};
+    int32_t ev[4] = {e4[j].x, e4[j].y, e4[j].z, e4[j].w};
+    int32_t ov[4];
+    float rv[4];
+    uint32_t ndw = 0, tw = 0, trw = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      uint32_t nd = (nd4[j] >> (8 * k)) & 0xFFu;
+      const uint32_t a = (a4[j] >> (8 * k)) & 0xFFu;
+      uint32_t term, trunc;
+      taxi_env<HANSEN, REPLAY>(P, T, q + k, reset_all, sv[k], ev[k], nd, a, ov[k], rv[k], term, trunc);
+      ndw |= (nd & 0xFFu) << (8 * k);
+      tw |= term << (8 * k);
+      trw |= trunc << (8 * k);
+    }
+    st_stream(reinterpret_cast<int4*>(P.s + q), make_int4(sv[0], sv[1], sv[2], sv[3]));
+    st_stream(reinterpret_cast<int4*>(P.elapsed + q), make_int4(ev[0], ev[1], ev[2], ev[3]));
+    st_stream(reinterpret_cast<uint32_t*>(P.ndrop + q), ndw);
+    st_stream(reinterpret_cast<int4*>(P.obs + q), make_int4(ov[0], ov[1], ov[2], ov[3]));
+    if (!reset_all) {
+      st_stream(reinterpret_cast<float4*>(P.reward + q), make_float4(rv[0], rv[1], rv[2], rv[3]));
+      st_stream(reinterpret_cast<uint32_t*>(P.terminated + q), tw);
+      st_stream(reinterpret_cast<uint32_t*>(P.truncated + q), trw);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------
+int taxi_create(gpt_env* env, const gpt_config* c) {
+  const int64_t cells = (int64_t)c->taxi_rows * c->taxi_cols;
+  const int64_t ns = cells * (c->taxi_nlocs + 1) * c->taxi_nlocs;
+  if (c->taxi_rows < 1 || c->taxi_cols < 1 || c->taxi_nlocs < 2 || c->taxi_nlocs > 254)
+    return fail(GPT_E_ARG, "taxi: need rows, cols >= 1 and 2 <= nlocs <= 254");
+  if (ns >= 65536) return fail(GPT_E_ARG, "taxi: rows*cols*(nlocs+1)*nlocs must be < 65536");
+  if (c->taxi_n_dropoffs < 0 || c->taxi_n_dropoffs > 255) return fail(GPT_E_ARG, "taxi: num_passengers must be in [0, 255]");
+  if (!c->taxi_wall_bits || !c->taxi_loc_cell || !c->taxi_valid_states || c->taxi_n_valid < 1)
+    return fail(GPT_E_ARG, "taxi: wall_bits / loc_cell / valid_states missing");
+  if (c->rng_mode == GPT_RNG_PHILOX && !c->taxi_reset_cdf) return fail(GPT_E_ARG, "taxi: reset_cdf required in Philox mode");
+
+  const uint32_t rep = cells <= 256 ? 32u : 1u;
+  env->taxi_rep_shift = rep == 32u ? 5u : 0u;
+  std::vector<uint16_t> celltab((size_t)cells * rep);
+  for (int64_t i = 0; i < cells; ++i) {
+    uint16_t ent = (uint16_t)(c->taxi_wall_bits[i] & 15u) | 0xFF00u;
+    for (int l = 0; l < c->taxi_nlocs; ++l) {
+      if (c->taxi_loc_cell[l] < 0 || c->taxi_loc_cell[l] >= cells) return fail(GPT_E_ARG, "taxi: loc_cell out of range");
+      if (c->taxi_loc_cell[l] == i) ent = (uint16_t)((ent & 0x00FFu) | (l << 8));
+    }
+    for (uint32_t r = 0; r < rep; ++r) celltab[i * rep + r] = ent;
+  }
+  std::vector<uint32_t> cdf(c->taxi_n_valid, 0xFFFFFFFFu);
+  std::vector<uint16_t> valid(c->taxi_n_valid);
+  for (int i = 0; i < c->taxi_n_valid; ++i) {
+    if (c->taxi_valid_states[i] < 0 || c->taxi_valid_states[i] >= ns) return fail(GPT_E_ARG, "taxi: valid state out of range");
+    valid[i] = (uint16_t)c->taxi_valid_states[i];
+    if (c->taxi_reset_cdf) cdf[i] = c->taxi_reset_cdf[i];
+  }
+  cdf.back() = 0xFFFFFFFFu;
+  std::vector<uint8_t> blob;
+  blob_append(blob, celltab);
+  env->taxi_cdf_off = blob_append(blob, cdf);
+  env->taxi_vs_off = blob_append(blob, valid);
+  if (int rc = upload_blob(env, blob)) return rc;
+
+  add_array(env, "s", GPT_ROLE_STATE, GPT_DT_I32, 1);
+  add_array(env, "elapsed", GPT_ROLE_STATE, GPT_DT_I32, 1);
+  add_array(env, "ndrop", GPT_ROLE_STATE, GPT_DT_U8, 1);
+  add_array(env, "obs", GPT_ROLE_OUTPUT, GPT_DT_I32, 1);
+  add_array(env, "reward", GPT_ROLE_OUTPUT, GPT_DT_F32, 1);
+  add_array(env, "terminated", GPT_ROLE_OUTPUT, GPT_DT_U8, 1);
+  add_array(env, "truncated", GPT_ROLE_OUTPUT, GPT_DT_U8, 1);
+  add_array(env, "replay_reset_state", GPT_ROLE_REPLAY, GPT_DT_I32, 1);
+  add_array(env, "replay_new_p", GPT_ROLE_REPLAY, GPT_DT_I8, 1);
+  add_array(env, "replay_new_d", GPT_ROLE_REPLAY, GPT_DT_I8, 1);
+  add_array(env, "actions", GPT_ROLE_ACTION, GPT_DT_I8, 1);
+  env->action_dtype = GPT_DT_I8;
+  env->action_cols = 1;
+  return GPT_OK;
+}
+
+int taxi_launch(gpt_env* env, const LaunchArgs& a) {
+  const gpt_config& c = env->cfg;
+  TaxiParams P{};
+  P.s = (int32_t*)env->ptr("s");
+  P.elapsed = (int32_t*)env->ptr("elapsed");
+  P.ndrop = (uint8_t*)env->ptr("ndrop");
+  P.actions = (const int8_t*)a.actions;
+  P.obs = (int32_t*)env->ptr("obs");
+  P.reward = (float*)env->ptr("reward");
+  P.terminated = (uint8_t*)env->ptr("terminated");
+  P.truncated = (uint8_t*)env->ptr("truncated");
+  if (!P.s || !P.elapsed || !P.ndrop || !P.obs || !P.reward || !P.terminated || !P.truncated)
+    return fail(GPT_E_UNBOUND, "taxi: state/output arrays must be bound before reset/step");
+  if (a.mode == kModeStep && !P.actions) return fail(GPT_E_ARG, "taxi: actions is NULL");
+  P.obs += a.out_row;
+  P.reward += a.out_row;
+  P.terminated += a.out_row;
+  P.truncated += a.out_row;
+  const bool replay = c.rng_mode == GPT_RNG_REPLAY;
+  if (replay) {
+    P.rp_reset_state = (const int32_t*)env->ptr("replay_reset_state");
+    P.rp_new_p = (const int8_t*)env->ptr("replay_new_p");
+    P.rp_new_d = (const int8_t*)env->ptr("replay_new_d");
+    if (!P.rp_reset_state || !P.rp_new_p || !P.rp_new_d) return fail(GPT_E_UNBOUND, "taxi: replay arrays must be bound in replay mode");
+  }
+  P.blob = env->d_blob;
+  P.blob_bytes = env->blob_bytes;
+  P.cdf_off = env->taxi_cdf_off;
+  P.vs_off = env->taxi_vs_off;
+  P.rep_shift = env->taxi_rep_shift;
+  P.env_offset = c.env_offset;
+  P.first_tile = a.first_tile;
+  P.n_tiles = a.n_tiles;
+  P.cols = c.taxi_cols;
+  P.nlocs = c.taxi_nlocs;
+  P.n_dropoffs = c.taxi_n_dropoffs;
+  P.time_limit = c.time_limit;
+  P.n_valid = c.taxi_n_valid;
+  P.mode = a.mode;
+  P.div_nlocs = make_fastdiv((uint32_t)c.taxi_nlocs);
+  P.div_nlocs1 = make_fastdiv((uint32_t)c.taxi_nlocs + 1);
+  P.r_goal = c.taxi_reward_goal;
+  P.r_bad = c.taxi_reward_bad;
+  P.r_any = c.taxi_reward_any;
+  P.rng = make_rng_key(env);
+
+  const int threads = 256, warps = threads / 32;
+  const int grid = (a.n_tiles + warps - 1) / warps;
+  if (grid <= 0) return GPT_OK;
+  const size_t smem = env->blob_bytes;
+  using K = void (*)(const TaxiParams);
+  K k = c.taxi_hansen_obs ? (replay ? (K)taxi_step_kernel<true, true> : (K)taxi_step_kernel<true, false>)
+                          : (replay ? (K)taxi_step_kernel<false, true> : (K)taxi_step_kernel<false, false>);
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute((const void*)k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(taxi)");
+  }
+  k<<<grid, threads, smem, a.stream>>>(P);
+  env->launches += 1;
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail(e, "taxi_step_kernel launch");
+  return GPT_OK;
+}
+
+}  // namespace gpt

@@ -1,0 +1,211 @@
+"""GPU: fused Taxi step (C ABI -> sm_100a kernel) vs the oracle, bit-exact on replayed draws."""
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from helpers import golden_names, load_golden, make_oracle, recorded_draws
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda:0"
+
+
+def _taxi_env(meta, num_envs=None, **extra):
+    from gym_po.envs import (ExtendedHansenTaxiVecEnv, ExtendedTaxiVecEnv, HansenTaxiVecEnv, TaxiVecEnv)
+    cls = {"TaxiVecEnv": TaxiVecEnv, "HansenTaxiVecEnv": HansenTaxiVecEnv, "ExtendedTaxiVecEnv": ExtendedTaxiVecEnv,
+           "ExtendedHansenTaxiVecEnv": ExtendedHansenTaxiVecEnv}[meta["cls"]]
+    return cls(num_envs or meta["B"], device=DEV, **meta["kwargs"], **extra)
+
+
+def _cmp(g, o, t, what=("obs", "reward", "terminated", "truncated")):
+    for name, x, y in zip(what, g, o):
+        np.testing.assert_array_equal(x.cpu().numpy(), np.asarray(y), err_msg=f"{name} at step {t}")
+
+
+@pytest.mark.parametrize("name", golden_names("taxi"))
+def test_golden_trajectory_free_running(name):
+    """The GPU env, fed the reference's own recorded draws, reproduces the reference trajectory
+    stored in tests/golden (obs, reward, terminated, truncated, final state) with no re-injection."""
+    fx = load_golden(name)
+    meta = fx["meta"]
+    orc = make_oracle(meta, recorded_draws(fx))       # used only to scatter the draws per env
+    env = _taxi_env(meta, rng_mode="replay")
+    orc.reset()
+    env.set_replay(**orc.draws)
+    obs, info = env.reset()
+    assert info == {}
+    np.testing.assert_array_equal(obs.cpu().numpy(), fx["obs0"])
+    for t in range(meta["T"]):
+        a = fx["actions"][t]
+        orc.step(a)
+        env.set_replay(**orc.draws)
+        g = env.step(torch.as_tensor(a, device=DEV))
+        _cmp(g[:4], (fx["obs"][t], fx["rew"][t], fx["term"][t], fx["trunc"][t]), t)
+        assert g[1].dtype == torch.float32 and g[2].dtype == torch.bool and g[3].dtype == torch.bool
+    st = env.get_state()
+    np.testing.assert_array_equal(st["s"].cpu().numpy(), fx["state_s"])
+    np.testing.assert_array_equal(st["elapsed"].cpu().numpy(), fx["state_elapsed"])
+    np.testing.assert_array_equal(st["ndrop"].cpu().numpy(), fx["state_ndrop"].astype(np.int64))
+
+
+@pytest.mark.parametrize("kwargs", [
+    {}, {"hansen_obs": True}, {"map": oracle.EXTENDED_TAXI_MAP, "num_passengers": 4, "time_limit": 37},
+    {"map": oracle.EXTENDED_TAXI_MAP, "hansen_obs": True, "time_limit": 11},
+    {"num_passengers": 0, "time_limit": 5},
+])
+@pytest.mark.parametrize("b", [1, 513, 70_000])
+def test_lockstep_vs_oracle(kwargs, b):
+    """Ragged sizes (1, one-over-a-tile, many tiles), all maps, multi-passenger, mass truncation."""
+    from gym_po.envs import TaxiVecEnv
+    orc = oracle.TaxiOracle(b, draws=oracle.GeneratorDraws(seed=11), **kwargs)
+    env = TaxiVecEnv(b, device=DEV, rng_mode="replay", **kwargs)
+    rng = np.random.default_rng(2)
+    # step before any reset is legal in the reference (state zeros)
+    a = rng.integers(5, size=b)
+    o = orc.step(a)
+    env.set_replay(**orc.draws)
+    _cmp(env.step(torch.as_tensor(a, dtype=torch.int8, device=DEV))[:4], o[:4], -1)
+    o_obs, _ = orc.reset()
+    env.set_replay(**orc.draws)
+    g_obs, _ = env.reset()
+    np.testing.assert_array_equal(g_obs.cpu().numpy(), o_obs)
+    steps = 120 if b > 1000 else 450
+    for t in range(steps):
+        a = rng.integers(5, size=b)
+        o = orc.step(a)
+        env.set_replay(**orc.draws)
+        _cmp(env.step(torch.as_tensor(a, dtype=torch.int8, device=DEV))[:4], o[:4], t)
+    st = env.get_state()
+    np.testing.assert_array_equal(st["s"].cpu().numpy(), orc.s)
+    np.testing.assert_array_equal(st["elapsed"].cpu().numpy(), orc.elapsed)
+    np.testing.assert_array_equal(st["ndrop"].cpu().numpy(), orc.ndrop)
+
+
+@pytest.mark.parametrize("extended", [False, True])
+def test_exhaustive_transition_table(extended):
+    """Every (state, action): teacher-force the oracle state, one step, compare everything."""
+    from gym_po.envs import TaxiVecEnv
+    kw = {"map": oracle.EXTENDED_TAXI_MAP} if extended else {}
+    probe = oracle.TaxiOracle(1, **kw)
+    ns = probe.ns
+    states = np.repeat(np.arange(ns), 5)
+    actions = np.tile(np.arange(5), ns)
+    b = states.size
+    for hansen in (False, True):
+        for elapsed0, ndrop0, npass in ((0, 0, 1), (199, 0, 1), (200, 1, 3), (5, 2, 3)):
+            orc = oracle.TaxiOracle(b, num_passengers=npass, hansen_obs=hansen, draws=oracle.GeneratorDraws(seed=1), **kw)
+            env = TaxiVecEnv(b, num_passengers=npass, hansen_obs=hansen, device=DEV, rng_mode="replay", **kw)
+            st = dict(s=states.copy(), elapsed=np.full(b, elapsed0), ndrop=np.full(b, ndrop0))
+            orc.set_state(**st)
+            env.set_state(**st)
+            o = orc.step(actions)
+            env.set_replay(**orc.draws)
+            _cmp(env.step(torch.as_tensor(actions, dtype=torch.int8, device=DEV))[:4], o[:4], 0)
+            np.testing.assert_array_equal(env.s.cpu().numpy(), orc.s)
+            np.testing.assert_array_equal(env.elapsed.cpu().numpy(), orc.elapsed)
+            np.testing.assert_array_equal(env.n_dropoffs_completed.cpu().numpy(), orc.ndrop)
+
+
+def test_full_size_properties_philox():
+    """BASELINE config 2 size (2^22 envs), Philox mode: size-independent invariants."""
+    from gym_po.envs import TaxiVecEnv
+    b = 1 << 22
+    env = TaxiVecEnv(b, device=DEV, seed=7)
+    obs, _ = env.reset()
+    valid = torch.zeros(env.ns, dtype=torch.bool, device=DEV)
+    valid[torch.as_tensor(env.valid_states, device=DEV).long()] = True
+    assert bool(valid[obs.long()].all()), "reset must land on valid states"
+    assert int(env.elapsed.max()) == 0
+    gen = torch.Generator(device=DEV).manual_seed(0)
+    total_term = 0
+    for t in range(205):
+        a = torch.randint(0, 5, (env.capacity,), dtype=torch.int8, device=DEV, generator=gen)
+        prev_elapsed = env.elapsed.clone()
+        obs, rew, term, trunc, _ = env.step(a)
+        done = term | trunc
+        # elapsed increments or resets; truncation exactly when elapsed would exceed the limit
+        assert bool((env.elapsed[~done] == prev_elapsed[~done] + 1).all())
+        assert bool((env.elapsed[done] == 0).all())
+        assert bool((trunc == (prev_elapsed + 1 > env.time_limit)).all())
+        assert bool(((rew == 1.0) | (rew == -0.5) | (rew == -0.05)).all())
+        assert bool((rew[term] == 1.0).all())            # single passenger: terminated <=> delivered
+        assert bool(valid[obs[done].long()].all())       # autoreset lands on valid states
+        assert int(obs.min()) >= 0 and int(obs.max()) < env.ns
+        total_term += int(term.sum())
+    assert total_term > 0
+    # step 201 after a synchronised reset truncates every env that did not terminate earlier
+    assert int(env.elapsed.max()) <= 205
+
+
+def test_philox_reset_law_and_gpu_count_independence():
+    """(i) reset states follow the reference's argmax-of-multinomial law (chi-square);
+    (ii) sharding the batch over 'ranks' with env_offset gives identical trajectories."""
+    from gym_po.envs import TaxiVecEnv
+    b = 1 << 21
+    env = TaxiVecEnv(b, device=DEV, seed=123)
+    obs, _ = env.reset()
+    counts = torch.bincount(obs.long(), minlength=env.ns).cpu().numpy()[env.valid_states]
+    expected = env.reset_law * b
+    chi2 = float(((counts - expected) ** 2 / expected).sum())
+    dof = len(expected) - 1
+    assert chi2 < dof + 6 * np.sqrt(2 * dof), f"chi2={chi2:.1f} dof={dof}"
+    # uniform would be rejected decisively: the law is far from flat
+    flat = np.full(len(expected), b / len(expected))
+    assert float(((counts - flat) ** 2 / flat).sum()) > 50 * dof
+
+    half = b // 2
+    lo = TaxiVecEnv(half, device=DEV, seed=123, env_offset=0)
+    hi = TaxiVecEnv(half, device=DEV, seed=123, env_offset=half)
+    whole = TaxiVecEnv(b, device=DEV, seed=123)
+    for e in (lo, hi, whole):
+        e.reset(seed=123)
+    gen = torch.Generator(device=DEV).manual_seed(5)
+    for t in range(230):
+        a = torch.randint(0, 5, (b,), dtype=torch.int8, device=DEV, generator=gen)
+        w = whole.step(a)
+        l = lo.step(a[:half].contiguous())
+        h = hi.step(a[half:].contiguous())
+        for k in range(4):
+            assert torch.equal(w[k][:half], l[k]) and torch.equal(w[k][half:], h[k]), f"output {k} at step {t}"
+
+
+def test_boundary_dlpack_and_errors():
+    from gym_po.envs import TaxiVecEnv
+    env = TaxiVecEnv(1024, device=DEV, seed=0)
+    env.reset()
+    a = torch.randint(0, 5, (env.capacity,), dtype=torch.int8, device=DEV)
+    ref = TaxiVecEnv(1024, device=DEV, seed=0)
+    ref.reset(seed=0)
+    env.reset(seed=0)
+    r1 = [x.clone() for x in ref.step(a)[:4]]
+    r2 = env.step_dlpack(a)[:4]
+    for x, y in zip(r1, r2):
+        assert torch.equal(x, y)
+    with pytest.raises(TypeError):      # wrong dtype through DLPack is rejected by the C library
+        env.step_dlpack(a.to(torch.int32))
+    with pytest.raises(TypeError):      # too few rows
+        env.step_dlpack(a[:512])
+    with pytest.raises(ValueError):
+        env.step(torch.zeros(7, dtype=torch.int8, device=DEV))
+    # int64 / numpy actions are accepted (converted / uploaded)
+    env.step(torch.zeros(1024, dtype=torch.int64, device=DEV))
+    env.step(np.zeros(1024, dtype=np.int64))
+    with pytest.raises(ValueError):
+        TaxiVecEnv(8, map=("AB",) * 200 + ("CD",) * 200, device=DEV)   # state space too large for the packed tables
+
+
+def test_host_path_matches_device_path():
+    from gym_po.envs import TaxiVecEnv
+    b = 20_000
+    dev_env = TaxiVecEnv(b, device=DEV, seed=9)
+    host_env = TaxiVecEnv(b, device=DEV, seed=9)
+    dev_env.reset(seed=9)
+    host_env.reset(seed=9)
+    rng = np.random.default_rng(0)
+    for t in range(210):
+        a = rng.integers(5, size=b).astype(np.int8)
+        d = dev_env.step(torch.as_tensor(a, device=DEV))
+        h = host_env.step_host(a)
+        for k in range(4):
+            np.testing.assert_array_equal(d[k].cpu().numpy(), h[k], err_msg=f"output {k} step {t}")
