@@ -188,7 +188,7 @@ def run_b200(args):
     run_steps(max(3, args.warmup))
     torch.cuda.synchronize()
     sampler.active.set()
-    t_end = time.monotonic() + 1.0
+    t_end = time.monotonic() + (0.0 if args.quick else 1.0)
     while time.monotonic() < t_end:
         run_steps(SLOTS * 16)
         torch.cuda.synchronize()
@@ -213,7 +213,7 @@ def run_b200(args):
     ms_max = float(t.item())
 
     # ---- end-to-end: public API with HOST buffers (pinned), H2D + step + D2H inside the timed region
-    e2e_steps = max(3, min(args.steps, args.e2e_steps))
+    e2e_steps = 1 if args.quick else max(3, min(args.steps, args.e2e_steps))
     host_actions = np.random.default_rng(99 + rank).integers(0, wl["n_act"], size=(SLOTS, b)).astype(np.int8)
     pinned = env.host_action_buffer()
     for i in range(3):
@@ -268,7 +268,7 @@ def run_b200(args):
                 line["roofline"]["traffic"] = json.load(open(traffic_file)).get("dram_bytes_per_launch")
             except Exception:
                 pass
-        if world == 1 and not args.no_cpu:
+        if world == 1 and not args.no_cpu and not args.quick:
             line["cpu_baseline"] = cpu_reference(wl["cpu_family"], seconds_target=args.cpu_seconds)
         else:
             line["cpu_baseline"] = None
@@ -313,6 +313,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=100)
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--quick", action="store_true", help="profiling runs: no load phase, no e2e, no CPU baseline")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -1,0 +1,217 @@
+// gpt_rooms.cu — host side of the fused ROOMS step: table building, array schema, launch.
+// The kernel is in gpt_rooms_kernel.cuh; its instantiations in gpt_rooms_k*.cu.
+#include "gpt_rooms_kernel.cuh"
+
+namespace gpt {
+
+// ------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------
+static const int kDY[8] = {-1, -1, 0, 1, 1, 1, 0, -1};
+static const int kDX[8] = {0, 1, 1, 1, 0, -1, -1, -1};
+
+int rooms_build_tables(gpt_env* env, const gpt_config* c, bool discrete_actions) {
+  const int h = c->rooms_h, w = c->rooms_w;
+  if (h < 3 || w < 3 || h > 255 || w > 255 || (int64_t)h * w >= 32768) return fail(GPT_E_ARG, "rooms: grid shape out of range");
+  if (!c->rooms_grid) return fail(GPT_E_ARG, "rooms: grid missing");
+  const int8_t* g = c->rooms_grid;
+  const int nc = h * w;
+  for (int y = 0; y < h; ++y)
+    for (int x = 0; x < w; ++x)
+      if ((y == 0 || x == 0 || y == h - 1 || x == w - 1) && g[y * w + x] >= 0)
+        return fail(GPT_E_ARG, "rooms: the map must have a solid wall border");
+  std::vector<uint8_t> nb8(nc, 0), room(nc, 0xFF);
+  std::vector<uint16_t> sid(nc, 0), valid;
+  int run = 0, max_room = -1;
+  for (int i = 0; i < nc; ++i) {
+    if (g[i] >= 0) {
+      ++run;
+      valid.push_back((uint16_t)i);
+      room[i] = (uint8_t)g[i];
+      if (g[i] > max_room) max_room = g[i];
+      const int y = i / w, x = i % w;
+      for (int d = 0; d < 8; ++d)
+        if (g[(y + kDY[d]) * w + (x + kDX[d])] >= 0) nb8[i] |= (uint8_t)(1u << d);
+    }
+    sid[i] = (uint16_t)(run > 0 ? run - 1 : 0);   // (grid>=0).cumsum()-1  (observations.py:27)
+  }
+  if (valid.empty()) return fail(GPT_E_ARG, "rooms: no walkable cell");
+  // number of rooms = number of distinct non-wall ids (observations.py:40)
+  std::vector<bool> seen(256, false);
+  int n_rooms = 0;
+  for (int i = 0; i < nc; ++i)
+    if (g[i] >= 0 && !seen[(uint8_t)g[i]]) { seen[(uint8_t)g[i]] = true; ++n_rooms; }
+  env->rl.n_valid = (int32_t)valid.size();
+  env->rl.n_rooms = n_rooms;
+  env->rl.n_cells = nc;
+
+  std::vector<uint32_t> thr32;
+  std::vector<double> thr64;
+  if (discrete_actions) {
+    const int n = c->rooms_n_actions;
+    if (n != 4 && n != 8) return fail(GPT_E_ARG, "rooms: n_actions must be 4 (cardinal) or 8 (ordinal)");
+    if (!c->rooms_slip_cumsum) return fail(GPT_E_ARG, "rooms: slip_cumsum missing");
+    thr64.assign(c->rooms_slip_cumsum, c->rooms_slip_cumsum + n * n);
+    thr32.resize(n * n);
+    for (int i = 0; i < n * n; ++i) {
+      const double t = thr64[i] * 4294967296.0;
+      thr32[i] = t >= 4294967295.0 ? 0xFFFFFFFFu : (t <= 0 ? 0u : (uint32_t)t);  // floor
+    }
+  }
+  // walkable-bit rows padded by the window radius (grid obs)
+  std::vector<uint64_t> rows;
+  const int gn = c->rooms_obs_kind == GPT_OBS_GRID ? c->rooms_obs_n : 0;
+  if (gn) {
+    if (gn < 1 || gn > 15) return fail(GPT_E_ARG, "rooms: grid obs_n must be in [1, 15]");
+    const int off = gn / 2;
+    if (w + 2 * off > 64) return fail(GPT_E_ARG, "rooms: map too wide for the bit-row window (w + 2*(n//2) <= 64)");
+    rows.assign(h + 2 * off + 1, 0ull);
+    for (int y = 0; y < h; ++y)
+      for (int x = 0; x < w; ++x)
+        if (g[y * w + x] >= 0) rows[y + off] |= 1ull << (x + off);
+  }
+  std::vector<uint8_t> blob;
+  env->rl.nb8_off = blob_append(blob, nb8);
+  env->rl.room_off = blob_append(blob, room);
+  env->rl.sid_off = blob_append(blob, sid);
+  env->rl.valid_off = blob_append(blob, valid);
+  env->rl.thr32_off = blob_append(blob, thr32);
+  env->rl.thr64_off = blob_append(blob, thr64);
+  env->rl.rows_off = blob_append(blob, rows);
+  return upload_blob(env, blob);
+}
+
+static int obs_desc(const gpt_config* c, int* dtype, int* cols) {
+  switch (c->rooms_obs_kind) {
+    case GPT_OBS_ROOM: case GPT_OBS_ROOM_GOAL: case GPT_OBS_MDP: case GPT_OBS_MDP_GOAL: case GPT_OBS_HANSEN:
+      *dtype = GPT_DT_I32; *cols = 1; return GPT_OK;
+    case GPT_OBS_VEC_MDP: *dtype = GPT_DT_U8; *cols = 2; return GPT_OK;
+    case GPT_OBS_VEC_MDP_GOAL: *dtype = GPT_DT_U8; *cols = 4; return GPT_OK;
+    case GPT_OBS_VEC_HANSEN: case GPT_OBS_VEC_HANSEN_GOAL: *dtype = GPT_DT_U8; *cols = c->rooms_obs_n; return GPT_OK;
+    case GPT_OBS_GRID: *dtype = GPT_DT_U8; *cols = c->rooms_obs_n * c->rooms_obs_n; return GPT_OK;
+  }
+  return fail(GPT_E_ARG, "rooms: unknown obs kind");
+}
+
+int rooms_create(gpt_env* env, const gpt_config* c) {
+  if ((c->rooms_obs_kind == GPT_OBS_HANSEN || c->rooms_obs_kind == GPT_OBS_VEC_HANSEN || c->rooms_obs_kind == GPT_OBS_VEC_HANSEN_GOAL) &&
+      c->rooms_obs_n != 4 && c->rooms_obs_n != 8)
+    return fail(GPT_E_ARG, "rooms: hansen obs_n must be 4 or 8");
+  if (c->env_offset % GPT_ENV_ALIGN != 0) return fail(GPT_E_ARG, "rooms: env_offset must be a multiple of GPT_ENV_ALIGN");
+  if (int rc = rooms_build_tables(env, c, true)) return rc;
+  const bool rgoal = c->rooms_goal_y < 0;
+  if (!rgoal) {
+    if (c->rooms_goal_y >= c->rooms_h || c->rooms_goal_x < 0 || c->rooms_goal_x >= c->rooms_w ||
+        c->rooms_grid[c->rooms_goal_y * c->rooms_w + c->rooms_goal_x] < 0)
+      return fail(GPT_E_ARG, "rooms: fixed goal must be a walkable cell");
+  }
+  int odt, ocols;
+  if (int rc = obs_desc(c, &odt, &ocols)) return rc;
+  add_array(env, "pos", GPT_ROLE_STATE, GPT_DT_U16, 1);
+  if (rgoal) add_array(env, "goal", GPT_ROLE_STATE, GPT_DT_U16, 1);
+  add_array(env, "elapsed", GPT_ROLE_STATE, GPT_DT_I32, 1);
+  add_array(env, "obs", GPT_ROLE_OUTPUT, odt, ocols);
+  add_array(env, "reward", GPT_ROLE_OUTPUT, GPT_DT_F32, 1);
+  add_array(env, "terminated", GPT_ROLE_OUTPUT, GPT_DT_U8, 1);
+  add_array(env, "truncated", GPT_ROLE_OUTPUT, GPT_DT_U8, 1);
+  add_array(env, "replay_u", GPT_ROLE_REPLAY, GPT_DT_F64, 1);
+  add_array(env, "replay_reset_agent", GPT_ROLE_REPLAY, GPT_DT_I32, 1);
+  add_array(env, "replay_reset_goal", GPT_ROLE_REPLAY, GPT_DT_I32, 1);
+  add_array(env, "actions", GPT_ROLE_ACTION, GPT_DT_I8, 1);
+  env->action_dtype = GPT_DT_I8;
+  env->action_cols = 1;
+  return GPT_OK;
+}
+
+
+static void* pick_kernel(int obs, int grid_n, bool rgoal, bool replay) {
+  switch (obs) {
+    case GPT_OBS_ROOM: case GPT_OBS_ROOM_GOAL: case GPT_OBS_MDP: case GPT_OBS_MDP_GOAL: return rooms_pick_table(obs, rgoal, replay);
+    case GPT_OBS_VEC_MDP: case GPT_OBS_VEC_MDP_GOAL: case GPT_OBS_HANSEN: return rooms_pick_vec(obs, rgoal, replay);
+    case GPT_OBS_VEC_HANSEN: case GPT_OBS_VEC_HANSEN_GOAL: return rooms_pick_vhansen(obs, rgoal, replay);
+    case GPT_OBS_GRID:
+      if (grid_n == 3 || grid_n == 5) return rooms_pick_grid_small(grid_n, rgoal, replay);
+      if (grid_n == 7 || grid_n == 9) return rooms_pick_grid_large(grid_n, rgoal, replay);
+      return rooms_pick_grid_any(rgoal, replay);
+  }
+  return nullptr;
+}
+
+int rooms_launch(gpt_env* env, const LaunchArgs& a) {
+  const gpt_config& c = env->cfg;
+  const bool rgoal = c.rooms_goal_y < 0;
+  const bool replay = c.rng_mode == GPT_RNG_REPLAY;
+  RoomsParams P{};
+  P.pos = (uint16_t*)env->ptr("pos");
+  P.goal = rgoal ? (uint16_t*)env->ptr("goal") : nullptr;
+  P.elapsed = (int32_t*)env->ptr("elapsed");
+  P.actions = (const int8_t*)a.actions;
+  P.obs = env->ptr("obs");
+  P.reward = (float*)env->ptr("reward");
+  P.terminated = (uint8_t*)env->ptr("terminated");
+  P.truncated = (uint8_t*)env->ptr("truncated");
+  if (!P.pos || (rgoal && !P.goal) || !P.elapsed || !P.obs || !P.reward || !P.terminated || !P.truncated)
+    return fail(GPT_E_UNBOUND, "rooms: state/output arrays must be bound before reset/step");
+  if (a.mode == kModeStep && !P.actions) return fail(GPT_E_ARG, "rooms: actions is NULL");
+  const int oi = env->find("obs");
+  const size_t obs_row = (size_t)env->arrays[oi].desc.cols * env->arrays[oi].desc.elem_size;
+  P.obs = (uint8_t*)P.obs + a.out_row * obs_row;
+  P.reward += a.out_row;
+  P.terminated += a.out_row;
+  P.truncated += a.out_row;
+  if (replay) {
+    P.rp_u = (const double*)env->ptr("replay_u");
+    P.rp_reset_agent = (const int32_t*)env->ptr("replay_reset_agent");
+    P.rp_reset_goal = (const int32_t*)env->ptr("replay_reset_goal");
+    if (!P.rp_u || !P.rp_reset_agent || !P.rp_reset_goal) return fail(GPT_E_UNBOUND, "rooms: replay arrays must be bound in replay mode");
+  }
+  P.blob = env->d_blob;
+  P.blob_bytes = env->blob_bytes;
+  P.nb8_off = env->rl.nb8_off;
+  P.room_off = env->rl.room_off;
+  P.sid_off = env->rl.sid_off;
+  P.valid_off = env->rl.valid_off;
+  P.thr32_off = env->rl.thr32_off;
+  P.thr64_off = env->rl.thr64_off;
+  P.rows_off = env->rl.rows_off;
+  P.stage_off = (env->blob_bytes + 127u) & ~127u;
+  P.env_offset = c.env_offset;
+  P.first_tile = a.first_tile;
+  P.n_tiles = a.n_tiles;
+  P.mode = a.mode;
+  P.w = c.rooms_w;
+  P.n_actions = c.rooms_n_actions;
+  P.n_valid = env->rl.n_valid;
+  P.n_rooms = env->rl.n_rooms;
+  P.time_limit = c.time_limit;
+  const bool grid = c.rooms_obs_kind == GPT_OBS_GRID;
+  P.hansen_n = grid ? 0 : c.rooms_obs_n;
+  P.grid_n = grid ? c.rooms_obs_n : 0;
+  P.goal_y = rgoal ? 0 : c.rooms_goal_y;
+  P.goal_x = rgoal ? 0 : c.rooms_goal_x;
+  P.goal_cell = rgoal ? 0 : c.rooms_goal_y * c.rooms_w + c.rooms_goal_x;
+  P.div_w = make_fastdiv((uint32_t)c.rooms_w);
+  P.r_step = c.rooms_step_reward;
+  P.r_wall = c.rooms_wall_reward;
+  P.r_goal = c.rooms_goal_reward;
+  P.rng = make_rng_key(env);
+
+  const int threads = grid ? 128 : 256, warps = threads / 32;
+  const int nblocks = (a.n_tiles + warps - 1) / warps;
+  if (nblocks <= 0) return GPT_OK;
+  size_t smem = env->blob_bytes;
+  if (grid) smem = P.stage_off + (size_t)warps * kQuadStride * P.grid_n * P.grid_n;
+  void* k = pick_kernel(c.rooms_obs_kind, P.grid_n, rgoal, replay);
+  if (!k) return fail(GPT_E_ARG, "rooms: no kernel for this obs kind");
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(rooms)");
+  }
+  void* args[] = {(void*)&P};
+  cudaError_t e = cudaLaunchKernel(k, dim3(nblocks), dim3(threads), args, smem, a.stream);
+  env->launches += 1;
+  if (e != cudaSuccess) return cuda_fail(e, "rooms_step_kernel launch");
+  return GPT_OK;
+}
+
+}  // namespace gpt

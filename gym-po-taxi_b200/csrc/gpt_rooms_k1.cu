@@ -1,0 +1,15 @@
+// gpt_rooms_k1.cu — instantiations of rooms_step_kernel (see gpt_rooms_kernel.cuh)
+#include "gpt_rooms_kernel.cuh"
+
+namespace gpt {
+
+void* rooms_pick_vec(int obs, bool rgoal, bool replay) {
+  switch (obs) {
+    case GPT_OBS_VEC_MDP: return pick_rr<GPT_OBS_VEC_MDP, 0>(rgoal, replay);
+    case GPT_OBS_VEC_MDP_GOAL: return pick_rr<GPT_OBS_VEC_MDP_GOAL, 0>(rgoal, replay);
+    case GPT_OBS_HANSEN: return pick_rr<GPT_OBS_HANSEN, 0>(rgoal, replay);
+  }
+  return nullptr;
+}
+
+}  // namespace gpt

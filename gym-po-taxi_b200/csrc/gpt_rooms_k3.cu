@@ -1,0 +1,10 @@
+// gpt_rooms_k3.cu — instantiations of rooms_step_kernel (see gpt_rooms_kernel.cuh)
+#include "gpt_rooms_kernel.cuh"
+
+namespace gpt {
+
+void* rooms_pick_grid_small(int n, bool rgoal, bool replay) {
+  return n == 3 ? pick_rr<GPT_OBS_GRID, 3>(rgoal, replay) : pick_rr<GPT_OBS_GRID, 5>(rgoal, replay);
+}
+
+}  // namespace gpt

@@ -1,0 +1,295 @@
+// gpt_rooms_kernel.cuh — fused discrete ROOMS / FourRooms step for sm_100a.
+//
+// One kernel = RoomsEnv.step (reference gym_po/envs/rooms/rooms.py:198-222): ++elapsed, action slip
+// (rooms/action_utils.py:73-90), move unless the target cell is a wall (:211-213, :224-226), reward with
+// precedence step -> wall -> goal (:215-219), terminated = on goal, truncated = elapsed > limit (:220),
+// same-step autoreset goal-then-agent (:191-196) and the observation of the post-reset state
+// (rooms/observations.py:44-131 and the table/room obs closures of rooms.py:22-48).
+//
+// HBM layout (SoA): pos uint16 (flat cell y*W+x) | [goal uint16, random-goal envs only] | elapsed int32 |
+// action int8  ->  pos, [goal], elapsed, obs, reward float32, terminated uint8, truncated uint8.
+// Thread mapping as in gpt_taxi.cu (warp tile of 512 envs, four quads of 4 consecutive envs per lane).
+//
+// Static tables, one TMA bulk copy per CTA into shared memory:
+//   nb8   uint8 [cells]  bit i = neighbour i (N,NE,E,SE,S,SW,W,NW) is walkable.  Drives BOTH the wall
+//                        collision (blocked = bit of the slipped direction clear) and the Hansen obs.
+//   room  uint8 [cells], sid uint16[cells] (dense cell id), valid uint16[n_valid] (spawn cells)
+//   thr32 uint32[n*n]    floor(cumsum(P[a]) * 2^32)  Philox-mode slip thresholds
+//   thr64 double[n*n]    cumsum(P[a]) exactly as numpy computes it (replay mode compares the recorded u)
+//   rows  uint64[H+2*off] walkable-bit rows, padded by the window radius (grid obs only)
+#pragma once
+#include "gpt_internal.h"
+
+namespace gpt {
+
+struct RoomsParams {
+  uint16_t* pos;
+  uint16_t* goal;
+  int32_t* elapsed;
+  const int8_t* actions;
+  void* obs;
+  float* reward;
+  uint8_t* terminated;
+  uint8_t* truncated;
+  const double* rp_u;
+  const int32_t* rp_reset_agent;
+  const int32_t* rp_reset_goal;
+  const uint8_t* blob;
+  uint32_t blob_bytes, nb8_off, room_off, sid_off, valid_off, thr32_off, thr64_off, rows_off, stage_off;
+  int64_t env_offset;
+  int32_t first_tile, n_tiles, mode;
+  int32_t w, n_actions, n_valid, n_rooms, time_limit;
+  int32_t hansen_n, grid_n, goal_cell, goal_y, goal_x;
+  FastDiv div_w;
+  float r_step, r_wall, r_goal;
+  RngKey rng;
+};
+
+struct RoomsTables {
+  const uint8_t* nb8;
+  const uint8_t* room;
+  const uint16_t* sid;
+  const uint16_t* valid;
+  const uint32_t* thr32;
+  const double* thr64;
+  const uint64_t* rows;
+};
+
+// ordinal direction -> (dy, dx), 2-bit fields holding value+1
+__device__ __forceinline__ int dir_dy(uint32_t d) { return (int)((0x1A90u >> (2 * d)) & 3u) - 1; }
+__device__ __forceinline__ int dir_dx(uint32_t d) { return (int)((0x01A9u >> (2 * d)) & 3u) - 1; }
+// (dy, dx) in {-1,0,1}^2 -> ordinal direction index, 0xF for (0,0)
+__device__ __forceinline__ uint32_t dir_of(int dy, int dx) {
+  return (uint32_t)((0x3452F6107ull >> (4 * ((dy + 1) * 3 + (dx + 1)))) & 0xFull);
+}
+// index (ordinal) of the neighbour holding the goal, 0xF if the goal is not adjacent
+__device__ __forceinline__ uint32_t goal_dir(int y, int x, int gy, int gx) {
+  const int dy = gy - y, dx = gx - x;
+  return ((unsigned)(dy + 1) <= 2u && (unsigned)(dx + 1) <= 2u) ? dir_of(dy, dx) : 0xFu;
+}
+__device__ __forceinline__ uint32_t spread4(uint32_t bits4) { return (bits4 * 0x00204081u) & 0x01010101u; }
+
+enum : int { kObsWords1 = 1 };
+
+template <int OBS, bool RGOAL, bool REPLAY, int GRID_N>
+__global__ void __launch_bounds__(OBS == GPT_OBS_GRID ? 128 : 256) rooms_step_kernel(const __grid_constant__ RoomsParams P) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  __shared__ uint64_t bar;
+  stage_tables_begin(smem, P.blob, P.blob_bytes, &bar);
+
+  const uint32_t lane = threadIdx.x & 31u;
+  const uint32_t warp = threadIdx.x >> 5;
+  const int32_t tile = P.first_tile + (int32_t)(blockIdx.x * (blockDim.x >> 5) + warp);
+  if (tile >= P.first_tile + P.n_tiles) return;
+  const int64_t base = (int64_t)tile * kTileEnvs + lane * kQuad;
+  const bool reset_all = P.mode == kModeReset;
+  const uint32_t n = (uint32_t)P.n_actions;
+
+  uint2 pos4[kQuadsPerThread], goal4[kQuadsPerThread];
+  int4 e4[kQuadsPerThread];
+  uint32_t a4[kQuadsPerThread];
+#pragma unroll
+  for (int j = 0; j < kQuadsPerThread; ++j) {
+    const int64_t q = base + j * kQuadStride;
+    pos4[j] = goal4[j] = make_uint2(0, 0);
+    e4[j] = make_int4(0, 0, 0, 0);
+    a4[j] = 0;
+    if (!reset_all) {
+      pos4[j] = ld_stream(reinterpret_cast<const uint2*>(P.pos + q));
+      if (RGOAL) goal4[j] = ld_stream(reinterpret_cast<const uint2*>(P.goal + q));
+      e4[j] = ld_stream(reinterpret_cast<const int4*>(P.elapsed + q));
+      a4[j] = ld_stream(reinterpret_cast<const uint32_t*>(P.actions + q));
+    }
+  }
+
+  stage_tables_wait(&bar);
+  RoomsTables T;
+  T.nb8 = smem + P.nb8_off;
+  T.room = smem + P.room_off;
+  T.sid = reinterpret_cast<const uint16_t*>(smem + P.sid_off);
+  T.valid = reinterpret_cast<const uint16_t*>(smem + P.valid_off);
+  T.thr32 = reinterpret_cast<const uint32_t*>(smem + P.thr32_off);
+  T.thr64 = reinterpret_cast<const double*>(smem + P.thr64_off);
+  T.rows = reinterpret_cast<const uint64_t*>(smem + P.rows_off);
+  const int gn = GRID_N > 0 ? GRID_N : P.grid_n;
+  uint8_t* stage = smem + P.stage_off + warp * (uint32_t)(kQuadStride * gn * gn);  // grid obs only
+
+#pragma unroll
+  for (int j = 0; j < kQuadsPerThread; ++j) {
+    const int64_t q = base + j * kQuadStride;
+    uint32_t cellv[4] = {pos4[j].x & 0xFFFFu, pos4[j].x >> 16, pos4[j].y & 0xFFFFu, pos4[j].y >> 16};
+    uint32_t goalv[4] = {goal4[j].x & 0xFFFFu, goal4[j].x >> 16, goal4[j].y & 0xFFFFu, goal4[j].y >> 16};
+    int32_t ev[4] = {e4[j].x, e4[j].y, e4[j].z, e4[j].w};
+    float rv[4];
+    uint32_t tw = 0, trw = 0;
+    uint32_t o32[4] = {0, 0, 0, 0};  // scalar obs, or packed bytes of the vector obs (lo)
+    uint32_t o32b[4] = {0, 0, 0, 0}; // second word for 8-byte vector obs
+
+    uint4 slip = make_uint4(0, 0, 0, 0);
+    if (!REPLAY && !reset_all) {  // one Philox block feeds the slip draws of the 4 envs of this quad
+      const uint64_t gq = (uint64_t)(P.env_offset + q) >> 2;
+      slip = philox4x32_10(make_uint4((uint32_t)gq, (uint32_t)(gq >> 32), P.rng.step_lo, P.rng.step_hi),
+                           make_uint2(P.rng.seed_lo, P.rng.seed_hi));
+    }
+    const uint32_t slipv[4] = {slip.x, slip.y, slip.z, slip.w};
+
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int64_t env = q + k;
+      uint32_t cell = cellv[k];
+      uint32_t gcell = RGOAL ? goalv[k] : (uint32_t)P.goal_cell;
+      bool again = reset_all;
+      rv[k] = 0.f;
+      if (!reset_all) {
+        ev[k] += 1;
+        uint32_t a = (a4[j] >> (8 * k)) & 0xFFu;
+        a = a < n ? a : n - 1;
+        // slipped action a' = #{j : cumsum(P[a])_j < u}, clamped to n-1   (action_utils.py:84-90)
+        uint32_t a2 = 0;
+        if (REPLAY) {
+          const double u = P.rp_u[env];
+          const double* row = T.thr64 + a * n;
+          for (uint32_t i = 0; i < n; ++i) a2 += row[i] < u ? 1u : 0u;
+          a2 = a2 < n ? a2 : n - 1;
+        } else {
+          const uint32_t* row = T.thr32 + a * n;
+          for (uint32_t s = n >> 1; s > 0; s >>= 1) a2 += row[a2 + s - 1] < slipv[k] ? s : 0u;
+        }
+        const uint32_t d8 = n == 4 ? a2 * 2 : a2;
+        const bool blocked = !((T.nb8[cell] >> d8) & 1u);   // grid[proposed] == -1   (rooms.py:212, :224-226)
+        if (!blocked) cell = (uint32_t)((int)cell + dir_dy(d8) * P.w + dir_dx(d8));
+        const bool at_goal = cell == gcell;                 // (:216)
+        rv[k] = at_goal ? P.r_goal : (blocked ? P.r_wall : P.r_step);
+        const bool trunc = ev[k] > P.time_limit;            // (:220)
+        tw |= (at_goal ? 1u : 0u) << (8 * k);
+        trw |= (trunc ? 1u : 0u) << (8 * k);
+        again = at_goal | trunc;
+      }
+      if (again) {  // _reset_some (:191-196): goal first, then agent
+        ev[k] = 0;
+        if (REPLAY) {
+          if (RGOAL) gcell = (uint32_t)P.rp_reset_goal[env];
+          cell = (uint32_t)P.rp_reset_agent[env];
+        } else {
+          const uint4 r = env_random(P.rng, (uint64_t)(P.env_offset + env), 1u);
+          if (RGOAL) gcell = T.valid[bounded(r.y, (uint32_t)P.n_valid)];
+          cell = T.valid[bounded(r.x, (uint32_t)P.n_valid)];
+        }
+      }
+      cellv[k] = cell;
+      goalv[k] = gcell;
+
+      // ---- observation of the (post-reset) state ------------------------------------------
+      if constexpr (OBS == GPT_OBS_ROOM) {
+        o32[k] = T.room[cell];
+      } else if constexpr (OBS == GPT_OBS_ROOM_GOAL) {
+        o32[k] = T.room[cell] + (uint32_t)P.n_rooms * T.room[gcell];
+      } else if constexpr (OBS == GPT_OBS_MDP) {
+        o32[k] = T.sid[cell];
+      } else if constexpr (OBS == GPT_OBS_MDP_GOAL) {
+        o32[k] = T.sid[cell] + (uint32_t)P.n_valid * T.sid[gcell];
+      } else {
+        const int y = (int)fdiv(cell, P.div_w), x = (int)cell - y * P.w;
+        int gy = P.goal_y, gx = P.goal_x;
+        if (RGOAL) {
+          gy = (int)fdiv(gcell, P.div_w);
+          gx = (int)gcell - gy * P.w;
+        }
+        if constexpr (OBS == GPT_OBS_VEC_MDP) {
+          o32[k] = (uint32_t)y | ((uint32_t)x << 8);
+        } else if constexpr (OBS == GPT_OBS_VEC_MDP_GOAL) {
+          o32[k] = (uint32_t)y | ((uint32_t)x << 8) | ((uint32_t)gy << 16) | ((uint32_t)gx << 24);
+        } else if constexpr (OBS == GPT_OBS_HANSEN) {  // observations.py:44-71
+          const uint32_t nb = T.nb8[cell];
+          const uint32_t gd = goal_dir(y, x, gy, gx);
+          if (P.hansen_n == 8) {
+            o32[k] = nb * (gd == 0xFu ? 1u : gd + 1u);
+          } else {
+            const uint32_t b4 = (nb & 1u) | ((nb >> 1) & 2u) | ((nb >> 2) & 4u) | ((nb >> 3) & 8u);
+            o32[k] = b4 * ((gd != 0xFu && !(gd & 1u)) ? (gd >> 1) + 1u : 1u);
+          }
+        } else if constexpr (OBS == GPT_OBS_VEC_HANSEN || OBS == GPT_OBS_VEC_HANSEN_GOAL) {  // :106-131
+          const uint32_t nb = T.nb8[cell];
+          uint32_t gd = 0xFu;
+          if constexpr (OBS == GPT_OBS_VEC_HANSEN_GOAL) gd = goal_dir(y, x, gy, gx);
+          if (P.hansen_n == 8) {
+            uint32_t lo = spread4(nb & 15u), hi = spread4(nb >> 4);
+            if (gd < 4u) lo = (lo & ~(0xFFu << (8 * gd))) | (2u << (8 * gd));
+            else if (gd < 8u) hi = (hi & ~(0xFFu << (8 * (gd - 4)))) | (2u << (8 * (gd - 4)));
+            o32[k] = lo;
+            o32b[k] = hi;
+          } else {
+            const uint32_t b4 = (nb & 1u) | ((nb >> 1) & 2u) | ((nb >> 2) & 4u) | ((nb >> 3) & 8u);
+            uint32_t lo = spread4(b4);
+            if (gd != 0xFu && !(gd & 1u)) lo = (lo & ~(0xFFu << (4 * gd))) | (2u << (4 * gd));
+            o32[k] = lo;
+          }
+        } else if constexpr (OBS == GPT_OBS_GRID) {  // observations.py:74-103
+          const int off = gn >> 1;
+          uint8_t* dst = stage + (uint32_t)(lane * kQuad + k) * (uint32_t)(gn * gn);
+          const uint64_t mask = (1ull << gn) - 1ull;
+#pragma unroll
+          for (int r = 0; r < (GRID_N > 0 ? GRID_N : 15); ++r) {
+            if (r < gn) {
+              const uint32_t bits = (uint32_t)((T.rows[y + r] >> x) & mask);
+#pragma unroll
+              for (int c = 0; c < (GRID_N > 0 ? GRID_N : 15); ++c)
+                if (c < gn) dst[r * gn + c] = (uint8_t)((bits >> c) & 1u);
+            }
+          }
+          const int gr = gy - y + off, gc = gx - x + off;
+          if ((unsigned)gr < (unsigned)gn && (unsigned)gc < (unsigned)gn) dst[gr * gn + gc] = 2;
+        }
+      }
+    }
+
+    // ---- stores ------------------------------------------------------------------------------
+    st_stream(reinterpret_cast<uint2*>(P.pos + q), make_uint2(cellv[0] | (cellv[1] << 16), cellv[2] | (cellv[3] << 16)));
+    if (RGOAL) st_stream(reinterpret_cast<uint2*>(P.goal + q), make_uint2(goalv[0] | (goalv[1] << 16), goalv[2] | (goalv[3] << 16)));
+    st_stream(reinterpret_cast<int4*>(P.elapsed + q), make_int4(ev[0], ev[1], ev[2], ev[3]));
+    if (!reset_all) {
+      st_stream(reinterpret_cast<float4*>(P.reward + q), make_float4(rv[0], rv[1], rv[2], rv[3]));
+      st_stream(reinterpret_cast<uint32_t*>(P.terminated + q), tw);
+      st_stream(reinterpret_cast<uint32_t*>(P.truncated + q), trw);
+    }
+    if constexpr (OBS == GPT_OBS_VEC_MDP) {
+      st_stream(reinterpret_cast<uint2*>((uint8_t*)P.obs + q * 2), make_uint2(o32[0] | (o32[1] << 16), o32[2] | (o32[3] << 16)));
+    } else if constexpr (OBS == GPT_OBS_VEC_HANSEN || OBS == GPT_OBS_VEC_HANSEN_GOAL) {
+      if (P.hansen_n == 8) {
+        int4* o = reinterpret_cast<int4*>((uint8_t*)P.obs + q * 8);
+        st_stream(o, make_int4((int)o32[0], (int)o32b[0], (int)o32[1], (int)o32b[1]));
+        st_stream(o + 1, make_int4((int)o32[2], (int)o32b[2], (int)o32[3], (int)o32b[3]));
+      } else {
+        st_stream(reinterpret_cast<int4*>((uint8_t*)P.obs + q * 4), make_int4((int)o32[0], (int)o32[1], (int)o32[2], (int)o32[3]));
+      }
+    } else if constexpr (OBS == GPT_OBS_GRID) {
+      // the warp's 128 envs x n^2 bytes are contiguous in HBM: stream them out with 16-byte stores
+      __syncwarp();
+      const uint32_t vecs = (uint32_t)(kQuadStride * gn * gn) >> 4;
+      const int4* src = reinterpret_cast<const int4*>(stage);
+      int4* dst = reinterpret_cast<int4*>((uint8_t*)P.obs + ((int64_t)tile * kTileEnvs + j * kQuadStride) * (gn * gn));
+      for (uint32_t i = lane; i < vecs; i += 32) st_stream(dst + i, src[i]);
+      __syncwarp();
+    } else {  // scalar int32 obs, or 4 packed bytes per env (VEC_MDP_GOAL)
+      st_stream(reinterpret_cast<int4*>((uint8_t*)P.obs + q * 4), make_int4((int)o32[0], (int)o32[1], (int)o32[2], (int)o32[3]));
+    }
+  }
+}
+
+template <int OBS, int GRID_N>
+static void* pick_rr(bool rgoal, bool replay) {
+  using K = void (*)(const RoomsParams);
+  K k = rgoal ? (replay ? (K)rooms_step_kernel<OBS, true, true, GRID_N> : (K)rooms_step_kernel<OBS, true, false, GRID_N>)
+              : (replay ? (K)rooms_step_kernel<OBS, false, true, GRID_N> : (K)rooms_step_kernel<OBS, false, false, GRID_N>);
+  return (void*)k;
+}
+
+// kernel instantiations live in gpt_rooms_k*.cu so that they compile in parallel
+void* rooms_pick_table(int obs, bool rgoal, bool replay);   // ROOM, ROOM_GOAL, MDP, MDP_GOAL
+void* rooms_pick_vec(int obs, bool rgoal, bool replay);     // VEC_MDP, VEC_MDP_GOAL, HANSEN
+void* rooms_pick_vhansen(int obs, bool rgoal, bool replay); // VEC_HANSEN, VEC_HANSEN_GOAL
+void* rooms_pick_grid_small(int n, bool rgoal, bool replay);  // 3, 5
+void* rooms_pick_grid_large(int n, bool rgoal, bool replay);  // 7, 9
+void* rooms_pick_grid_any(bool rgoal, bool replay);           // run-time n <= 15
+
+}  // namespace gpt

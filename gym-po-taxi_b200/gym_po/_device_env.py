@@ -79,7 +79,9 @@ class DeviceVecEnv:
                 continue
             shape = (self.capacity,) if desc.cols == 1 else (self.capacity, desc.cols)
             t = torch.zeros(shape, dtype=_TORCH_DTYPES[desc.dtype], device=dev)
-            N.check(N.lib.gpt_bind_dlpack(self._h, i, N.dlpack_pointer(to_dlpack(t))))
+            capsule = to_dlpack(t)  # must stay alive across the call: it owns the DLManagedTensor
+            N.check(N.lib.gpt_bind_dlpack(self._h, i, N.dlpack_pointer(capsule)))
+            del capsule
             self._arrays[name] = t
         ashape = (self.capacity,) if self._action_cols == 1 else (self.capacity, self._action_cols)
         self._action_pad = torch.zeros(ashape, dtype=self._action_dtype, device=dev)

@@ -1,0 +1,197 @@
+"""GPU: fused ROOMS step vs the oracle / golden fixtures, bit-exact on replayed draws."""
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from helpers import golden_names, load_golden, make_oracle, recorded_draws
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _cmp(g, o, t):
+    for name, x, y in zip(("obs", "reward", "terminated", "truncated"), g, o):
+        np.testing.assert_array_equal(x.cpu().numpy().astype(np.float64), np.asarray(y, dtype=np.float64),
+                                      err_msg=f"{name} at step {t}")
+
+
+def _kw(meta):
+    kw = dict(meta["kwargs"])
+    if kw.get("goal_xy", 0) is not None and "goal_xy" in kw:
+        kw["goal_xy"] = tuple(kw["goal_xy"])
+    return kw
+
+
+@pytest.mark.parametrize("name", golden_names("rooms"))
+def test_golden_trajectory_free_running(name):
+    """Fed the reference's recorded draws, the GPU env reproduces the reference trajectory exactly."""
+    from gym_po.envs import RoomsEnv
+    fx = load_golden(name)
+    meta = fx["meta"]
+    orc = make_oracle(meta, recorded_draws(fx))
+    env = RoomsEnv(meta["B"], device=DEV, rng_mode="replay", **_kw(meta))
+    orc.reset()
+    env.set_replay(**orc.draws)
+    obs = env.reset()
+    assert isinstance(obs, torch.Tensor)          # reset returns obs only (reference rooms.py:189)
+    np.testing.assert_array_equal(obs.cpu().numpy(), fx["obs0"])
+    for t in range(meta["T"]):
+        a = fx["actions"][t]
+        orc.step(a)
+        env.set_replay(**orc.draws)
+        g = env.step(torch.as_tensor(a, device=DEV))
+        _cmp(g[:4], (fx["obs"][t], fx["rew"][t], fx["term"][t], fx["trunc"][t]), t)
+    st = env.get_state()
+    np.testing.assert_array_equal(st["agent"].cpu().numpy(), fx["state_agent"])
+    np.testing.assert_array_equal(st["goal"].cpu().numpy(), fx["state_goal"])
+    np.testing.assert_array_equal(st["elapsed"].cpu().numpy(), fx["state_elapsed"])
+
+
+OBS_TYPES = ["room", "room_goal", "mdp", "mdp_goal", "vector_mdp", "vector_mdp_goal", "hansen", "hansen8", "vector_hansen",
+             "vector_hansen8", "vector_goal_hansen", "vector_goal_hansen8", "grid"]
+
+
+@pytest.mark.parametrize("obs_type", OBS_TYPES)
+@pytest.mark.parametrize("goal_xy", [(0, 0), None])
+def test_lockstep_all_obs_variants(obs_type, goal_xy):
+    """All 13 obs variants x fixed/random goal, ragged batch, short time limit (many resets)."""
+    from gym_po.envs import RoomsEnv
+    b = 3000
+    layout = "10b" if goal_xy is None else "4"
+    action_type = "cardinal" if obs_type in ("hansen", "vector_hansen", "mdp") else "ordinal"
+    kw = dict(layout=layout, obs_type=obs_type, obs_n=5, goal_xy=goal_xy, time_limit=23, action_type=action_type,
+              action_failure_probability=0.3, step_reward=-0.01, wall_reward=-0.2, goal_reward=2.0)
+    orc = oracle.RoomsOracle(b, draws=oracle.GeneratorDraws(seed=5), **kw)
+    env = RoomsEnv(b, device=DEV, rng_mode="replay", **kw)
+    o = orc.reset()
+    env.set_replay(**orc.draws)
+    np.testing.assert_array_equal(env.reset().cpu().numpy(), o)
+    rng = np.random.default_rng(3)
+    for t in range(150):
+        a = rng.integers(orc.n_actions, size=b)
+        o = orc.step(a)
+        env.set_replay(**orc.draws)
+        _cmp(env.step(torch.as_tensor(a, dtype=torch.int8, device=DEV))[:4], o[:4], t)
+    st = env.get_state()
+    np.testing.assert_array_equal(st["agent"].cpu().numpy(), orc.agent)
+    np.testing.assert_array_equal(st["goal"].cpu().numpy(), orc.goal)
+    np.testing.assert_array_equal(st["elapsed"].cpu().numpy(), orc.elapsed)
+
+
+@pytest.mark.parametrize("layout", list(oracle.LAYOUT_NAMES))
+@pytest.mark.parametrize("n", [3, 4, 9, 11])
+def test_grid_window_every_cell_every_layout(layout, n):
+    """Every walkable cell of all 12 layouts as agent position, random goals: window obs incl. map edges."""
+    from gym_po.envs import RoomsEnv
+    grid = oracle.load_layout(layout)
+    cells = np.stack(np.nonzero(grid >= 0), -1)
+    b = len(cells)
+    rng = np.random.default_rng(1)
+    goals = cells[rng.integers(b, size=b)]
+    kw = dict(layout=layout, obs_type="grid", obs_n=n, goal_xy=None)
+    orc = oracle.RoomsOracle(b, draws=oracle.GeneratorDraws(seed=2), **kw)
+    env = RoomsEnv(b, device=DEV, rng_mode="replay", **kw)
+    orc.reset()
+    env.set_replay(**orc.draws)
+    env.reset()
+    st = dict(agent=cells, goal=goals, elapsed=np.zeros(b, dtype=int))
+    orc.set_state(**st)
+    env.set_state(**st)
+    for a in range(8):
+        act = np.full(b, a)
+        o = orc.step(act)
+        env.set_replay(**orc.draws)
+        _cmp(env.step(torch.as_tensor(act, dtype=torch.int8, device=DEV))[:4], o[:4], a)
+
+
+@pytest.mark.parametrize("action_type,n_act", [("ordinal", 8), ("cardinal", 4)])
+def test_exhaustive_cell_x_slipped_action(action_type, n_act):
+    """Every cell x intended action x every slip outcome (u placed just inside each threshold band)."""
+    from gym_po.envs import RoomsEnv
+    for layout in ("4", "32b"):
+        grid = oracle.load_layout(layout)
+        cells = np.stack(np.nonzero(grid >= 0), -1)
+        P = oracle.rooms.slip_matrix(n_act, 0.2).cumsum(axis=1)
+        cases = [(c, a, j) for c in range(len(cells)) for a in range(n_act) for j in range(n_act)]
+        ci, ai, ji = (np.array(v) for v in zip(*cases))
+        lo = np.where(ji > 0, P[ai, np.maximum(ji - 1, 0)], 0.0)
+        u = np.nextafter(lo, 2.0)                       # smallest u with exactly j thresholds below it
+        u = np.where(ji == 0, 0.0, u)
+        b = len(cases)
+
+        class Fixed(oracle.GeneratorDraws):
+            def random(self, n):
+                return u.copy()
+
+        kw = dict(layout=layout, obs_type="hansen8", action_type=action_type, goal_xy=(0, 0))
+        orc = oracle.RoomsOracle(b, draws=Fixed(seed=0), **kw)
+        env = RoomsEnv(b, device=DEV, rng_mode="replay", **kw)
+        orc.reset(); env.set_replay(**orc.draws); env.reset()
+        st = dict(agent=cells[ci], goal=orc.goal, elapsed=np.zeros(b, dtype=int))
+        orc.set_state(**st); env.set_state(**st)
+        o = orc.step(ai)
+        env.set_replay(**orc.draws)
+        _cmp(env.step(torch.as_tensor(ai, dtype=torch.int8, device=DEV))[:4], o[:4], 0)
+        np.testing.assert_array_equal(env.agent_yx.cpu().numpy(), orc.agent)
+
+
+def test_philox_statistics_and_invariants_full_size():
+    """2^22 envs (BASELINE configs 3/4 per-GPU size): slip rate, wall collisions, goal hits, resets."""
+    from gym_po.envs import RoomsEnv
+    b = 1 << 22
+    env = RoomsEnv(b, "4", obs_type="hansen8", device=DEV, seed=3)
+    obs = env.reset(seed=3)
+    grid = torch.as_tensor(env.grid, device=DEV)
+    a0 = env.agent_yx
+    assert bool((grid[a0[:, 0], a0[:, 1]] >= 0).all())
+    # spawn is uniform over the 200 valid cells
+    cnt = torch.bincount(a0[:, 0] * 17 + a0[:, 1], minlength=289)[torch.as_tensor(env.valid_states, device=DEV)].cpu().numpy()
+    exp = b / 200
+    chi2 = float(((cnt - exp) ** 2 / exp).sum())
+    assert chi2 < 199 + 6 * np.sqrt(2 * 199), chi2
+    # slip: intended N from an open cell moves N w.p. 0.8, each other direction w.p. 0.2/7
+    st = dict(agent=np.tile([3, 3], (b, 1)), goal=None, elapsed=np.zeros(b, dtype=int))
+    env.set_state(**st)
+    env.step(torch.zeros(env.capacity, dtype=torch.int8, device=DEV))
+    d = (env.agent_yx - torch.tensor([3, 3], device=DEV))
+    key = ((d[:, 0] + 1) * 3 + (d[:, 1] + 1)).cpu().numpy()
+    frac = np.bincount(key, minlength=9) / b
+    assert abs(frac[1] - 0.8) < 2e-3                               # (-1,0) = N
+    for k in (0, 2, 3, 5, 6, 7, 8):
+        assert abs(frac[k] - 0.2 / 7) < 1e-3, (k, frac[k])
+    assert frac[4] == 0.0                                          # never stays in an open area
+    gen = torch.Generator(device=DEV).manual_seed(0)
+    for t in range(60):
+        a = torch.randint(0, 8, (env.capacity,), dtype=torch.int8, device=DEV, generator=gen)
+        prev = env.elapsed.clone()
+        obs, rew, term, trunc, _ = env.step(a)
+        ayx = env.agent_yx
+        assert bool((grid[ayx[:, 0], ayx[:, 1]] >= 0).all())       # never inside a wall
+        assert bool((rew[term] == 1.0).all()) and bool((rew[~term] == 0.0).all())
+        assert bool((env.elapsed[term | trunc] == 0).all())
+        assert bool((env.elapsed[~(term | trunc)] == prev[~(term | trunc)] + 1).all())
+        assert int(obs.min()) >= 0 and int(obs.max()) <= 2040
+
+
+def test_gpu_count_independence_and_host_path():
+    from gym_po.envs import RoomsEnv
+    b = 1 << 14
+    kw = dict(layout="8", obs_type="vector_goal_hansen8", goal_xy=None, time_limit=30)
+    whole = RoomsEnv(b, device=DEV, seed=11, **kw)
+    lo = RoomsEnv(b // 2, device=DEV, seed=11, env_offset=0, **kw)
+    hi = RoomsEnv(b // 2, device=DEV, seed=11, env_offset=b // 2, **kw)
+    host = RoomsEnv(b, device=DEV, seed=11, **kw)
+    for e in (whole, lo, hi, host):
+        e.reset(seed=11)
+    rng = np.random.default_rng(0)
+    for t in range(80):
+        a_np = rng.integers(8, size=b).astype(np.int8)
+        a = torch.as_tensor(a_np, device=DEV)
+        w = whole.step(a)
+        l = lo.step(a[: b // 2].contiguous())
+        h = hi.step(a[b // 2:].contiguous())
+        hp = host.step_host(a_np)
+        for k in range(4):
+            assert torch.equal(w[k][: b // 2], l[k]) and torch.equal(w[k][b // 2:], h[k]), (k, t)
+            np.testing.assert_array_equal(w[k].cpu().numpy(), hp[k])

@@ -54,7 +54,7 @@ def test_golden_trajectory_free_running(name):
     {"map": oracle.EXTENDED_TAXI_MAP, "hansen_obs": True, "time_limit": 11},
     {"num_passengers": 0, "time_limit": 5},
 ])
-@pytest.mark.parametrize("b", [1, 513, 70_000])
+@pytest.mark.parametrize("b", [1, 513, 20_000])
 def test_lockstep_vs_oracle(kwargs, b):
     """Ragged sizes (1, one-over-a-tile, many tiles), all maps, multi-passenger, mass truncation."""
     from gym_po.envs import TaxiVecEnv
@@ -84,12 +84,17 @@ def test_lockstep_vs_oracle(kwargs, b):
 
 @pytest.mark.parametrize("extended", [False, True])
 def test_exhaustive_transition_table(extended):
-    """Every (state, action): teacher-force the oracle state, one step, compare everything."""
+    """Every reachable (state, action): teacher-force the oracle state, one step, compare everything.
+    (States with the taxi standing ON a wall cell of the 8x8 map are unreachable — resets land on
+    non-wall cells and moves never enter walls — and are excluded.)"""
     from gym_po.envs import TaxiVecEnv
     kw = {"map": oracle.EXTENDED_TAXI_MAP} if extended else {}
     probe = oracle.TaxiOracle(1, **kw)
-    ns = probe.ns
-    states = np.repeat(np.arange(ns), 5)
+    all_s = np.arange(probe.ns)
+    r, c, _, _ = probe.decode(all_s)
+    all_s = all_s[probe.tgrid[r, c] != "|"]
+    ns = all_s.size
+    states = np.repeat(all_s, 5)
     actions = np.tile(np.arange(5), ns)
     b = states.size
     for hansen in (False, True):
