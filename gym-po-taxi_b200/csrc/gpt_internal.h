@@ -43,11 +43,13 @@ struct gpt_env {
   gpt::HostPath host;
 
   // ---- taxi ----
-  uint32_t taxi_cdf_off = 0, taxi_vs_off = 0, taxi_rep_shift = 0;
+  uint32_t taxi_cdf_off = 0, taxi_vs_off = 0, taxi_rep_shift = 0, taxi_trans_off = 0, taxi_hobs_off = 0;
+  bool taxi_use_table = false;
+  int taxi_shape = 0;  // launch-shape tuning knob (GPT_TAXI_SHAPE), 0 = default
   // ---- rooms / crooms ----
   struct RoomsLayout {
     uint32_t nb8_off = 0, yx_off = 0, room_off = 0, sid_off = 0, valid_off = 0, thr32_off = 0, thr64_off = 0,
-             rows_off = 0, dirs_off = 0;
+             rows_off = 0, grid_off = 0;
     int32_t n_valid = 0, n_rooms = 0, n_cells = 0;
   } rl;
   int32_t action_dtype = GPT_DT_I8, action_cols = 1;

@@ -78,6 +78,10 @@ int rooms_build_tables(gpt_env* env, const gpt_config* c, bool discrete_actions)
   env->rl.thr32_off = blob_append(blob, thr32);
   env->rl.thr64_off = blob_append(blob, thr64);
   env->rl.rows_off = blob_append(blob, rows);
+  if (!discrete_actions || c->family == GPT_FAMILY_CROOMS) {  // continuous env: wall test on floor(pos / cell)
+    std::vector<int8_t> grid(g, g + nc);
+    env->rl.grid_off = blob_append(blob, grid);
+  }
   return upload_blob(env, blob);
 }
 

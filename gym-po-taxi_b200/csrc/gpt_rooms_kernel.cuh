@@ -69,7 +69,108 @@ __device__ __forceinline__ uint32_t goal_dir(int y, int x, int gy, int gx) {
 }
 __device__ __forceinline__ uint32_t spread4(uint32_t bits4) { return (bits4 * 0x00204081u) & 0x01010101u; }
 
-enum : int { kObsWords1 = 1 };
+
+// what the observation functions need besides the tables
+struct ObsCtx {
+  int w, n_rooms, n_valid, hansen_n, gn;
+  FastDiv div_w;
+};
+
+// Observation of one env from its agent cell and goal cell (rooms.py:22-67, observations.py:44-131).
+// Scalar kinds return the value in `lo`; byte-vector kinds return up to 8 packed bytes in lo/hi; the
+// n x n window is written to `grid_dst` (n*n bytes in shared memory).
+template <int OBS, int GRID_N>
+__device__ __forceinline__ void cell_obs(const RoomsTables& T, const ObsCtx& C, uint32_t cell, uint32_t gcell,
+                                         uint8_t* grid_dst, uint32_t& lo, uint32_t& hi) {
+  if constexpr (OBS == GPT_OBS_ROOM) {
+    lo = T.room[cell];
+  } else if constexpr (OBS == GPT_OBS_ROOM_GOAL) {
+    lo = T.room[cell] + (uint32_t)C.n_rooms * T.room[gcell];
+  } else if constexpr (OBS == GPT_OBS_MDP) {
+    lo = T.sid[cell];
+  } else if constexpr (OBS == GPT_OBS_MDP_GOAL) {
+    lo = T.sid[cell] + (uint32_t)C.n_valid * T.sid[gcell];
+  } else {
+    const int y = (int)fdiv(cell, C.div_w), x = (int)cell - y * C.w;
+    const int gy = (int)fdiv(gcell, C.div_w), gx = (int)gcell - gy * C.w;
+    if constexpr (OBS == GPT_OBS_VEC_MDP) {
+      lo = (uint32_t)y | ((uint32_t)x << 8);
+    } else if constexpr (OBS == GPT_OBS_VEC_MDP_GOAL) {
+      lo = (uint32_t)y | ((uint32_t)x << 8) | ((uint32_t)gy << 16) | ((uint32_t)gx << 24);
+    } else if constexpr (OBS == GPT_OBS_HANSEN) {  // observations.py:44-71
+      const uint32_t nb = T.nb8[cell];
+      const uint32_t gd = goal_dir(y, x, gy, gx);
+      if (C.hansen_n == 8) {
+        lo = nb * (gd == 0xFu ? 1u : gd + 1u);
+      } else {
+        const uint32_t b4 = (nb & 1u) | ((nb >> 1) & 2u) | ((nb >> 2) & 4u) | ((nb >> 3) & 8u);
+        lo = b4 * ((gd != 0xFu && !(gd & 1u)) ? (gd >> 1) + 1u : 1u);
+      }
+    } else if constexpr (OBS == GPT_OBS_VEC_HANSEN || OBS == GPT_OBS_VEC_HANSEN_GOAL) {  // :106-131
+      const uint32_t nb = T.nb8[cell];
+      uint32_t gd = 0xFu;
+      if constexpr (OBS == GPT_OBS_VEC_HANSEN_GOAL) gd = goal_dir(y, x, gy, gx);
+      if (C.hansen_n == 8) {
+        lo = spread4(nb & 15u);
+        hi = spread4(nb >> 4);
+        if (gd < 4u) lo = (lo & ~(0xFFu << (8 * gd))) | (2u << (8 * gd));
+        else if (gd < 8u) hi = (hi & ~(0xFFu << (8 * (gd - 4)))) | (2u << (8 * (gd - 4)));
+      } else {
+        const uint32_t b4 = (nb & 1u) | ((nb >> 1) & 2u) | ((nb >> 2) & 4u) | ((nb >> 3) & 8u);
+        lo = spread4(b4);
+        if (gd != 0xFu && !(gd & 1u)) lo = (lo & ~(0xFFu << (4 * gd))) | (2u << (4 * gd));
+      }
+    } else if constexpr (OBS == GPT_OBS_GRID) {  // observations.py:74-103
+      const int gn = GRID_N > 0 ? GRID_N : C.gn;
+      const int off = gn >> 1;
+      const uint64_t mask = (1ull << gn) - 1ull;
+      if constexpr (GRID_N > 0) {
+#pragma unroll
+        for (int r = 0; r < GRID_N; ++r) {
+          const uint32_t bits = (uint32_t)((T.rows[y + r] >> x) & mask);
+#pragma unroll
+          for (int c = 0; c < GRID_N; ++c) grid_dst[r * GRID_N + c] = (uint8_t)((bits >> c) & 1u);
+        }
+      } else {  // run-time window size: rolled loops
+#pragma unroll 1
+        for (int r = 0; r < gn; ++r) {
+          const uint32_t bits = (uint32_t)((T.rows[y + r] >> x) & mask);
+#pragma unroll 1
+          for (int c = 0; c < gn; ++c) grid_dst[r * gn + c] = (uint8_t)((bits >> c) & 1u);
+        }
+      }
+      const int gr = gy - y + off, gc = gx - x + off;
+      if ((unsigned)gr < (unsigned)gn && (unsigned)gc < (unsigned)gn) grid_dst[gr * gn + gc] = 2;
+    }
+  }
+}
+
+// Stores the observations of one quad (4 consecutive envs starting at env index q).  For the window
+// obs the warp's 128 envs x n^2 bytes (contiguous in HBM) are streamed out of shared memory.
+template <int OBS>
+__device__ __forceinline__ void store_obs(void* obs, int64_t q, int64_t warp_quad_base, int hansen_n, int gn, uint32_t lane,
+                                          const uint8_t* stage, const uint32_t (&lo)[4], const uint32_t (&hi)[4]) {
+  if constexpr (OBS == GPT_OBS_VEC_MDP) {
+    st_stream(reinterpret_cast<uint2*>((uint8_t*)obs + q * 2), make_uint2(lo[0] | (lo[1] << 16), lo[2] | (lo[3] << 16)));
+  } else if constexpr (OBS == GPT_OBS_VEC_HANSEN || OBS == GPT_OBS_VEC_HANSEN_GOAL) {
+    if (hansen_n == 8) {
+      int4* o = reinterpret_cast<int4*>((uint8_t*)obs + q * 8);
+      st_stream(o, make_int4((int)lo[0], (int)hi[0], (int)lo[1], (int)hi[1]));
+      st_stream(o + 1, make_int4((int)lo[2], (int)hi[2], (int)lo[3], (int)hi[3]));
+    } else {
+      st_stream(reinterpret_cast<int4*>((uint8_t*)obs + q * 4), make_int4((int)lo[0], (int)lo[1], (int)lo[2], (int)lo[3]));
+    }
+  } else if constexpr (OBS == GPT_OBS_GRID) {
+    __syncwarp();
+    const uint32_t vecs = (uint32_t)(kQuadStride * gn * gn) >> 4;
+    const int4* src = reinterpret_cast<const int4*>(stage);
+    int4* dst = reinterpret_cast<int4*>((uint8_t*)obs + warp_quad_base * (gn * gn));
+    for (uint32_t i = lane; i < vecs; i += 32) st_stream(dst + i, src[i]);
+    __syncwarp();
+  } else {  // scalar int32 obs, or 4 packed bytes per env (VEC_MDP_GOAL)
+    st_stream(reinterpret_cast<int4*>((uint8_t*)obs + q * 4), make_int4((int)lo[0], (int)lo[1], (int)lo[2], (int)lo[3]));
+  }
+}
 
 template <int OBS, bool RGOAL, bool REPLAY, int GRID_N>
 __global__ void __launch_bounds__(OBS == GPT_OBS_GRID ? 128 : 256) rooms_step_kernel(const __grid_constant__ RoomsParams P) {
@@ -112,6 +213,8 @@ __global__ void __launch_bounds__(OBS == GPT_OBS_GRID ? 128 : 256) rooms_step_ke
   T.thr64 = reinterpret_cast<const double*>(smem + P.thr64_off);
   T.rows = reinterpret_cast<const uint64_t*>(smem + P.rows_off);
   const int gn = GRID_N > 0 ? GRID_N : P.grid_n;
+  ObsCtx OC;
+  OC.w = P.w; OC.n_rooms = P.n_rooms; OC.n_valid = P.n_valid; OC.hansen_n = P.hansen_n; OC.gn = gn; OC.div_w = P.div_w;
   uint8_t* stage = smem + P.stage_off + warp * (uint32_t)(kQuadStride * gn * gn);  // grid obs only
 
 #pragma unroll
@@ -180,67 +283,7 @@ __global__ void __launch_bounds__(OBS == GPT_OBS_GRID ? 128 : 256) rooms_step_ke
       goalv[k] = gcell;
 
       // ---- observation of the (post-reset) state ------------------------------------------
-      if constexpr (OBS == GPT_OBS_ROOM) {
-        o32[k] = T.room[cell];
-      } else if constexpr (OBS == GPT_OBS_ROOM_GOAL) {
-        o32[k] = T.room[cell] + (uint32_t)P.n_rooms * T.room[gcell];
-      } else if constexpr (OBS == GPT_OBS_MDP) {
-        o32[k] = T.sid[cell];
-      } else if constexpr (OBS == GPT_OBS_MDP_GOAL) {
-        o32[k] = T.sid[cell] + (uint32_t)P.n_valid * T.sid[gcell];
-      } else {
-        const int y = (int)fdiv(cell, P.div_w), x = (int)cell - y * P.w;
-        int gy = P.goal_y, gx = P.goal_x;
-        if (RGOAL) {
-          gy = (int)fdiv(gcell, P.div_w);
-          gx = (int)gcell - gy * P.w;
-        }
-        if constexpr (OBS == GPT_OBS_VEC_MDP) {
-          o32[k] = (uint32_t)y | ((uint32_t)x << 8);
-        } else if constexpr (OBS == GPT_OBS_VEC_MDP_GOAL) {
-          o32[k] = (uint32_t)y | ((uint32_t)x << 8) | ((uint32_t)gy << 16) | ((uint32_t)gx << 24);
-        } else if constexpr (OBS == GPT_OBS_HANSEN) {  // observations.py:44-71
-          const uint32_t nb = T.nb8[cell];
-          const uint32_t gd = goal_dir(y, x, gy, gx);
-          if (P.hansen_n == 8) {
-            o32[k] = nb * (gd == 0xFu ? 1u : gd + 1u);
-          } else {
-            const uint32_t b4 = (nb & 1u) | ((nb >> 1) & 2u) | ((nb >> 2) & 4u) | ((nb >> 3) & 8u);
-            o32[k] = b4 * ((gd != 0xFu && !(gd & 1u)) ? (gd >> 1) + 1u : 1u);
-          }
-        } else if constexpr (OBS == GPT_OBS_VEC_HANSEN || OBS == GPT_OBS_VEC_HANSEN_GOAL) {  // :106-131
-          const uint32_t nb = T.nb8[cell];
-          uint32_t gd = 0xFu;
-          if constexpr (OBS == GPT_OBS_VEC_HANSEN_GOAL) gd = goal_dir(y, x, gy, gx);
-          if (P.hansen_n == 8) {
-            uint32_t lo = spread4(nb & 15u), hi = spread4(nb >> 4);
-            if (gd < 4u) lo = (lo & ~(0xFFu << (8 * gd))) | (2u << (8 * gd));
-            else if (gd < 8u) hi = (hi & ~(0xFFu << (8 * (gd - 4)))) | (2u << (8 * (gd - 4)));
-            o32[k] = lo;
-            o32b[k] = hi;
-          } else {
-            const uint32_t b4 = (nb & 1u) | ((nb >> 1) & 2u) | ((nb >> 2) & 4u) | ((nb >> 3) & 8u);
-            uint32_t lo = spread4(b4);
-            if (gd != 0xFu && !(gd & 1u)) lo = (lo & ~(0xFFu << (4 * gd))) | (2u << (4 * gd));
-            o32[k] = lo;
-          }
-        } else if constexpr (OBS == GPT_OBS_GRID) {  // observations.py:74-103
-          const int off = gn >> 1;
-          uint8_t* dst = stage + (uint32_t)(lane * kQuad + k) * (uint32_t)(gn * gn);
-          const uint64_t mask = (1ull << gn) - 1ull;
-#pragma unroll
-          for (int r = 0; r < (GRID_N > 0 ? GRID_N : 15); ++r) {
-            if (r < gn) {
-              const uint32_t bits = (uint32_t)((T.rows[y + r] >> x) & mask);
-#pragma unroll
-              for (int c = 0; c < (GRID_N > 0 ? GRID_N : 15); ++c)
-                if (c < gn) dst[r * gn + c] = (uint8_t)((bits >> c) & 1u);
-            }
-          }
-          const int gr = gy - y + off, gc = gx - x + off;
-          if ((unsigned)gr < (unsigned)gn && (unsigned)gc < (unsigned)gn) dst[gr * gn + gc] = 2;
-        }
-      }
+      cell_obs<OBS, GRID_N>(T, OC, cell, gcell, stage + (uint32_t)(lane * kQuad + k) * (uint32_t)(gn * gn), o32[k], o32b[k]);
     }
 
     // ---- stores ------------------------------------------------------------------------------
@@ -252,27 +295,7 @@ __global__ void __launch_bounds__(OBS == GPT_OBS_GRID ? 128 : 256) rooms_step_ke
       st_stream(reinterpret_cast<uint32_t*>(P.terminated + q), tw);
       st_stream(reinterpret_cast<uint32_t*>(P.truncated + q), trw);
     }
-    if constexpr (OBS == GPT_OBS_VEC_MDP) {
-      st_stream(reinterpret_cast<uint2*>((uint8_t*)P.obs + q * 2), make_uint2(o32[0] | (o32[1] << 16), o32[2] | (o32[3] << 16)));
-    } else if constexpr (OBS == GPT_OBS_VEC_HANSEN || OBS == GPT_OBS_VEC_HANSEN_GOAL) {
-      if (P.hansen_n == 8) {
-        int4* o = reinterpret_cast<int4*>((uint8_t*)P.obs + q * 8);
-        st_stream(o, make_int4((int)o32[0], (int)o32b[0], (int)o32[1], (int)o32b[1]));
-        st_stream(o + 1, make_int4((int)o32[2], (int)o32b[2], (int)o32[3], (int)o32b[3]));
-      } else {
-        st_stream(reinterpret_cast<int4*>((uint8_t*)P.obs + q * 4), make_int4((int)o32[0], (int)o32[1], (int)o32[2], (int)o32[3]));
-      }
-    } else if constexpr (OBS == GPT_OBS_GRID) {
-      // the warp's 128 envs x n^2 bytes are contiguous in HBM: stream them out with 16-byte stores
-      __syncwarp();
-      const uint32_t vecs = (uint32_t)(kQuadStride * gn * gn) >> 4;
-      const int4* src = reinterpret_cast<const int4*>(stage);
-      int4* dst = reinterpret_cast<int4*>((uint8_t*)P.obs + ((int64_t)tile * kTileEnvs + j * kQuadStride) * (gn * gn));
-      for (uint32_t i = lane; i < vecs; i += 32) st_stream(dst + i, src[i]);
-      __syncwarp();
-    } else {  // scalar int32 obs, or 4 packed bytes per env (VEC_MDP_GOAL)
-      st_stream(reinterpret_cast<int4*>((uint8_t*)P.obs + q * 4), make_int4((int)o32[0], (int)o32[1], (int)o32[2], (int)o32[3]));
-    }
+    store_obs<OBS>(P.obs, q, (int64_t)tile * kTileEnvs + j * kQuadStride, P.hansen_n, gn, lane, stage, o32, o32b);
   }
 }
 

@@ -11,13 +11,24 @@
 // consecutive envs at tile + j*128 + 4*l (j = 0..3), so every warp-wide access is one fully used
 // 512 B (int32/float32 streams) or 128 B (byte streams) contiguous segment.
 //
-// Static tables (<= 8 KB) are packed on the host into one blob and staged into shared memory by
+// Two kernels implement the same step:
+//   * taxi_table_kernel (used when ns <= 8192, i.e. both reference maps): the complete (state, action) ->
+//     (next state, delivered?, illegal?) relation is tabulated on the host (ns x 6 uint16, 6 KB for the
+//     5x5 map) and lives in shared memory, so the per-env main path is ONE data-dependent LDS plus ~20
+//     ALU instructions.  The rare branches (autoreset ~0.5 % of env-steps, passenger respawn) are NOT in
+//     the unrolled main path: a thread records them in a 32-bit mask and patches the affected envs with
+//     scalar stores in a compact loop after its vector stores.
+//   * taxi_arith_kernel: decode / wall-bit move / pickup-dropoff arithmetic, any map with ns < 65536.
+//
+// Static tables are packed on the host into one blob and staged into shared memory by
 // one TMA bulk copy per CTA:
 //     celltab uint16[cells x REP]: bits 0-3 = wall bits N,S,W,E around the cell (1 = blocked; this is
 //         hansen_encodings, extended_taxi.py:102-114, which also decides motion — SURVEY.md A.1),
 //         bits 8-15 = index of the named location on that cell (0xFF none).  Replicated per lane
 //         (REP = 32) when small so that the data-dependent lookups are bank-conflict free.
 //     reset_cdf uint32[n_valid], valid_states uint16[n_valid]: Philox-mode autoreset sampler.
+#include <cstdlib>
+
 #include "gpt_internal.h"
 
 namespace gpt {
@@ -36,6 +47,8 @@ struct TaxiParams {
   const int8_t* rp_new_d;
   const uint8_t* blob;
   uint32_t blob_bytes, cdf_off, vs_off, rep_shift;
+  uint32_t trans_off, hobs_off;   // table kernel: transition table / hansen obs table offsets in the blob
+  FastDiv div_pd;                 // divide by (nlocs+1)*nlocs
   int64_t env_offset;
   int32_t first_tile, n_tiles;
   int32_t cols, nlocs, n_dropoffs, time_limit, n_valid, mode;
@@ -129,7 +142,7 @@ __device__ __forceinline__ void taxi_env(const TaxiParams& P, const TaxiTables& 
 }
 
 template <bool HANSEN, bool REPLAY>
-__global__ void __launch_bounds__(256) taxi_step_kernel(const __grid_constant__ TaxiParams P) {
+__global__ void __launch_bounds__(256) taxi_arith_kernel(const __grid_constant__ TaxiParams P) {
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ uint64_t bar;
   stage_tables_begin(smem, P.blob, P.blob_bytes, &bar);
@@ -194,6 +207,138 @@ __global__ void __launch_bounds__(256) taxi_step_kernel(const __grid_constant__ 
   }
 }
 
+
+// ------------------------------------------------------------------------------------------
+// table-driven kernel
+// ------------------------------------------------------------------------------------------
+constexpr uint32_t kTransState = 0x1FFFu, kTransGoal = 1u << 13, kTransBad = 1u << 14;
+constexpr int kTransCols = 6;  // actions 0..4 + "no-op" column for out-of-range action bytes
+
+template <bool HANSEN, bool REPLAY, int QPT, int THREADS>
+__global__ void __launch_bounds__(THREADS) taxi_table_kernel(const __grid_constant__ TaxiParams P) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  __shared__ uint64_t bar;
+  stage_tables_begin(smem, P.blob, P.blob_bytes, &bar);
+
+  constexpr int kEnvsPerWarp = kWarp * kQuad * QPT;
+  const uint32_t lane = threadIdx.x & 31u;
+  const int64_t wtile = (int64_t)blockIdx.x * (THREADS / 32) + (threadIdx.x >> 5);
+  const int64_t first = (int64_t)P.first_tile * kTileEnvs, last = first + (int64_t)P.n_tiles * kTileEnvs;
+  const int64_t base = first + wtile * kEnvsPerWarp + lane * kQuad;
+  if (base >= last) return;
+  const bool reset_all = P.mode == kModeReset;
+
+  int4 s4[QPT], e4[QPT];
+  uint32_t nd4[QPT], a4[QPT];
+#pragma unroll
+  for (int j = 0; j < QPT; ++j) {
+    const int64_t q = base + j * kQuadStride;
+    if (!reset_all) {
+      s4[j] = ld_stream(reinterpret_cast<const int4*>(P.s + q));
+      e4[j] = ld_stream(reinterpret_cast<const int4*>(P.elapsed + q));
+      nd4[j] = ld_stream(reinterpret_cast<const uint32_t*>(P.ndrop + q));
+      a4[j] = ld_stream(reinterpret_cast<const uint32_t*>(P.actions + q));
+    } else {
+      s4[j] = e4[j] = make_int4(0, 0, 0, 0);
+      nd4[j] = a4[j] = 0u;
+    }
+  }
+
+  stage_tables_wait(&bar);
+  const uint16_t* trans = reinterpret_cast<const uint16_t*>(smem + P.trans_off);
+  const uint16_t* hobs = reinterpret_cast<const uint16_t*>(smem + P.hobs_off);
+  const uint32_t* cdf = reinterpret_cast<const uint32_t*>(smem + P.cdf_off);
+  const uint16_t* valid = reinterpret_cast<const uint16_t*>(smem + P.vs_off);
+
+  uint32_t reset_mask = reset_all ? 0xFFFFFFFFu >> (32 - 4 * QPT) : 0u;  // bit 4j+k: env needs a full reset
+  uint32_t respawn_mask = 0u;                                             // bit 4j+k: new passenger + destination
+  int32_t keep_s[4 * QPT];                                                // post-move states (respawn needs the taxi cell)
+
+#pragma unroll
+  for (int j = 0; j < QPT; ++j) {
+    const int64_t q = base + j * kQuadStride;
+    int32_t sv[4] = {s4[j].x, s4[j].y, s4[j].z, s4[j].w};
+    int32_t ev[4] = {e4[j].x, e4[j].y, e4[j].z, e4[j].w};
+    int32_t ov[4];
+    float rv[4];
+    uint32_t ndw = 0, tw = 0, trw = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (!reset_all) {
+        const uint32_t a = min((a4[j] >> (8 * k)) & 0xFFu, (uint32_t)(kTransCols - 1));
+        const uint32_t ent = trans[(uint32_t)sv[k] * kTransCols + a];
+        const uint32_t goal = (ent >> 13) & 1u;
+        const uint32_t nd = ((nd4[j] >> (8 * k)) & 0xFFu) + goal;
+        sv[k] = (int32_t)(ent & kTransState);
+        ev[k] += 1;
+        rv[k] = goal ? P.r_goal : ((ent & kTransBad) ? P.r_bad : P.r_any);
+        const uint32_t term = nd == (uint32_t)P.n_dropoffs;
+        const uint32_t trunc = ev[k] > P.time_limit;
+        const uint32_t done = term | trunc;
+        reset_mask |= done << (4 * j + k);
+        respawn_mask |= (goal & ~done & 1u) << (4 * j + k);
+        ndw |= (nd & 0xFFu) << (8 * k);
+        tw |= term << (8 * k);
+        trw |= trunc << (8 * k);
+      }
+      ov[k] = HANSEN ? (int32_t)hobs[sv[k]] : sv[k];
+      keep_s[4 * j + k] = sv[k];
+    }
+    st_stream(reinterpret_cast<int4*>(P.s + q), make_int4(sv[0], sv[1], sv[2], sv[3]));
+    st_stream(reinterpret_cast<int4*>(P.elapsed + q), make_int4(ev[0], ev[1], ev[2], ev[3]));
+    st_stream(reinterpret_cast<uint32_t*>(P.ndrop + q), ndw);
+    st_stream(reinterpret_cast<int4*>(P.obs + q), make_int4(ov[0], ov[1], ov[2], ov[3]));
+    if (!reset_all) {
+      st_stream(reinterpret_cast<float4*>(P.reward + q), make_float4(rv[0], rv[1], rv[2], rv[3]));
+      st_stream(reinterpret_cast<uint32_t*>(P.terminated + q), tw);
+      st_stream(reinterpret_cast<uint32_t*>(P.truncated + q), trw);
+    }
+  }
+
+  // ---- rare branches: patch the affected envs (same thread, later stores to the same addresses win)
+  uint32_t todo = reset_mask | respawn_mask;
+#pragma unroll 1
+  while (todo) {
+    const int b = __ffs(todo) - 1;
+    todo &= todo - 1;
+    const int64_t env = base + (b >> 2) * kQuadStride + (b & 3);
+    uint4 rnd = make_uint4(0, 0, 0, 0);
+    if (!REPLAY) rnd = env_random(P.rng, (uint64_t)(P.env_offset + env), 0u);
+    uint32_t fresh;
+    if ((reset_mask >> b) & 1u) {  // _reset_mask (extended_taxi.py:344-352)
+      if (REPLAY) {
+        fresh = (uint32_t)P.rp_reset_state[env];
+      } else {  // inverse CDF of the law of argmax(multinomial(ns, uniform over valid states))
+        int lo = 0, hi = P.n_valid - 1;
+        while (lo < hi) {
+          const int mid = (lo + hi) >> 1;
+          if (rnd.x <= cdf[mid]) hi = mid; else lo = mid + 1;
+        }
+        fresh = valid[lo];
+      }
+      P.elapsed[env] = 0;
+      P.ndrop[env] = 0;
+    } else {  // _reset_passenger_and_destination (:354-364): taxi cell kept, p uniform, d uniform over the others
+      int32_t cur = 0;
+#pragma unroll
+      for (int i = 0; i < 4 * QPT; ++i) cur = i == b ? keep_s[i] : cur;
+      const uint32_t cell = fdiv((uint32_t)cur, P.div_pd);
+      uint32_t p, d;
+      if (REPLAY) {
+        p = (uint32_t)P.rp_new_p[env];
+        d = (uint32_t)P.rp_new_d[env];
+      } else {
+        p = bounded(rnd.y, (uint32_t)P.nlocs);
+        d = bounded(rnd.z, (uint32_t)P.nlocs - 1);
+        d += d >= p ? 1u : 0u;
+      }
+      fresh = (cell * (uint32_t)(P.nlocs + 1) + p) * (uint32_t)P.nlocs + d;
+    }
+    P.s[env] = (int32_t)fresh;
+    P.obs[env] = HANSEN ? (int32_t)hobs[fresh] : (int32_t)fresh;
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------
@@ -208,6 +353,7 @@ int taxi_create(gpt_env* env, const gpt_config* c) {
     return fail(GPT_E_ARG, "taxi: wall_bits / loc_cell / valid_states missing");
   if (c->rng_mode == GPT_RNG_PHILOX && !c->taxi_reset_cdf) return fail(GPT_E_ARG, "taxi: reset_cdf required in Philox mode");
 
+  if (const char* shape = getenv("GPT_TAXI_SHAPE")) env->taxi_shape = atoi(shape);
   const uint32_t rep = cells <= 256 ? 32u : 1u;
   env->taxi_rep_shift = rep == 32u ? 5u : 0u;
   std::vector<uint16_t> celltab((size_t)cells * rep);
@@ -228,7 +374,38 @@ int taxi_create(gpt_env* env, const gpt_config* c) {
   }
   cdf.back() = 0xFFFFFFFFu;
   std::vector<uint8_t> blob;
-  blob_append(blob, celltab);
+  env->taxi_use_table = ns <= (int64_t)kTransState + 1;
+  if (env->taxi_use_table) {
+    // tabulate the whole step relation with the same rule the arithmetic kernel applies per env
+    const int nl = c->taxi_nlocs, cols = c->taxi_cols;
+    std::vector<uint16_t> trans((size_t)ns * kTransCols), hobs((size_t)ns);
+    for (int64_t st = 0; st < ns; ++st) {
+      const int d0 = (int)(st % nl), p0 = (int)((st / nl) % (nl + 1)), cell0 = (int)(st / nl / (nl + 1));
+      hobs[st] = (uint16_t)((((celltab[(size_t)cell0 * rep] & 15) * (nl + 1)) + p0) * nl + d0);
+      for (int a = 0; a < kTransCols; ++a) {
+        int cell = cell0, p = p0;
+        uint16_t ent = celltab[(size_t)cell * rep];
+        if (a < 4 && !((ent >> a) & 1)) {
+          const int step = (a & 2) ? 1 : cols;
+          const int to = cell + ((a & 1) ? step : -step);
+          if (to >= 0 && to < cells) cell = to;   // only unreachable wall-cell states can point outside
+          ent = celltab[(size_t)cell * rep];
+        }
+        const int here = ent >> 8;
+        const bool act = a == 4;
+        const bool goal = act && p == nl && here == d0;
+        const bool pickup = act && p < nl && here == p;
+        if (pickup) p = nl;
+        const bool bad = act && !goal && !pickup;
+        const int64_t s2 = ((int64_t)cell * (nl + 1) + p) * nl + d0;
+        trans[(size_t)st * kTransCols + a] = (uint16_t)(s2 | (goal ? kTransGoal : 0u) | (bad ? kTransBad : 0u));
+      }
+    }
+    env->taxi_trans_off = blob_append(blob, trans);
+    env->taxi_hobs_off = blob_append(blob, hobs);
+  } else {
+    blob_append(blob, celltab);
+  }
   env->taxi_cdf_off = blob_append(blob, cdf);
   env->taxi_vs_off = blob_append(blob, valid);
   if (int rc = upload_blob(env, blob)) return rc;
@@ -295,13 +472,38 @@ int taxi_launch(gpt_env* env, const LaunchArgs& a) {
   P.r_any = c.taxi_reward_any;
   P.rng = make_rng_key(env);
 
-  const int threads = 256, warps = threads / 32;
-  const int grid = (a.n_tiles + warps - 1) / warps;
-  if (grid <= 0) return GPT_OK;
+  P.trans_off = env->taxi_trans_off;
+  P.hobs_off = env->taxi_hobs_off;
+  P.div_pd = make_fastdiv((uint32_t)(c.taxi_nlocs + 1) * (uint32_t)c.taxi_nlocs);
+  if (a.n_tiles <= 0) return GPT_OK;
   const size_t smem = env->blob_bytes;
   using K = void (*)(const TaxiParams);
-  K k = c.taxi_hansen_obs ? (replay ? (K)taxi_step_kernel<true, true> : (K)taxi_step_kernel<true, false>)
-                          : (replay ? (K)taxi_step_kernel<false, true> : (K)taxi_step_kernel<false, false>);
+  K k;
+  int threads, grid;
+  const bool hansen = c.taxi_hansen_obs != 0;
+  if (env->taxi_use_table) {
+    // launch shape: GPT_TAXI_SHAPE = "<quads per thread>x<threads>" (tuning knob; default 4x128)
+    const int shape = env->taxi_shape;
+#define GPT_TAXI_PICK(Q, T)                                                                                      \
+  (hansen ? (replay ? (K)taxi_table_kernel<true, true, Q, T> : (K)taxi_table_kernel<true, false, Q, T>)            \
+          : (replay ? (K)taxi_table_kernel<false, true, Q, T> : (K)taxi_table_kernel<false, false, Q, T>))
+    int qpt;
+    switch (shape) {
+      case 2128: k = GPT_TAXI_PICK(2, 128); qpt = 2; threads = 128; break;
+      case 2256: k = GPT_TAXI_PICK(2, 256); qpt = 2; threads = 256; break;
+      case 4256: k = GPT_TAXI_PICK(4, 256); qpt = 4; threads = 256; break;
+      case 1256: k = GPT_TAXI_PICK(1, 256); qpt = 1; threads = 256; break;
+      default: k = GPT_TAXI_PICK(4, 128); qpt = 4; threads = 128; break;
+    }
+#undef GPT_TAXI_PICK
+    const int64_t envs_per_cta = (int64_t)threads * kQuad * qpt;
+    grid = (int)(((int64_t)a.n_tiles * kTileEnvs + envs_per_cta - 1) / envs_per_cta);
+  } else {
+    threads = 256;
+    grid = (a.n_tiles + 7) / 8;
+    k = hansen ? (replay ? (K)taxi_arith_kernel<true, true> : (K)taxi_arith_kernel<true, false>)
+               : (replay ? (K)taxi_arith_kernel<false, true> : (K)taxi_arith_kernel<false, false>);
+  }
   if (smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute((const void*)k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(taxi)");
@@ -309,7 +511,7 @@ int taxi_launch(gpt_env* env, const LaunchArgs& a) {
   k<<<grid, threads, smem, a.stream>>>(P);
   env->launches += 1;
   cudaError_t e = cudaGetLastError();
-  if (e != cudaSuccess) return cuda_fail(e, "taxi_step_kernel launch");
+  if (e != cudaSuccess) return cuda_fail(e, "taxi step kernel launch");
   return GPT_OK;
 }
 

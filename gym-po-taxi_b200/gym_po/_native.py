@@ -42,7 +42,7 @@ class GptConfig(C.Structure):
         ("rooms_step_reward", C.c_float), ("rooms_wall_reward", C.c_float), ("rooms_goal_reward", C.c_float),
         # continuous
         ("c_cell_size", C.c_double), ("c_action_std", C.c_double), ("c_action_power", C.c_double),
-        ("c_goal_threshold", C.c_double), ("c_use_velocity", C.c_int32), ("c_reserved", C.c_int32),
+        ("c_goal_threshold", C.c_double), ("c_use_velocity", C.c_int32), ("c_action_f64", C.c_int32),
     ]
 
 

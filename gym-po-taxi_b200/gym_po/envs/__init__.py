@@ -1,6 +1,7 @@
 from .extended_taxi import (TaxiVecEnv, HansenTaxiVecEnv, ExtendedHansenTaxiVecEnv, EXTENDED_TAXI_MAP,  # noqa: F401
                             ExtendedTaxiVecEnv, TAXI_MAP)
-from .rooms import RoomsEnv  # noqa: F401
+from .rooms import RoomsEnv, CRoomsEnv  # noqa: F401
+from .tag import TagVecEnv  # noqa: F401
 
-__all__ = ["RoomsEnv", "TaxiVecEnv", "HansenTaxiVecEnv", "ExtendedHansenTaxiVecEnv", "ExtendedTaxiVecEnv", "EXTENDED_TAXI_MAP",
+__all__ = ["RoomsEnv", "CRoomsEnv", "TagVecEnv", "TaxiVecEnv", "HansenTaxiVecEnv", "ExtendedHansenTaxiVecEnv", "ExtendedTaxiVecEnv", "EXTENDED_TAXI_MAP",
            "TAXI_MAP"]

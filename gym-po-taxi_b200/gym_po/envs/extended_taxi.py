@@ -174,6 +174,13 @@ class TaxiVecEnv(DeviceVecEnv):
         self.na = 5
         cells = self.rows * self.cols
         self.ns = cells * (self.nlocs + 1) * self.nlocs
+        # limits of the packed device tables (checked before any table is built)
+        if self.nlocs < 2:
+            raise ValueError("the map needs at least two pickup/dropoff locations")
+        if self.ns >= 65536 or self.nlocs > 254:
+            raise ValueError(f"state space too large for the device tables: rows*cols*(nlocs+1)*nlocs = {self.ns} >= 65536")
+        if not 0 <= int(num_passengers) <= 255:
+            raise ValueError("num_passengers must be in [0, 255]")
         self.no = (16 if self.hansen else cells) * (self.nlocs + 1) * self.nlocs
         self.single_observation_space = Discrete(self.no)
         self.observation_space = batch_space(self.single_observation_space, self.num_envs)

@@ -1,1 +1,2 @@
+from .crooms import CRoomsEnv  # noqa: F401
 from .rooms import RoomsEnv  # noqa: F401

@@ -131,7 +131,7 @@ typedef struct gpt_config {
   /* ---- CROOMS / TAG (continuous) ---- */
   double c_cell_size, c_action_std, c_action_power, c_goal_threshold;
   int32_t c_use_velocity;
-  int32_t c_reserved;
+  int32_t c_action_f64; /* continuous (yx) actions are float32 [B,2] (0) or float64 [B,2] (1) */
 } gpt_config;
 
 typedef struct gpt_array_desc {

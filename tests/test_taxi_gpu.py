@@ -197,7 +197,7 @@ def test_boundary_dlpack_and_errors():
     env.step(torch.zeros(1024, dtype=torch.int64, device=DEV))
     env.step(np.zeros(1024, dtype=np.int64))
     with pytest.raises(ValueError):
-        TaxiVecEnv(8, map=("AB",) * 200 + ("CD",) * 200, device=DEV)   # state space too large for the packed tables
+        TaxiVecEnv(8, map=("A" + " " * 58 + "B",) + (" " * 60,) * 58 + ("C" + " " * 57 + "DE",), device=DEV)  # ns = 108000
 
 
 def test_host_path_matches_device_path():
