@@ -118,4 +118,28 @@ __device__ __forceinline__ void stage_tables_begin(void* smem_dst, const void* g
 }
 __device__ __forceinline__ void stage_tables_wait(uint64_t* bar) { mbar_wait(bar, 0); }
 
+// ------------------------------------------------------------------------------------------
+// episode statistics: per-thread partial sums -> warp shuffle reduce -> one atomicAdd per warp and field
+// stats[0] episodes, [1] sum of returns, [2] sum of lengths, [3] sum of squared returns, [4] env-steps
+// ------------------------------------------------------------------------------------------
+struct EpisodeAcc {
+  float episodes = 0.f, ret = 0.f, len = 0.f, ret2 = 0.f, steps = 0.f;
+  __device__ __forceinline__ void finish(float episode_return, int episode_length) {
+    episodes += 1.f;
+    ret += episode_return;
+    len += (float)episode_length;
+    ret2 += episode_return * episode_return;
+  }
+  __device__ __forceinline__ void flush(double* stats) {
+    float v[5] = {episodes, ret, len, ret2, steps};
+#pragma unroll
+    for (int i = 0; i < 5; ++i) {
+      double d = (double)v[i];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) d += __shfl_xor_sync(0xFFFFFFFFu, d, o);
+      if ((threadIdx.x & 31u) == 0 && d != 0.0) atomicAdd(stats + i, d);
+    }
+  }
+};
+
 }  // namespace gpt

@@ -85,6 +85,7 @@ __global__ void __launch_bounds__(128) crooms_step_kernel(const __grid_constant_
   const int gn = P.grid_n;
   ObsCtx OC;
   OC.w = P.w; OC.n_rooms = P.n_rooms; OC.n_valid = P.n_valid; OC.hansen_n = P.hansen_n; OC.gn = gn; OC.div_w = P.div_w;
+  OC.fixed_goal = 0; OC.gy = 0; OC.gx = 0;   // goal cell always derived from the goal position
   uint8_t* stage = smem + P.stage_off + warp * (uint32_t)(kQuadStride * gn * gn);
 
   float rv[4] = {0.f, 0.f, 0.f, 0.f};
@@ -371,6 +372,9 @@ int crooms_create(gpt_env* env, const gpt_config* c) {
     return fail(GPT_E_ARG, "crooms: hansen obs_n must be 4 or 8");
   if (int rc = rooms_build_tables(env, c, c->rooms_n_actions > 0)) return rc;
   const bool rgoal = c->rooms_goal_y < 0;
+  if (!rgoal && (c->rooms_goal_y >= c->rooms_h || c->rooms_goal_x >= c->rooms_w || c->rooms_goal_x < 0) &&
+      (kind == GPT_OBS_ROOM_GOAL || kind == GPT_OBS_MDP_GOAL))
+    return fail(GPT_E_ARG, "crooms: goal-indexed observations need the fixed goal inside the grid");
   const int ak = action_kind(c);
   add_array(env, "agent", GPT_ROLE_STATE, GPT_DT_F64, 2);
   if (rgoal) add_array(env, "goal", GPT_ROLE_STATE, GPT_DT_F64, 2);
@@ -499,7 +503,7 @@ int crooms_launch(gpt_env* env, const LaunchArgs& a) {
     case GPT_OBS_GRID: k = pick_c<GPT_OBS_GRID>(replay); break;
   }
   if (!k) return fail(GPT_E_ARG, "crooms: no kernel for this obs kind");
-  if (smem > 48 * 1024) {
+  if (smem > 40 * 1024) {  // static + dynamic shared memory above 48 KB needs the opt-in
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(crooms)");
   }

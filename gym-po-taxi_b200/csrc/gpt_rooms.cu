@@ -105,9 +105,12 @@ int rooms_create(gpt_env* env, const gpt_config* c) {
   if (int rc = rooms_build_tables(env, c, true)) return rc;
   const bool rgoal = c->rooms_goal_y < 0;
   if (!rgoal) {
-    if (c->rooms_goal_y >= c->rooms_h || c->rooms_goal_x < 0 || c->rooms_goal_x >= c->rooms_w ||
-        c->rooms_grid[c->rooms_goal_y * c->rooms_w + c->rooms_goal_x] < 0)
-      return fail(GPT_E_ARG, "rooms: fixed goal must be a walkable cell");
+    // A fixed goal outside the grid is legal and simply unreachable: the reference's default goal for
+    // layouts '32'/'32b' is ENDS = (x 47, y 32) on a 25 x 49 grid (layouts.py:197-205, rooms.py:153-158).
+    const bool inside = c->rooms_goal_y < c->rooms_h && c->rooms_goal_x >= 0 && c->rooms_goal_x < c->rooms_w;
+    if (!inside && (c->rooms_obs_kind == GPT_OBS_ROOM_GOAL || c->rooms_obs_kind == GPT_OBS_MDP_GOAL))
+      return fail(GPT_E_ARG, "rooms: goal-indexed observations need the fixed goal inside the grid");
+    if (c->rooms_goal_y > 255 || c->rooms_goal_x > 255 || c->rooms_goal_x < 0) return fail(GPT_E_ARG, "rooms: fixed goal out of range");
   }
   int odt, ocols;
   if (int rc = obs_desc(c, &odt, &ocols)) return rc;
@@ -193,7 +196,8 @@ int rooms_launch(gpt_env* env, const LaunchArgs& a) {
   P.grid_n = grid ? c.rooms_obs_n : 0;
   P.goal_y = rgoal ? 0 : c.rooms_goal_y;
   P.goal_x = rgoal ? 0 : c.rooms_goal_x;
-  P.goal_cell = rgoal ? 0 : c.rooms_goal_y * c.rooms_w + c.rooms_goal_x;
+  const bool goal_inside = !rgoal && c.rooms_goal_y < c.rooms_h && c.rooms_goal_x < c.rooms_w;
+  P.goal_cell = goal_inside ? c.rooms_goal_y * c.rooms_w + c.rooms_goal_x : 0xFFFF;  // 0xFFFF never equals a cell
   P.div_w = make_fastdiv((uint32_t)c.rooms_w);
   P.r_step = c.rooms_step_reward;
   P.r_wall = c.rooms_wall_reward;
@@ -207,7 +211,7 @@ int rooms_launch(gpt_env* env, const LaunchArgs& a) {
   if (grid) smem = P.stage_off + (size_t)warps * kQuadStride * P.grid_n * P.grid_n;
   void* k = pick_kernel(c.rooms_obs_kind, P.grid_n, rgoal, replay);
   if (!k) return fail(GPT_E_ARG, "rooms: no kernel for this obs kind");
-  if (smem > 48 * 1024) {
+  if (smem > 40 * 1024) {  // static + dynamic shared memory above 48 KB needs the opt-in
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(rooms)");
   }

@@ -73,6 +73,7 @@ __device__ __forceinline__ uint32_t spread4(uint32_t bits4) { return (bits4 * 0x
 // what the observation functions need besides the tables
 struct ObsCtx {
   int w, n_rooms, n_valid, hansen_n, gn;
+  int fixed_goal, gy, gx;   // fixed goal: its (y, x) — may lie outside the grid (unreachable goal)
   FastDiv div_w;
 };
 
@@ -92,7 +93,11 @@ __device__ __forceinline__ void cell_obs(const RoomsTables& T, const ObsCtx& C, 
     lo = T.sid[cell] + (uint32_t)C.n_valid * T.sid[gcell];
   } else {
     const int y = (int)fdiv(cell, C.div_w), x = (int)cell - y * C.w;
-    const int gy = (int)fdiv(gcell, C.div_w), gx = (int)gcell - gy * C.w;
+    int gy = C.gy, gx = C.gx;
+    if (!C.fixed_goal) {
+      gy = (int)fdiv(gcell, C.div_w);
+      gx = (int)gcell - gy * C.w;
+    }
     if constexpr (OBS == GPT_OBS_VEC_MDP) {
       lo = (uint32_t)y | ((uint32_t)x << 8);
     } else if constexpr (OBS == GPT_OBS_VEC_MDP_GOAL) {
@@ -215,6 +220,7 @@ __global__ void __launch_bounds__(OBS == GPT_OBS_GRID ? 128 : 256) rooms_step_ke
   const int gn = GRID_N > 0 ? GRID_N : P.grid_n;
   ObsCtx OC;
   OC.w = P.w; OC.n_rooms = P.n_rooms; OC.n_valid = P.n_valid; OC.hansen_n = P.hansen_n; OC.gn = gn; OC.div_w = P.div_w;
+  OC.fixed_goal = !RGOAL; OC.gy = P.goal_y; OC.gx = P.goal_x;
   uint8_t* stage = smem + P.stage_off + warp * (uint32_t)(kQuadStride * gn * gn);  // grid obs only
 
 #pragma unroll

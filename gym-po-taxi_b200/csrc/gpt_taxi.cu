@@ -42,6 +42,9 @@ struct TaxiParams {
   float* reward;
   uint8_t* terminated;
   uint8_t* truncated;
+  float* ep_return;   // running return per env (track_stats only, else NULL)
+  double* stats;      // device float64[8] (track_stats only, else NULL)
+  int64_t num_envs;   // rows >= num_envs are padding: excluded from the statistics
   const int32_t* rp_reset_state;
   const int8_t* rp_new_p;
   const int8_t* rp_new_d;
@@ -214,7 +217,7 @@ __global__ void __launch_bounds__(256) taxi_arith_kernel(const __grid_constant__
 constexpr uint32_t kTransState = 0x1FFFu, kTransGoal = 1u << 13, kTransBad = 1u << 14;
 constexpr int kTransCols = 6;  // actions 0..4 + "no-op" column for out-of-range action bytes
 
-template <bool HANSEN, bool REPLAY, int QPT, int THREADS>
+template <bool HANSEN, bool REPLAY, bool STATS, int QPT, int THREADS>
 __global__ void __launch_bounds__(THREADS) taxi_table_kernel(const __grid_constant__ TaxiParams P) {
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ uint64_t bar;
@@ -230,14 +233,19 @@ __global__ void __launch_bounds__(THREADS) taxi_table_kernel(const __grid_consta
 
   int4 s4[QPT], e4[QPT];
   uint32_t nd4[QPT], a4[QPT];
+  float4 ret4[QPT];
+  constexpr bool stats = STATS;
+  EpisodeAcc acc;
 #pragma unroll
   for (int j = 0; j < QPT; ++j) {
     const int64_t q = base + j * kQuadStride;
+    ret4[j] = make_float4(0.f, 0.f, 0.f, 0.f);
     if (!reset_all) {
       s4[j] = ld_stream(reinterpret_cast<const int4*>(P.s + q));
       e4[j] = ld_stream(reinterpret_cast<const int4*>(P.elapsed + q));
       nd4[j] = ld_stream(reinterpret_cast<const uint32_t*>(P.ndrop + q));
       a4[j] = ld_stream(reinterpret_cast<const uint32_t*>(P.actions + q));
+      if (stats) ret4[j] = __ldcs(reinterpret_cast<const float4*>(P.ep_return + q));
     } else {
       s4[j] = e4[j] = make_int4(0, 0, 0, 0);
       nd4[j] = a4[j] = 0u;
@@ -277,6 +285,15 @@ __global__ void __launch_bounds__(THREADS) taxi_table_kernel(const __grid_consta
         const uint32_t done = term | trunc;
         reset_mask |= done << (4 * j + k);
         respawn_mask |= (goal & ~done & 1u) << (4 * j + k);
+        if (stats) {
+          float& ret = k == 0 ? ret4[j].x : (k == 1 ? ret4[j].y : (k == 2 ? ret4[j].z : ret4[j].w));
+          ret += rv[k];
+          if (q + k < P.num_envs) {
+            acc.steps += 1.f;
+            if (done) acc.finish(ret, ev[k]);
+          }
+          ret = done ? 0.f : ret;
+        }
         ndw |= (nd & 0xFFu) << (8 * k);
         tw |= term << (8 * k);
         trw |= trunc << (8 * k);
@@ -293,7 +310,9 @@ __global__ void __launch_bounds__(THREADS) taxi_table_kernel(const __grid_consta
       st_stream(reinterpret_cast<uint32_t*>(P.terminated + q), tw);
       st_stream(reinterpret_cast<uint32_t*>(P.truncated + q), trw);
     }
+    if (stats) st_stream(reinterpret_cast<float4*>(P.ep_return + q), ret4[j]);
   }
+  if (stats && !reset_all) acc.flush(P.stats);
 
   // ---- rare branches: patch the affected envs (same thread, later stores to the same addresses win)
   uint32_t todo = reset_mask | respawn_mask;
@@ -413,6 +432,10 @@ int taxi_create(gpt_env* env, const gpt_config* c) {
   add_array(env, "s", GPT_ROLE_STATE, GPT_DT_I32, 1);
   add_array(env, "elapsed", GPT_ROLE_STATE, GPT_DT_I32, 1);
   add_array(env, "ndrop", GPT_ROLE_STATE, GPT_DT_U8, 1);
+  if (c->track_stats) {
+    if (!env->taxi_use_table) return fail(GPT_E_ARG, "taxi: track_stats needs the table kernel (ns <= 8192)");
+    add_array(env, "ep_return", GPT_ROLE_STATE, GPT_DT_F32, 1);
+  }
   add_array(env, "obs", GPT_ROLE_OUTPUT, GPT_DT_I32, 1);
   add_array(env, "reward", GPT_ROLE_OUTPUT, GPT_DT_F32, 1);
   add_array(env, "terminated", GPT_ROLE_OUTPUT, GPT_DT_U8, 1);
@@ -472,6 +495,12 @@ int taxi_launch(gpt_env* env, const LaunchArgs& a) {
   P.r_any = c.taxi_reward_any;
   P.rng = make_rng_key(env);
 
+  if (c.track_stats) {
+    P.ep_return = (float*)env->ptr("ep_return");
+    P.stats = env->d_stats;
+    if (!P.ep_return) return fail(GPT_E_UNBOUND, "taxi: ep_return must be bound when track_stats=1");
+  }
+  P.num_envs = c.num_envs;
   P.trans_off = env->taxi_trans_off;
   P.hobs_off = env->taxi_hobs_off;
   P.div_pd = make_fastdiv((uint32_t)(c.taxi_nlocs + 1) * (uint32_t)c.taxi_nlocs);
@@ -484,9 +513,10 @@ int taxi_launch(gpt_env* env, const LaunchArgs& a) {
   if (env->taxi_use_table) {
     // launch shape: GPT_TAXI_SHAPE = "<quads per thread>x<threads>" (tuning knob; default 4x128)
     const int shape = env->taxi_shape;
-#define GPT_TAXI_PICK(Q, T)                                                                                      \
-  (hansen ? (replay ? (K)taxi_table_kernel<true, true, Q, T> : (K)taxi_table_kernel<true, false, Q, T>)            \
-          : (replay ? (K)taxi_table_kernel<false, true, Q, T> : (K)taxi_table_kernel<false, false, Q, T>))
+#define GPT_TAXI_PICK2(S, Q, T)                                                                                  \
+  (hansen ? (replay ? (K)taxi_table_kernel<true, true, S, Q, T> : (K)taxi_table_kernel<true, false, S, Q, T>)      \
+          : (replay ? (K)taxi_table_kernel<false, true, S, Q, T> : (K)taxi_table_kernel<false, false, S, Q, T>))
+#define GPT_TAXI_PICK(Q, T) (c.track_stats ? GPT_TAXI_PICK2(true, Q, T) : GPT_TAXI_PICK2(false, Q, T))
     int qpt;
     switch (shape) {
       case 2128: k = GPT_TAXI_PICK(2, 128); qpt = 2; threads = 128; break;
@@ -496,6 +526,7 @@ int taxi_launch(gpt_env* env, const LaunchArgs& a) {
       default: k = GPT_TAXI_PICK(4, 128); qpt = 4; threads = 128; break;
     }
 #undef GPT_TAXI_PICK
+#undef GPT_TAXI_PICK2
     const int64_t envs_per_cta = (int64_t)threads * kQuad * qpt;
     grid = (int)(((int64_t)a.n_tiles * kTileEnvs + envs_per_cta - 1) / envs_per_cta);
   } else {
@@ -504,7 +535,7 @@ int taxi_launch(gpt_env* env, const LaunchArgs& a) {
     k = hansen ? (replay ? (K)taxi_arith_kernel<true, true> : (K)taxi_arith_kernel<true, false>)
                : (replay ? (K)taxi_arith_kernel<false, true> : (K)taxi_arith_kernel<false, false>);
   }
-  if (smem > 48 * 1024) {
+  if (smem > 40 * 1024) {  // static + dynamic shared memory above 48 KB needs the opt-in
     cudaError_t e = cudaFuncSetAttribute((const void*)k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(taxi)");
   }

@@ -67,6 +67,11 @@ class CRoomsEnv(DeviceVecEnv):
         self.goal_threshold, self.cell_size, self.action_power = goal_threshold, cell_size, action_power
         self.render_mode = render_mode
         self.fixed_goal = None if goal_xy is None else fixed_goal_yx(self.grid, layout, goal_xy)
+        if self.fixed_goal is not None and kind in (N.OBS_ROOM_GOAL, N.OBS_MDP_GOAL) and not (
+                self.fixed_goal[0] < self.grid.shape[0] and self.fixed_goal[1] < self.grid.shape[1]):
+            # the reference's default goal for layouts '32'/'32b' lies outside the grid; it indexes the
+            # table with it at reset() and raises IndexError (rooms.py:27,42-45)
+            raise IndexError(f"fixed goal {self.fixed_goal} is outside the {self.grid.shape} grid")
 
         cfg.family = N.FAMILY_CROOMS
         cfg.time_limit = int(time_limit)

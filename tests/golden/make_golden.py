@@ -67,6 +67,11 @@ CASES = [
                                         "goal_xy": None, "time_limit": 20}, 4, 200),
     ("rooms_grid3_rg", "RoomsEnv", {"layout": "32b", "obs_type": "grid", "obs_n": 3, "goal_xy": None, "time_limit": 30}, 8, 200),
     ("rooms_grid7_goalxy", "RoomsEnv", {"layout": "10", "obs_type": "grid", "obs_n": 7, "goal_xy": (3, 2), "time_limit": 50}, 8, 200),
+    # the reference's default goal for '32'/'32b' (ENDS = x 47, y 32) lies OUTSIDE the 25 x 49 grid: unreachable goal
+    ("rooms32_hansen8_defgoal", "RoomsEnv", {"layout": "32", "obs_type": "hansen8", "time_limit": 30}, 8, 150),
+    ("rooms32b_grid5_defgoal", "RoomsEnv", {"layout": "32b", "obs_type": "grid", "obs_n": 5, "time_limit": 30}, 8, 150),
+    ("rooms32_vghansen8_defgoal", "RoomsEnv", {"layout": "32", "obs_type": "vector_goal_hansen8", "time_limit": 30}, 8, 150),
+    ("crooms32_vghansen8_defgoal", "CRoomsEnv", {"layout": "32", "obs_type": "vector_goal_hansen8", "time_limit": 30}, 0, 150),
     ("crooms_vmdp", "CRoomsEnv", {"layout": "4", "obs_type": "vector_mdp"}, 0, 500),
     ("crooms_hansen8_ord", "CRoomsEnv", {"layout": "4", "obs_type": "hansen8", "action_type": "ordinal"}, 8, 500),
     ("crooms_vel_rg", "CRoomsEnv", {"layout": "8", "obs_type": "vector_mdp_goal", "use_velocity": True, "goal_xy": None,
