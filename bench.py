@@ -32,11 +32,11 @@ WORKLOADS = {
                  desc="Taxi POMDP 5x5 (4 locations, time_limit 200), fused step+obs+autoreset, Philox RNG, uniform random actions"),
     "taxi_hansen": dict(alg_bytes=29, n_act=5, dtype="int32", cpu_family="taxi",
                         desc="Hansen-obs Taxi 5x5, fused step+obs+autoreset, Philox RNG"),
-    "rooms_hansen8": dict(alg_bytes=21, n_act=8, dtype="int32", cpu_family="rooms_hansen8",
+    "rooms_hansen8": dict(alg_bytes=23, n_act=8, dtype="int32", cpu_family="rooms_hansen8",
                           desc="FourRooms '4' discrete, hansen8 obs, 0.2 action-slip, fixed goal, Philox RNG"),
-    "rooms_grid5": dict(alg_bytes=17 + 25, n_act=8, dtype="u8", cpu_family="rooms_grid5",
+    "rooms_grid5": dict(alg_bytes=19 + 25, n_act=8, dtype="u8", cpu_family="rooms_grid5",
                         desc="FourRooms '4', 5x5 egocentric window obs, 0.2 action-slip, fixed goal"),
-    "rooms_grid9": dict(alg_bytes=17 + 81, n_act=8, dtype="u8", cpu_family="rooms_grid9",
+    "rooms_grid9": dict(alg_bytes=19 + 81, n_act=8, dtype="u8", cpu_family="rooms_grid9",
                         desc="FourRooms '4', 9x9 egocentric window obs, 0.2 action-slip, fixed goal"),
 }
 

@@ -1,5 +1,6 @@
 // gpt_api.cu — the extern "C" surface declared in include/gpt_b200.h.
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 
@@ -145,6 +146,8 @@ static int host_path_init(gpt_env* env) {
   if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc(host path actions)");
   e = cudaMemset(h.d_actions, 0, abytes);
   if (e != cudaSuccess) return cuda_fail(e, "cudaMemset(host path actions)");
+  h.n_chunks = 4;
+  if (const char* e2 = getenv("GPT_HOST_CHUNKS")) h.n_chunks = atoi(e2);
   h.ready = true;
   return GPT_OK;
 }
@@ -352,7 +355,11 @@ int gpt_step_host(gpt_env* env, const gpt_host_io* io) {
   const int64_t B = env->cfg.num_envs;
 
   // chunk the tile range over the internal streams so H2D, compute and D2H overlap
-  const int n_chunks = env->n_tiles < HostPath::kStreams * 2 ? 1 : HostPath::kStreams * 2;
+  // chunks: enough to overlap the H2D of chunk i+1 with the D2H of chunk i, few enough that every copy
+  // stays large (PCIe efficiency); GPT_HOST_CHUNKS overrides (tuning knob)
+  int n_chunks = h.n_chunks;
+  if (n_chunks > env->n_tiles) n_chunks = env->n_tiles;
+  if (n_chunks < 1) n_chunks = 1;
   const int32_t per = (env->n_tiles + n_chunks - 1) / n_chunks;
   int rc = GPT_OK;
   for (int c = 0; c < n_chunks && rc == GPT_OK; ++c) {

@@ -511,19 +511,16 @@ int taxi_launch(gpt_env* env, const LaunchArgs& a) {
   int threads, grid;
   const bool hansen = c.taxi_hansen_obs != 0;
   if (env->taxi_use_table) {
-    // launch shape: GPT_TAXI_SHAPE = "<quads per thread>x<threads>" (tuning knob; default 4x128)
+    // launch shape: GPT_TAXI_SHAPE = "<quads per thread>x<threads>" (tuning knob; default 2x128)
     const int shape = env->taxi_shape;
 #define GPT_TAXI_PICK2(S, Q, T)                                                                                  \
   (hansen ? (replay ? (K)taxi_table_kernel<true, true, S, Q, T> : (K)taxi_table_kernel<true, false, S, Q, T>)      \
           : (replay ? (K)taxi_table_kernel<false, true, S, Q, T> : (K)taxi_table_kernel<false, false, S, Q, T>))
 #define GPT_TAXI_PICK(Q, T) (c.track_stats ? GPT_TAXI_PICK2(true, Q, T) : GPT_TAXI_PICK2(false, Q, T))
     int qpt;
-    switch (shape) {
-      case 2128: k = GPT_TAXI_PICK(2, 128); qpt = 2; threads = 128; break;
-      case 2256: k = GPT_TAXI_PICK(2, 256); qpt = 2; threads = 256; break;
-      case 4256: k = GPT_TAXI_PICK(4, 256); qpt = 4; threads = 256; break;
-      case 1256: k = GPT_TAXI_PICK(1, 256); qpt = 1; threads = 256; break;
-      default: k = GPT_TAXI_PICK(4, 128); qpt = 4; threads = 128; break;
+    switch (shape) {  // measured on B200 at 2^22 envs: 2x128 18.9 us, 4x128 19.3 us, 1x256 20.3 us per step
+      case 4128: k = GPT_TAXI_PICK(4, 128); qpt = 4; threads = 128; break;
+      default: k = GPT_TAXI_PICK(2, 128); qpt = 2; threads = 128; break;
     }
 #undef GPT_TAXI_PICK
 #undef GPT_TAXI_PICK2

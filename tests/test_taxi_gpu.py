@@ -214,3 +214,41 @@ def test_host_path_matches_device_path():
         h = host_env.step_host(a)
         for k in range(4):
             np.testing.assert_array_equal(d[k].cpu().numpy(), h[k], err_msg=f"output {k} step {t}")
+
+
+def test_episode_statistics_match_oracle_rollout():
+    """track_stats=1: on-device {episodes, sum_return, sum_length, sum_return^2, env_steps} equal the values
+    accumulated on the host from the oracle's rewards / done flags (padding rows excluded)."""
+    from gym_po.envs import TaxiVecEnv
+    b = 3000                       # ragged: capacity 3072
+    kw = dict(time_limit=25, num_passengers=2)
+    orc = oracle.TaxiOracle(b, draws=oracle.GeneratorDraws(seed=21), **kw)
+    env = TaxiVecEnv(b, device=DEV, rng_mode="replay", track_stats=True, **kw)
+    orc.reset()
+    env.set_replay(**orc.draws)
+    env.reset()
+    rng = np.random.default_rng(6)
+    ret = np.zeros(b, dtype=np.float32)
+    length = np.zeros(b, dtype=np.int64)
+    tot = np.zeros(5)
+    for t in range(150):
+        a = rng.integers(5, size=b)
+        o, r, term, trunc, _ = orc.step(a)
+        env.set_replay(**orc.draws)
+        env.step(torch.as_tensor(a, dtype=torch.int8, device=DEV))
+        ret += r
+        length += 1
+        done = term | trunc
+        tot += [done.sum(), ret[done].astype(np.float64).sum(), length[done].sum(), (ret[done].astype(np.float64) ** 2).sum(), b]
+        ret[done] = 0
+        length[done] = 0
+    got = env.stats_tensor().cpu().numpy()
+    assert got[0] == tot[0] and got[2] == tot[2] and got[4] == tot[4]
+    np.testing.assert_allclose(got[1], tot[1], rtol=1e-5)
+    np.testing.assert_allclose(got[3], tot[3], rtol=1e-5)
+    from gym_po.sharding import allreduce_stats
+    out = allreduce_stats(env.stats_tensor().clone())
+    assert abs(out["mean_length"] - tot[2] / tot[0]) < 1e-9
+    env.stats_reset()
+    torch.cuda.synchronize()
+    assert float(env.stats_tensor().abs().sum()) == 0.0
