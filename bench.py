@@ -213,7 +213,10 @@ def run_b200(args):
     ms_max = float(t.item())
 
     # ---- end-to-end: public API with HOST buffers (pinned), H2D + step + D2H inside the timed region
-    e2e_steps = 1 if args.quick else max(3, min(args.steps, args.e2e_steps))
+    if args.e2e_steps is not None:
+        e2e_steps = max(1, args.e2e_steps)
+    else:
+        e2e_steps = 1 if args.quick else max(3, min(args.steps, 100))
     host_actions = np.random.default_rng(99 + rank).integers(0, wl["n_act"], size=(SLOTS, b)).astype(np.int8)
     pinned = env.host_action_buffer()
     for i in range(3):
@@ -310,7 +313,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="taxi", choices=sorted(WORKLOADS))
     ap.add_argument("--log2-envs", type=int, default=22, help="log2 of envs per GPU")
-    ap.add_argument("--e2e-steps", type=int, default=100)
+    ap.add_argument("--e2e-steps", type=int, default=None)
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--quick", action="store_true", help="profiling runs: no load phase, no e2e, no CPU baseline")

@@ -70,7 +70,65 @@ int rooms_build_tables(gpt_env* env, const gpt_config* c, bool discrete_actions)
       for (int x = 0; x < w; ++x)
         if (g[y * w + x] >= 0) rows[y + off] |= 1ull << (x + off);
   }
+  // move table: [cell*8 + ordinal dir] -> next cell, bit 15 set when the target is a wall (agent stays)
+  std::vector<uint16_t> move((size_t)nc * 8);
+  for (int i = 0; i < nc; ++i)
+    for (int d = 0; d < 8; ++d) {
+      const int y = i / w + kDY[d], x = i % w + kDX[d];
+      const bool free_target = g[i] >= 0 && y >= 0 && y < h && x >= 0 && x < w && g[y * w + x] >= 0;
+      move[(size_t)i * 8 + d] = (uint16_t)(free_target ? (y * w + x) : (i | 0x8000));
+    }
+  // fixed goal: every non-window observation is a function of the agent cell alone -> tabulate it
+  std::vector<uint32_t> obstab;
+  const int kind = c->rooms_obs_kind;
+  if (c->family == GPT_FAMILY_ROOMS && c->rooms_goal_y >= 0 && kind != GPT_OBS_GRID) {
+    const int gy = c->rooms_goal_y, gx = c->rooms_goal_x;
+    const bool inside = gy < h && gx >= 0 && gx < w;
+    const int gcell = inside ? gy * w + gx : 0;
+    const bool two = (kind == GPT_OBS_VEC_HANSEN || kind == GPT_OBS_VEC_HANSEN_GOAL) && c->rooms_obs_n == 8;
+    obstab.assign((size_t)nc * (two ? 2 : 1), 0u);
+    auto spread4 = [](uint32_t b) { return (b * 0x00204081u) & 0x01010101u; };
+    for (int i = 0; i < nc; ++i) {
+      const int y = i / w, x = i % w;
+      const uint32_t nb = nb8[i];
+      const uint32_t b4 = (nb & 1u) | ((nb >> 1) & 2u) | ((nb >> 2) & 4u) | ((nb >> 3) & 8u);
+      int gd = -1;  // ordinal index of the neighbour holding the goal
+      for (int d = 0; d < 8; ++d)
+        if (y + kDY[d] == gy && x + kDX[d] == gx) gd = d;
+      uint32_t lo = 0, hi = 0;
+      switch (kind) {
+        case GPT_OBS_ROOM: lo = room[i]; break;
+        case GPT_OBS_ROOM_GOAL: lo = room[i] + (uint32_t)n_rooms * room[gcell]; break;
+        case GPT_OBS_MDP: lo = sid[i]; break;
+        case GPT_OBS_MDP_GOAL: lo = sid[i] + (uint32_t)valid.size() * sid[gcell]; break;
+        case GPT_OBS_VEC_MDP: lo = (uint32_t)y | ((uint32_t)x << 8); break;
+        case GPT_OBS_VEC_MDP_GOAL: lo = (uint32_t)y | ((uint32_t)x << 8) | ((uint32_t)gy << 16) | ((uint32_t)gx << 24); break;
+        case GPT_OBS_HANSEN:
+          if (c->rooms_obs_n == 8) lo = nb * (gd < 0 ? 1u : (uint32_t)gd + 1u);
+          else lo = b4 * ((gd >= 0 && !(gd & 1)) ? (uint32_t)(gd >> 1) + 1u : 1u);
+          break;
+        case GPT_OBS_VEC_HANSEN:
+        case GPT_OBS_VEC_HANSEN_GOAL: {
+          const int g8 = kind == GPT_OBS_VEC_HANSEN_GOAL ? gd : -1;
+          if (c->rooms_obs_n == 8) {
+            lo = spread4(nb & 15u);
+            hi = spread4(nb >> 4);
+            if (g8 >= 0 && g8 < 4) lo = (lo & ~(0xFFu << (8 * g8))) | (2u << (8 * g8));
+            else if (g8 >= 4) hi = (hi & ~(0xFFu << (8 * (g8 - 4)))) | (2u << (8 * (g8 - 4)));
+          } else {
+            lo = spread4(b4);
+            if (g8 >= 0 && !(g8 & 1)) lo = (lo & ~(0xFFu << (4 * g8))) | (2u << (4 * g8));
+          }
+          break;
+        }
+      }
+      if (two) { obstab[(size_t)i * 2] = lo; obstab[(size_t)i * 2 + 1] = hi; }
+      else obstab[i] = lo;
+    }
+  }
   std::vector<uint8_t> blob;
+  env->rl.move_off = blob_append(blob, move);
+  env->rl.obstab_off = blob_append(blob, obstab);
   env->rl.nb8_off = blob_append(blob, nb8);
   env->rl.room_off = blob_append(blob, room);
   env->rl.sid_off = blob_append(blob, sid);
@@ -160,6 +218,15 @@ int rooms_launch(gpt_env* env, const LaunchArgs& a) {
   if (!P.pos || (rgoal && !P.goal) || !P.elapsed || !P.obs || !P.reward || !P.terminated || !P.truncated)
     return fail(GPT_E_UNBOUND, "rooms: state/output arrays must be bound before reset/step");
   if (a.mode == kModeStep && !P.actions) return fail(GPT_E_ARG, "rooms: actions is NULL");
+  const bool reset = a.mode == kModeReset;
+  if (reset) {
+    // reset() = every env truncates: poison `elapsed` (0x7F7F7F7F > any time limit), step once with any
+    // valid action bytes (the `terminated` array holds 0/1), then clear the flags the step wrote.
+    if (c.time_limit >= 0x7F7F7F7E) return fail(GPT_E_ARG, "rooms: time_limit too large");
+    cudaError_t e = cudaMemsetAsync(P.elapsed, 0x7F, (size_t)env->capacity * sizeof(int32_t), a.stream);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(elapsed)");
+    P.actions = (const int8_t*)P.terminated;
+  }
   const int oi = env->find("obs");
   const size_t obs_row = (size_t)env->arrays[oi].desc.cols * env->arrays[oi].desc.elem_size;
   P.obs = (uint8_t*)P.obs + a.out_row * obs_row;
@@ -181,6 +248,8 @@ int rooms_launch(gpt_env* env, const LaunchArgs& a) {
   P.thr32_off = env->rl.thr32_off;
   P.thr64_off = env->rl.thr64_off;
   P.rows_off = env->rl.rows_off;
+  P.move_off = env->rl.move_off;
+  P.obstab_off = env->rl.obstab_off;
   P.stage_off = (env->blob_bytes + 127u) & ~127u;
   P.env_offset = c.env_offset;
   P.first_tile = a.first_tile;
@@ -204,8 +273,10 @@ int rooms_launch(gpt_env* env, const LaunchArgs& a) {
   P.r_goal = c.rooms_goal_reward;
   P.rng = make_rng_key(env);
 
-  const int threads = grid ? 128 : 256, warps = threads / 32;
-  const int nblocks = (a.n_tiles + warps - 1) / warps;
+  const int threads = 128, warps = threads / 32;
+  const int qpt = grid ? RoomsShape<GPT_OBS_GRID>::kQpt : RoomsShape<GPT_OBS_MDP>::kQpt;
+  const int64_t envs_per_cta = (int64_t)threads * kQuad * qpt;
+  const int nblocks = (int)(((int64_t)a.n_tiles * kTileEnvs + envs_per_cta - 1) / envs_per_cta);
   if (nblocks <= 0) return GPT_OK;
   size_t smem = env->blob_bytes;
   if (grid) smem = P.stage_off + (size_t)warps * kQuadStride * P.grid_n * P.grid_n;
@@ -219,6 +290,12 @@ int rooms_launch(gpt_env* env, const LaunchArgs& a) {
   cudaError_t e = cudaLaunchKernel(k, dim3(nblocks), dim3(threads), args, smem, a.stream);
   env->launches += 1;
   if (e != cudaSuccess) return cuda_fail(e, "rooms_step_kernel launch");
+  if (reset) {
+    e = cudaMemsetAsync(P.terminated, 0, (size_t)env->capacity, a.stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(P.truncated, 0, (size_t)env->capacity, a.stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(P.reward, 0, (size_t)env->capacity * sizeof(float), a.stream);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(reset outputs)");
+  }
   return GPT_OK;
 }
 

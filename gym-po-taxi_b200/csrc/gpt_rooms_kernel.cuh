@@ -35,7 +35,7 @@ struct RoomsParams {
   const int32_t* rp_reset_agent;
   const int32_t* rp_reset_goal;
   const uint8_t* blob;
-  uint32_t blob_bytes, nb8_off, room_off, sid_off, valid_off, thr32_off, thr64_off, rows_off, stage_off;
+  uint32_t blob_bytes, nb8_off, room_off, sid_off, valid_off, thr32_off, thr64_off, rows_off, stage_off, move_off, obstab_off;
   int64_t env_offset;
   int32_t first_tile, n_tiles, mode;
   int32_t w, n_actions, n_valid, n_rooms, time_limit;
@@ -177,35 +177,59 @@ __device__ __forceinline__ void store_obs(void* obs, int64_t q, int64_t warp_qua
   }
 }
 
+// Number of quads (4 envs) a thread handles and the CTA size, per observation kind.  Measured on B200
+// (Taxi, same access pattern): 2 quads x 128 threads beats 4 x 256 — more, smaller CTAs backfill better.
+template <int OBS> struct RoomsShape { static constexpr int kQpt = 2, kThreads = 128; };
+template <> struct RoomsShape<GPT_OBS_GRID> { static constexpr int kQpt = 4, kThreads = 128; };
+
+// Rare path, deliberately out of line (one copy per kernel instead of one per unrolled env):
+// _reset_some (rooms.py:191-196) — new goal first (random-goal envs), then new agent cell.
+template <bool RGOAL, bool REPLAY>
+__device__ __noinline__ uint32_t rooms_respawn(const RoomsParams& P, const uint16_t* valid, int64_t env, uint32_t gcell) {
+  uint32_t cell;
+  if (REPLAY) {
+    if (RGOAL) gcell = (uint32_t)P.rp_reset_goal[env];
+    cell = (uint32_t)P.rp_reset_agent[env];
+  } else {
+    const uint4 r = env_random(P.rng, (uint64_t)(P.env_offset + env), 1u);
+    if (RGOAL) gcell = valid[bounded(r.y, (uint32_t)P.n_valid)];
+    cell = valid[bounded(r.x, (uint32_t)P.n_valid)];
+  }
+  return cell | (gcell << 16);   // values, not references: no local-memory round trip at the call site
+}
+
 template <int OBS, bool RGOAL, bool REPLAY, int GRID_N>
-__global__ void __launch_bounds__(OBS == GPT_OBS_GRID ? 128 : 256) rooms_step_kernel(const __grid_constant__ RoomsParams P) {
+__global__ void __launch_bounds__(RoomsShape<OBS>::kThreads) rooms_step_kernel(const __grid_constant__ RoomsParams P) {
+  constexpr int QPT = RoomsShape<OBS>::kQpt;
+  constexpr int kEnvsPerWarp = kWarp * kQuad * QPT;
+  // fixed goal + non-window obs: the observation is a pure function of the agent cell -> one table lookup
+  constexpr bool kObsTable = !RGOAL && OBS != GPT_OBS_GRID;
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ uint64_t bar;
   stage_tables_begin(smem, P.blob, P.blob_bytes, &bar);
 
   const uint32_t lane = threadIdx.x & 31u;
   const uint32_t warp = threadIdx.x >> 5;
-  const int32_t tile = P.first_tile + (int32_t)(blockIdx.x * (blockDim.x >> 5) + warp);
-  if (tile >= P.first_tile + P.n_tiles) return;
-  const int64_t base = (int64_t)tile * kTileEnvs + lane * kQuad;
-  const bool reset_all = P.mode == kModeReset;
+  const int64_t first = (int64_t)P.first_tile * kTileEnvs, last = first + (int64_t)P.n_tiles * kTileEnvs;
+  const int64_t wbase = first + ((int64_t)blockIdx.x * (RoomsShape<OBS>::kThreads / 32) + warp) * kEnvsPerWarp;
+  if (wbase >= last) return;
+  const int64_t base = wbase + lane * kQuad;
   const uint32_t n = (uint32_t)P.n_actions;
+  const uint32_t dir_shift = n == 4 ? 1u : 0u;   // cardinal action i = ordinal direction 2i
 
-  uint2 pos4[kQuadsPerThread], goal4[kQuadsPerThread];
-  int4 e4[kQuadsPerThread];
-  uint32_t a4[kQuadsPerThread];
+  // reset() is not a separate code path: the host poisons `elapsed` so that every env truncates and
+  // launches this same kernel (gpt_rooms.cu), which keeps the hot loop free of mode branches.
+  uint2 pos4[QPT], goal4[QPT];
+  int4 e4[QPT];
+  uint32_t a4[QPT];
 #pragma unroll
-  for (int j = 0; j < kQuadsPerThread; ++j) {
+  for (int j = 0; j < QPT; ++j) {
     const int64_t q = base + j * kQuadStride;
-    pos4[j] = goal4[j] = make_uint2(0, 0);
-    e4[j] = make_int4(0, 0, 0, 0);
-    a4[j] = 0;
-    if (!reset_all) {
-      pos4[j] = ld_stream(reinterpret_cast<const uint2*>(P.pos + q));
-      if (RGOAL) goal4[j] = ld_stream(reinterpret_cast<const uint2*>(P.goal + q));
-      e4[j] = ld_stream(reinterpret_cast<const int4*>(P.elapsed + q));
-      a4[j] = ld_stream(reinterpret_cast<const uint32_t*>(P.actions + q));
-    }
+    goal4[j] = make_uint2(0, 0);
+    pos4[j] = ld_stream(reinterpret_cast<const uint2*>(P.pos + q));
+    if (RGOAL) goal4[j] = ld_stream(reinterpret_cast<const uint2*>(P.goal + q));
+    e4[j] = ld_stream(reinterpret_cast<const int4*>(P.elapsed + q));
+    a4[j] = ld_stream(reinterpret_cast<const uint32_t*>(P.actions + q));
   }
 
   stage_tables_wait(&bar);
@@ -217,14 +241,18 @@ __global__ void __launch_bounds__(OBS == GPT_OBS_GRID ? 128 : 256) rooms_step_ke
   T.thr32 = reinterpret_cast<const uint32_t*>(smem + P.thr32_off);
   T.thr64 = reinterpret_cast<const double*>(smem + P.thr64_off);
   T.rows = reinterpret_cast<const uint64_t*>(smem + P.rows_off);
+  const uint16_t* move = reinterpret_cast<const uint16_t*>(smem + P.move_off);     // [cell*8 + dir] next cell | blocked << 15
+  const uint32_t* obstab = reinterpret_cast<const uint32_t*>(smem + P.obstab_off); // [cell] or [cell*2] packed observation
   const int gn = GRID_N > 0 ? GRID_N : P.grid_n;
   ObsCtx OC;
   OC.w = P.w; OC.n_rooms = P.n_rooms; OC.n_valid = P.n_valid; OC.hansen_n = P.hansen_n; OC.gn = gn; OC.div_w = P.div_w;
   OC.fixed_goal = !RGOAL; OC.gy = P.goal_y; OC.gx = P.goal_x;
-  uint8_t* stage = smem + P.stage_off + warp * (uint32_t)(kQuadStride * gn * gn);  // grid obs only
+  uint8_t* stage = smem + P.stage_off + warp * (uint32_t)(kQuadStride * gn * gn);  // window obs only
+  constexpr bool kObs8 = OBS == GPT_OBS_VEC_HANSEN || OBS == GPT_OBS_VEC_HANSEN_GOAL;
+  const bool obs_two_words = kObs8 && P.hansen_n == 8;
 
 #pragma unroll
-  for (int j = 0; j < kQuadsPerThread; ++j) {
+  for (int j = 0; j < QPT; ++j) {
     const int64_t q = base + j * kQuadStride;
     uint32_t cellv[4] = {pos4[j].x & 0xFFFFu, pos4[j].x >> 16, pos4[j].y & 0xFFFFu, pos4[j].y >> 16};
     uint32_t goalv[4] = {goal4[j].x & 0xFFFFu, goal4[j].x >> 16, goal4[j].y & 0xFFFFu, goal4[j].y >> 16};
@@ -235,7 +263,7 @@ __global__ void __launch_bounds__(OBS == GPT_OBS_GRID ? 128 : 256) rooms_step_ke
     uint32_t o32b[4] = {0, 0, 0, 0}; // second word for 8-byte vector obs
 
     uint4 slip = make_uint4(0, 0, 0, 0);
-    if (!REPLAY && !reset_all) {  // one Philox block feeds the slip draws of the 4 envs of this quad
+    if (!REPLAY) {  // one Philox block feeds the slip draws of the 4 envs of this quad
       const uint64_t gq = (uint64_t)(P.env_offset + q) >> 2;
       slip = philox4x32_10(make_uint4((uint32_t)gq, (uint32_t)(gq >> 32), P.rng.step_lo, P.rng.step_hi),
                            make_uint2(P.rng.seed_lo, P.rng.seed_hi));
@@ -247,61 +275,61 @@ __global__ void __launch_bounds__(OBS == GPT_OBS_GRID ? 128 : 256) rooms_step_ke
       const int64_t env = q + k;
       uint32_t cell = cellv[k];
       uint32_t gcell = RGOAL ? goalv[k] : (uint32_t)P.goal_cell;
-      bool again = reset_all;
-      rv[k] = 0.f;
-      if (!reset_all) {
-        ev[k] += 1;
-        uint32_t a = (a4[j] >> (8 * k)) & 0xFFu;
-        a = a < n ? a : n - 1;
-        // slipped action a' = #{j : cumsum(P[a])_j < u}, clamped to n-1   (action_utils.py:84-90)
-        uint32_t a2 = 0;
-        if (REPLAY) {
-          const double u = P.rp_u[env];
-          const double* row = T.thr64 + a * n;
-          for (uint32_t i = 0; i < n; ++i) a2 += row[i] < u ? 1u : 0u;
-          a2 = a2 < n ? a2 : n - 1;
-        } else {
-          const uint32_t* row = T.thr32 + a * n;
-          for (uint32_t s = n >> 1; s > 0; s >>= 1) a2 += row[a2 + s - 1] < slipv[k] ? s : 0u;
-        }
-        const uint32_t d8 = n == 4 ? a2 * 2 : a2;
-        const bool blocked = !((T.nb8[cell] >> d8) & 1u);   // grid[proposed] == -1   (rooms.py:212, :224-226)
-        if (!blocked) cell = (uint32_t)((int)cell + dir_dy(d8) * P.w + dir_dx(d8));
-        const bool at_goal = cell == gcell;                 // (:216)
-        rv[k] = at_goal ? P.r_goal : (blocked ? P.r_wall : P.r_step);
-        const bool trunc = ev[k] > P.time_limit;            // (:220)
-        tw |= (at_goal ? 1u : 0u) << (8 * k);
-        trw |= (trunc ? 1u : 0u) << (8 * k);
-        again = at_goal | trunc;
+      ev[k] += 1;
+      uint32_t a = (a4[j] >> (8 * k)) & 0xFFu;
+      a = a < n ? a : n - 1;
+      // slipped action a' = #{j : cumsum(P[a])_j < u}, clamped to n-1   (action_utils.py:84-90)
+      uint32_t a2 = 0;
+      if (REPLAY) {
+        const double u = P.rp_u[env];
+        const double* row = T.thr64 + a * n;
+        for (uint32_t i = 0; i < n; ++i) a2 += row[i] < u ? 1u : 0u;
+        a2 = a2 < n ? a2 : n - 1;
+      } else {
+        const uint32_t* row = T.thr32 + a * n;
+        if (n == 8) a2 = row[3] < slipv[k] ? 4u : 0u;
+        a2 += row[a2 + 1] < slipv[k] ? 2u : 0u;
+        a2 += row[a2] < slipv[k] ? 1u : 0u;
       }
-      if (again) {  // _reset_some (:191-196): goal first, then agent
+      const uint32_t mv = move[cell * 8 + (a2 << dir_shift)];   // grid[proposed] == -1 -> stay (rooms.py:212-213, :224-226)
+      const bool blocked = (mv & 0x8000u) != 0;
+      cell = mv & 0x7FFFu;
+      const bool at_goal = cell == gcell;                 // (:216)
+      rv[k] = at_goal ? P.r_goal : (blocked ? P.r_wall : P.r_step);
+      const bool trunc = ev[k] > P.time_limit;            // (:220)
+      tw |= (at_goal ? 1u : 0u) << (8 * k);
+      trw |= (trunc ? 1u : 0u) << (8 * k);
+      if (at_goal | trunc) {
         ev[k] = 0;
-        if (REPLAY) {
-          if (RGOAL) gcell = (uint32_t)P.rp_reset_goal[env];
-          cell = (uint32_t)P.rp_reset_agent[env];
-        } else {
-          const uint4 r = env_random(P.rng, (uint64_t)(P.env_offset + env), 1u);
-          if (RGOAL) gcell = T.valid[bounded(r.y, (uint32_t)P.n_valid)];
-          cell = T.valid[bounded(r.x, (uint32_t)P.n_valid)];
-        }
+        const uint32_t fresh = rooms_respawn<RGOAL, REPLAY>(P, T.valid, env, gcell);
+        cell = fresh & 0xFFFFu;
+        gcell = fresh >> 16;
       }
       cellv[k] = cell;
       goalv[k] = gcell;
 
       // ---- observation of the (post-reset) state ------------------------------------------
-      cell_obs<OBS, GRID_N>(T, OC, cell, gcell, stage + (uint32_t)(lane * kQuad + k) * (uint32_t)(gn * gn), o32[k], o32b[k]);
+      if constexpr (kObsTable) {
+        if (obs_two_words) {
+          const uint2 o = reinterpret_cast<const uint2*>(obstab)[cell];
+          o32[k] = o.x;
+          o32b[k] = o.y;
+        } else {
+          o32[k] = obstab[cell];
+        }
+      } else {
+        cell_obs<OBS, GRID_N>(T, OC, cell, gcell, stage + (uint32_t)(lane * kQuad + k) * (uint32_t)(gn * gn), o32[k], o32b[k]);
+      }
     }
 
     // ---- stores ------------------------------------------------------------------------------
     st_stream(reinterpret_cast<uint2*>(P.pos + q), make_uint2(cellv[0] | (cellv[1] << 16), cellv[2] | (cellv[3] << 16)));
     if (RGOAL) st_stream(reinterpret_cast<uint2*>(P.goal + q), make_uint2(goalv[0] | (goalv[1] << 16), goalv[2] | (goalv[3] << 16)));
     st_stream(reinterpret_cast<int4*>(P.elapsed + q), make_int4(ev[0], ev[1], ev[2], ev[3]));
-    if (!reset_all) {
-      st_stream(reinterpret_cast<float4*>(P.reward + q), make_float4(rv[0], rv[1], rv[2], rv[3]));
-      st_stream(reinterpret_cast<uint32_t*>(P.terminated + q), tw);
-      st_stream(reinterpret_cast<uint32_t*>(P.truncated + q), trw);
-    }
-    store_obs<OBS>(P.obs, q, (int64_t)tile * kTileEnvs + j * kQuadStride, P.hansen_n, gn, lane, stage, o32, o32b);
+    st_stream(reinterpret_cast<float4*>(P.reward + q), make_float4(rv[0], rv[1], rv[2], rv[3]));
+    st_stream(reinterpret_cast<uint32_t*>(P.terminated + q), tw);
+    st_stream(reinterpret_cast<uint32_t*>(P.truncated + q), trw);
+    store_obs<OBS>(P.obs, q, wbase + j * kQuadStride, P.hansen_n, gn, lane, stage, o32, o32b);
   }
 }
 

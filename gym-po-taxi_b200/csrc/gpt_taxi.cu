@@ -229,7 +229,8 @@ __global__ void __launch_bounds__(THREADS) taxi_table_kernel(const __grid_consta
   const int64_t first = (int64_t)P.first_tile * kTileEnvs, last = first + (int64_t)P.n_tiles * kTileEnvs;
   const int64_t base = first + wtile * kEnvsPerWarp + lane * kQuad;
   if (base >= last) return;
-  const bool reset_all = P.mode == kModeReset;
+  // reset() is not a separate code path: the host poisons `elapsed` so that every env truncates and
+  // launches this same kernel (taxi_launch), which keeps the hot loop free of mode branches.
 
   int4 s4[QPT], e4[QPT];
   uint32_t nd4[QPT], a4[QPT];
@@ -240,16 +241,11 @@ __global__ void __launch_bounds__(THREADS) taxi_table_kernel(const __grid_consta
   for (int j = 0; j < QPT; ++j) {
     const int64_t q = base + j * kQuadStride;
     ret4[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (!reset_all) {
-      s4[j] = ld_stream(reinterpret_cast<const int4*>(P.s + q));
-      e4[j] = ld_stream(reinterpret_cast<const int4*>(P.elapsed + q));
-      nd4[j] = ld_stream(reinterpret_cast<const uint32_t*>(P.ndrop + q));
-      a4[j] = ld_stream(reinterpret_cast<const uint32_t*>(P.actions + q));
-      if (stats) ret4[j] = __ldcs(reinterpret_cast<const float4*>(P.ep_return + q));
-    } else {
-      s4[j] = e4[j] = make_int4(0, 0, 0, 0);
-      nd4[j] = a4[j] = 0u;
-    }
+    s4[j] = ld_stream(reinterpret_cast<const int4*>(P.s + q));
+    e4[j] = ld_stream(reinterpret_cast<const int4*>(P.elapsed + q));
+    nd4[j] = ld_stream(reinterpret_cast<const uint32_t*>(P.ndrop + q));
+    a4[j] = ld_stream(reinterpret_cast<const uint32_t*>(P.actions + q));
+    if (stats) ret4[j] = __ldcs(reinterpret_cast<const float4*>(P.ep_return + q));
   }
 
   stage_tables_wait(&bar);
@@ -258,7 +254,7 @@ __global__ void __launch_bounds__(THREADS) taxi_table_kernel(const __grid_consta
   const uint32_t* cdf = reinterpret_cast<const uint32_t*>(smem + P.cdf_off);
   const uint16_t* valid = reinterpret_cast<const uint16_t*>(smem + P.vs_off);
 
-  uint32_t reset_mask = reset_all ? 0xFFFFFFFFu >> (32 - 4 * QPT) : 0u;  // bit 4j+k: env needs a full reset
+  uint32_t reset_mask = 0u;                                               // bit 4j+k: env needs a full reset
   uint32_t respawn_mask = 0u;                                             // bit 4j+k: new passenger + destination
   int32_t keep_s[4 * QPT];                                                // post-move states (respawn needs the taxi cell)
 
@@ -272,7 +268,7 @@ __global__ void __launch_bounds__(THREADS) taxi_table_kernel(const __grid_consta
     uint32_t ndw = 0, tw = 0, trw = 0;
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      if (!reset_all) {
+      {
         const uint32_t a = min((a4[j] >> (8 * k)) & 0xFFu, (uint32_t)(kTransCols - 1));
         const uint32_t ent = trans[(uint32_t)sv[k] * kTransCols + a];
         const uint32_t goal = (ent >> 13) & 1u;
@@ -305,14 +301,12 @@ __global__ void __launch_bounds__(THREADS) taxi_table_kernel(const __grid_consta
     st_stream(reinterpret_cast<int4*>(P.elapsed + q), make_int4(ev[0], ev[1], ev[2], ev[3]));
     st_stream(reinterpret_cast<uint32_t*>(P.ndrop + q), ndw);
     st_stream(reinterpret_cast<int4*>(P.obs + q), make_int4(ov[0], ov[1], ov[2], ov[3]));
-    if (!reset_all) {
-      st_stream(reinterpret_cast<float4*>(P.reward + q), make_float4(rv[0], rv[1], rv[2], rv[3]));
-      st_stream(reinterpret_cast<uint32_t*>(P.terminated + q), tw);
-      st_stream(reinterpret_cast<uint32_t*>(P.truncated + q), trw);
-    }
+    st_stream(reinterpret_cast<float4*>(P.reward + q), make_float4(rv[0], rv[1], rv[2], rv[3]));
+    st_stream(reinterpret_cast<uint32_t*>(P.terminated + q), tw);
+    st_stream(reinterpret_cast<uint32_t*>(P.truncated + q), trw);
     if (stats) st_stream(reinterpret_cast<float4*>(P.ep_return + q), ret4[j]);
   }
-  if (stats && !reset_all) acc.flush(P.stats);
+  if (stats) acc.flush(P.stats);
 
   // ---- rare branches: patch the affected envs (same thread, later stores to the same addresses win)
   uint32_t todo = reset_mask | respawn_mask;
@@ -463,6 +457,15 @@ int taxi_launch(gpt_env* env, const LaunchArgs& a) {
   if (!P.s || !P.elapsed || !P.ndrop || !P.obs || !P.reward || !P.terminated || !P.truncated)
     return fail(GPT_E_UNBOUND, "taxi: state/output arrays must be bound before reset/step");
   if (a.mode == kModeStep && !P.actions) return fail(GPT_E_ARG, "taxi: actions is NULL");
+  const bool table_reset = a.mode == kModeReset && env->taxi_use_table;
+  if (table_reset) {
+    // reset() = every env truncates: poison `elapsed` (0x7F7F7F7F > any time limit), step once with any
+    // action bytes (the `terminated` array holds 0/1), then clear the outputs the step wrote.
+    if (c.time_limit >= 0x7F7F7F7E) return fail(GPT_E_ARG, "taxi: time_limit too large");
+    cudaError_t e = cudaMemsetAsync(P.elapsed, 0x7F, (size_t)env->capacity * sizeof(int32_t), a.stream);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(elapsed)");
+    P.actions = (const int8_t*)P.terminated;
+  }
   P.obs += a.out_row;
   P.reward += a.out_row;
   P.terminated += a.out_row;
@@ -500,7 +503,7 @@ int taxi_launch(gpt_env* env, const LaunchArgs& a) {
     P.stats = env->d_stats;
     if (!P.ep_return) return fail(GPT_E_UNBOUND, "taxi: ep_return must be bound when track_stats=1");
   }
-  P.num_envs = c.num_envs;
+  P.num_envs = table_reset ? 0 : c.num_envs;   // a reset() does not count as finished episodes
   P.trans_off = env->taxi_trans_off;
   P.hobs_off = env->taxi_hobs_off;
   P.div_pd = make_fastdiv((uint32_t)(c.taxi_nlocs + 1) * (uint32_t)c.taxi_nlocs);
@@ -540,6 +543,12 @@ int taxi_launch(gpt_env* env, const LaunchArgs& a) {
   env->launches += 1;
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return cuda_fail(e, "taxi step kernel launch");
+  if (table_reset) {
+    e = cudaMemsetAsync(P.terminated, 0, (size_t)env->capacity, a.stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(P.truncated, 0, (size_t)env->capacity, a.stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(P.reward, 0, (size_t)env->capacity * sizeof(float), a.stream);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(reset outputs)");
+  }
   return GPT_OK;
 }
 
