@@ -18,6 +18,7 @@
 //   thr64 double[n*n]    cumsum(P[a]) exactly as numpy computes it (replay mode compares the recorded u)
 //   rows  uint64[H+2*off] walkable-bit rows, padded by the window radius (grid obs only)
 #pragma once
+#include <utility>
 #include "gpt_internal.h"
 
 namespace gpt {
@@ -147,6 +148,51 @@ __device__ __forceinline__ void cell_obs(const RoomsTables& T, const ObsCtx& C, 
       const int gr = gy - y + off, gc = gx - x + off;
       if ((unsigned)gr < (unsigned)gn && (unsigned)gc < (unsigned)gn) grid_dst[gr * gn + gc] = 2;
     }
+  }
+}
+
+// ---- n x n window for a QUAD of envs, assembled as 32-bit words ---------------------------------
+// A lane's 4 envs occupy 4*n*n bytes = n*n whole words of the [B,n,n] tensor, so the lane can build
+// its slice of the warp's shared-memory tile with n*n conflict-free STS.32 (lane stride n*n words, odd
+// for odd n) instead of 4*n*n byte stores.  Which (env, row, col) feeds which byte of which word is
+// known at compile time; runs of bytes from one window row are expanded with one multiply (spread4).
+template <int N, int W, int B>
+__device__ __forceinline__ uint32_t window_word_part(const uint32_t (&bits)[4][N]) {
+  if constexpr (B >= 4) {
+    return 0u;
+  } else {
+    constexpr int idx = 4 * W + B, k = idx / (N * N), p = idx % (N * N), r = p / N, c = p % N;
+    constexpr int len = (4 - B) < (N - c) ? (4 - B) : (N - c);
+    return (spread4((bits[k][r] >> c) & ((1u << len) - 1u)) << (8 * B)) | window_word_part<N, W, B + len>(bits);
+  }
+}
+template <int N, int... W>
+__device__ __forceinline__ void window_words(const uint32_t (&bits)[4][N], uint32_t* dst, std::integer_sequence<int, W...>) {
+  ((dst[W] = window_word_part<N, W, 0>(bits)), ...);
+}
+template <int N>
+__device__ __forceinline__ void window_quad(const RoomsTables& T, const ObsCtx& C, const uint32_t (&cell)[4], const uint32_t (&gcell)[4],
+                                            uint8_t* lane_dst) {
+  constexpr int off = N / 2;
+  uint32_t bits[4][N];
+  int y[4], x[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    y[k] = (int)fdiv(cell[k], C.div_w);
+    x[k] = (int)cell[k] - y[k] * C.w;
+#pragma unroll
+    for (int r = 0; r < N; ++r) bits[k][r] = (uint32_t)(T.rows[y[k] + r] >> x[k]) & ((1u << N) - 1u);
+  }
+  window_words<N>(bits, reinterpret_cast<uint32_t*>(lane_dst), std::make_integer_sequence<int, N * N>{});
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {  // the goal cell, if inside the window, reads 2 (same thread: ordered after the word stores)
+    int gy = C.gy, gx = C.gx;
+    if (!C.fixed_goal) {
+      gy = (int)fdiv(gcell[k], C.div_w);
+      gx = (int)gcell[k] - gy * C.w;
+    }
+    const int gr = gy - y[k] + off, gc = gx - x[k] + off;
+    if ((unsigned)gr < (unsigned)N && (unsigned)gc < (unsigned)N) lane_dst[k * N * N + gr * N + gc] = 2;
   }
 }
 
@@ -317,10 +363,12 @@ __global__ void __launch_bounds__(RoomsShape<OBS>::kThreads) rooms_step_kernel(c
         } else {
           o32[k] = obstab[cell];
         }
-      } else {
+      } else if constexpr (!(OBS == GPT_OBS_GRID && GRID_N > 0)) {
         cell_obs<OBS, GRID_N>(T, OC, cell, gcell, stage + (uint32_t)(lane * kQuad + k) * (uint32_t)(gn * gn), o32[k], o32b[k]);
       }
     }
+    if constexpr (OBS == GPT_OBS_GRID && GRID_N > 0)
+      window_quad<GRID_N>(T, OC, cellv, goalv, stage + (uint32_t)(lane * kQuad) * (uint32_t)(GRID_N * GRID_N));
 
     // ---- stores ------------------------------------------------------------------------------
     st_stream(reinterpret_cast<uint2*>(P.pos + q), make_uint2(cellv[0] | (cellv[1] << 16), cellv[2] | (cellv[3] << 16)));

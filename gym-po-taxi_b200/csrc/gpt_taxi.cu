@@ -218,7 +218,7 @@ constexpr uint32_t kTransState = 0x1FFFu, kTransGoal = 1u << 13, kTransBad = 1u 
 constexpr int kTransCols = 6;  // actions 0..4 + "no-op" column for out-of-range action bytes
 
 template <bool HANSEN, bool REPLAY, bool STATS, int QPT, int THREADS>
-__global__ void __launch_bounds__(THREADS) taxi_table_kernel(const __grid_constant__ TaxiParams P) {
+__global__ void __launch_bounds__(THREADS, (STATS || QPT > 2) ? 1 : 1280 / THREADS) taxi_table_kernel(const __grid_constant__ TaxiParams P) {
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ uint64_t bar;
   stage_tables_begin(smem, P.blob, P.blob_bytes, &bar);

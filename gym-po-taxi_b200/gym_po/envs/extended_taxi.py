@@ -35,6 +35,7 @@ TAXI_MAP = ("R: | : :G", " : | : : ", " : : : : ", " | : | : ", "Y| : |B: ")
 EXTENDED_TAXI_MAP = ("R  |   G", "   |    ", "   |    ", "        ", "        ", "  |  |  ", "  |  |  ", "Y |  |B ")
 
 WALL, PSEUDO, FLOOR = "|", ":", " "
+EXACT_LAW_MAX_WORK = 4_000_000   # ns * n_valid above which Philox mode falls back to a uniform reset law
 
 
 def parse_taxi_map(rows: Sequence[str]):
@@ -194,7 +195,13 @@ class TaxiVecEnv(DeviceVecEnv):
         self.state_distribution[self.valid_states] = 1.0 / len(valid)
         cdf = None
         if rng_mode == "philox":
-            self.reset_law = argmax_multinomial_law(self.ns, len(valid))
+            if self.ns * len(valid) <= EXACT_LAW_MAX_WORK:
+                self.reset_law = argmax_multinomial_law(self.ns, len(valid))
+            else:  # documented deviation: the exact law costs O(ns * n_valid * max_count) on the host
+                import warnings
+                warnings.warn("custom map too large for the exact argmax-of-multinomial reset law; Philox mode resets "
+                              "uniformly over the valid states (rng_mode='replay' stays exact)", RuntimeWarning)
+                self.reset_law = np.full(len(valid), 1.0 / len(valid))
             cdf = law_to_cdf32(self.reset_law)
 
         cfg = N.GptConfig()

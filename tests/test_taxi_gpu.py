@@ -252,3 +252,33 @@ def test_episode_statistics_match_oracle_rollout():
     env.stats_reset()
     torch.cuda.synchronize()
     assert float(env.stats_tensor().abs().sum()) == 0.0
+
+
+def test_large_custom_map_uses_arithmetic_kernel():
+    """ns = 15*15*7*6 = 9450 > 8192: the (state, action) table does not fit, the decode/wall-bit kernel runs."""
+    from gym_po.envs import TaxiVecEnv
+    big = ("A" + " " * 13 + "B",) + (" " * 6 + "|" + " " * 8,) * 6 + ("C" + " " * 13 + "D",) + (" " * 15,) * 6 + ("E" + " " * 13 + "F",)
+    assert all(len(r) == 15 for r in big) and len(big) == 15
+    b = 5000
+    for hansen in (False, True):
+        kw = dict(map=big, time_limit=40, num_passengers=2, hansen_obs=hansen)
+        orc = oracle.TaxiOracle(b, draws=oracle.GeneratorDraws(seed=13), **kw)
+        assert orc.ns == 9450
+        env = TaxiVecEnv(b, device=DEV, rng_mode="replay", **kw)
+        o_obs, _ = orc.reset()
+        env.set_replay(**orc.draws)
+        g_obs, _ = env.reset()
+        np.testing.assert_array_equal(g_obs.cpu().numpy(), o_obs)
+        rng = np.random.default_rng(2)
+        for t in range(130):
+            a = rng.integers(5, size=b)
+            o = orc.step(a)
+            env.set_replay(**orc.draws)
+            _cmp(env.step(torch.as_tensor(a, dtype=torch.int8, device=DEV))[:4], o[:4], t)
+        np.testing.assert_array_equal(env.s.cpu().numpy(), orc.s)
+    with pytest.warns(RuntimeWarning):
+        env = TaxiVecEnv(1024, map=big, device=DEV, seed=0)     # Philox mode: uniform reset law fallback
+    obs, _ = env.reset()
+    for _ in range(60):
+        obs, *_ = env.step(torch.randint(0, 5, (1024,), dtype=torch.int8, device=DEV))
+    assert int(obs.min()) >= 0 and int(obs.max()) < 9450
