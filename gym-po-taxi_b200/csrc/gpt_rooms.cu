@@ -274,7 +274,16 @@ int rooms_launch(gpt_env* env, const LaunchArgs& a) {
   P.rng = make_rng_key(env);
 
   const int threads = 128, warps = threads / 32;
-  const int qpt = grid ? RoomsShape<GPT_OBS_GRID>::kQpt : RoomsShape<GPT_OBS_MDP>::kQpt;
+  int qpt = RoomsShape<GPT_OBS_MDP, 0>::kQpt;
+  if (grid) {
+    switch (P.grid_n) {
+      case 3: qpt = RoomsShape<GPT_OBS_GRID, 3>::kQpt; break;
+      case 5: qpt = RoomsShape<GPT_OBS_GRID, 5>::kQpt; break;
+      case 7: qpt = RoomsShape<GPT_OBS_GRID, 7>::kQpt; break;
+      case 9: qpt = RoomsShape<GPT_OBS_GRID, 9>::kQpt; break;
+      default: qpt = RoomsShape<GPT_OBS_GRID, 0>::kQpt; break;
+    }
+  }
   const int64_t envs_per_cta = (int64_t)threads * kQuad * qpt;
   const int nblocks = (int)(((int64_t)a.n_tiles * kTileEnvs + envs_per_cta - 1) / envs_per_cta);
   if (nblocks <= 0) return GPT_OK;

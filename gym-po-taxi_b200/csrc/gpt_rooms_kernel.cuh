@@ -225,8 +225,25 @@ __device__ __forceinline__ void store_obs(void* obs, int64_t q, int64_t warp_qua
 
 // Number of quads (4 envs) a thread handles and the CTA size, per observation kind.  Measured on B200
 // (Taxi, same access pattern): 2 quads x 128 threads beats 4 x 256 — more, smaller CTAs backfill better.
-template <int OBS> struct RoomsShape { static constexpr int kQpt = 2, kThreads = 128; };
-template <> struct RoomsShape<GPT_OBS_GRID> { static constexpr int kQpt = 4, kThreads = 128; };
+#ifndef GPT_ROOMS_QPT_SCALAR
+#define GPT_ROOMS_QPT_SCALAR 2
+#endif
+#ifndef GPT_ROOMS_QPT_GRID
+#define GPT_ROOMS_QPT_GRID 4
+#endif
+#ifndef GPT_ROOMS_MINB_SCALAR
+#define GPT_ROOMS_MINB_SCALAR 10
+#endif
+#ifndef GPT_ROOMS_MINB_GRID
+#define GPT_ROOMS_MINB_GRID 1
+#endif
+// measured on B200 (2^22 envs, layout '4'): scalar obs 2 quads/thread; window obs n <= 5: 2 quads and a
+// 64-register cap (82 % of HBM peak vs 73 %), n >= 7: 4 quads, no cap (85 % vs 74-81 %)
+template <int OBS, int GRID_N> struct RoomsShape { static constexpr int kQpt = GPT_ROOMS_QPT_SCALAR, kThreads = 128, kMinBlocks = GPT_ROOMS_MINB_SCALAR; };
+template <int GRID_N> struct RoomsShape<GPT_OBS_GRID, GRID_N> {
+  static constexpr bool kSmall = GRID_N > 0 && GRID_N <= 5;
+  static constexpr int kQpt = kSmall ? 2 : GPT_ROOMS_QPT_GRID, kThreads = 128, kMinBlocks = kSmall ? 8 : GPT_ROOMS_MINB_GRID;
+};
 
 // Rare path, deliberately out of line (one copy per kernel instead of one per unrolled env):
 // _reset_some (rooms.py:191-196) — new goal first (random-goal envs), then new agent cell.
@@ -245,8 +262,8 @@ __device__ __noinline__ uint32_t rooms_respawn(const RoomsParams& P, const uint1
 }
 
 template <int OBS, bool RGOAL, bool REPLAY, int GRID_N>
-__global__ void __launch_bounds__(RoomsShape<OBS>::kThreads) rooms_step_kernel(const __grid_constant__ RoomsParams P) {
-  constexpr int QPT = RoomsShape<OBS>::kQpt;
+__global__ void __launch_bounds__(RoomsShape<OBS, GRID_N>::kThreads, RoomsShape<OBS, GRID_N>::kMinBlocks) rooms_step_kernel(const __grid_constant__ RoomsParams P) {
+  constexpr int QPT = RoomsShape<OBS, GRID_N>::kQpt;
   constexpr int kEnvsPerWarp = kWarp * kQuad * QPT;
   // fixed goal + non-window obs: the observation is a pure function of the agent cell -> one table lookup
   constexpr bool kObsTable = !RGOAL && OBS != GPT_OBS_GRID;
@@ -257,7 +274,7 @@ __global__ void __launch_bounds__(RoomsShape<OBS>::kThreads) rooms_step_kernel(c
   const uint32_t lane = threadIdx.x & 31u;
   const uint32_t warp = threadIdx.x >> 5;
   const int64_t first = (int64_t)P.first_tile * kTileEnvs, last = first + (int64_t)P.n_tiles * kTileEnvs;
-  const int64_t wbase = first + ((int64_t)blockIdx.x * (RoomsShape<OBS>::kThreads / 32) + warp) * kEnvsPerWarp;
+  const int64_t wbase = first + ((int64_t)blockIdx.x * (RoomsShape<OBS, GRID_N>::kThreads / 32) + warp) * kEnvsPerWarp;
   if (wbase >= last) return;
   const int64_t base = wbase + lane * kQuad;
   const uint32_t n = (uint32_t)P.n_actions;
@@ -316,14 +333,15 @@ __global__ void __launch_bounds__(RoomsShape<OBS>::kThreads) rooms_step_kernel(c
     }
     const uint32_t slipv[4] = {slip.x, slip.y, slip.z, slip.w};
 
+    // ---- transition of the 4 envs: straight-line code, no branches, so the compiler can interleave the
+    //      four dependent lookup chains (thresholds -> move table)
+    uint32_t again = 0u;   // bit k: env k finished its episode (goal reached or time limit)
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       const int64_t env = q + k;
-      uint32_t cell = cellv[k];
-      uint32_t gcell = RGOAL ? goalv[k] : (uint32_t)P.goal_cell;
+      const uint32_t gcell = RGOAL ? goalv[k] : (uint32_t)P.goal_cell;
       ev[k] += 1;
-      uint32_t a = (a4[j] >> (8 * k)) & 0xFFu;
-      a = a < n ? a : n - 1;
+      const uint32_t a = ((a4[j] >> (8 * k)) & 0xFFu) & (n - 1u);   // n is 4 or 8; out-of-range bytes wrap
       // slipped action a' = #{j : cumsum(P[a])_j < u}, clamped to n-1   (action_utils.py:84-90)
       uint32_t a2 = 0;
       if (REPLAY) {
@@ -337,34 +355,49 @@ __global__ void __launch_bounds__(RoomsShape<OBS>::kThreads) rooms_step_kernel(c
         a2 += row[a2 + 1] < slipv[k] ? 2u : 0u;
         a2 += row[a2] < slipv[k] ? 1u : 0u;
       }
-      const uint32_t mv = move[cell * 8 + (a2 << dir_shift)];   // grid[proposed] == -1 -> stay (rooms.py:212-213, :224-226)
+      const uint32_t mv = move[cellv[k] * 8 + (a2 << dir_shift)];   // grid[proposed] == -1 -> stay (rooms.py:212-213, :224-226)
       const bool blocked = (mv & 0x8000u) != 0;
-      cell = mv & 0x7FFFu;
-      const bool at_goal = cell == gcell;                 // (:216)
+      cellv[k] = mv & 0x7FFFu;
+      const bool at_goal = cellv[k] == gcell;             // (:216)
       rv[k] = at_goal ? P.r_goal : (blocked ? P.r_wall : P.r_step);
       const bool trunc = ev[k] > P.time_limit;            // (:220)
       tw |= (at_goal ? 1u : 0u) << (8 * k);
       trw |= (trunc ? 1u : 0u) << (8 * k);
-      if (at_goal | trunc) {
-        ev[k] = 0;
-        const uint32_t fresh = rooms_respawn<RGOAL, REPLAY>(P, T.valid, env, gcell);
-        cell = fresh & 0xFFFFu;
-        gcell = fresh >> 16;
-      }
-      cellv[k] = cell;
+      again |= ((at_goal | trunc) ? 1u : 0u) << k;
       goalv[k] = gcell;
-
-      // ---- observation of the (post-reset) state ------------------------------------------
+    }
+    // ---- rare: respawn finished envs (one divergence point per quad, not per env) ----
+    if (again) {
+#pragma unroll 1
+      for (uint32_t m = again; m; m &= m - 1) {
+        const int k = __ffs(m) - 1;
+        uint32_t g = 0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) g = i == k ? goalv[i] : g;
+        const uint32_t fresh = rooms_respawn<RGOAL, REPLAY>(P, T.valid, q + k, g);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          if (i == k) {
+            cellv[i] = fresh & 0xFFFFu;
+            goalv[i] = fresh >> 16;
+            ev[i] = 0;
+          }
+        }
+      }
+    }
+    // ---- observation of the (post-reset) state ------------------------------------------------
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
       if constexpr (kObsTable) {
         if (obs_two_words) {
-          const uint2 o = reinterpret_cast<const uint2*>(obstab)[cell];
+          const uint2 o = reinterpret_cast<const uint2*>(obstab)[cellv[k]];
           o32[k] = o.x;
           o32b[k] = o.y;
         } else {
-          o32[k] = obstab[cell];
+          o32[k] = obstab[cellv[k]];
         }
       } else if constexpr (!(OBS == GPT_OBS_GRID && GRID_N > 0)) {
-        cell_obs<OBS, GRID_N>(T, OC, cell, gcell, stage + (uint32_t)(lane * kQuad + k) * (uint32_t)(gn * gn), o32[k], o32b[k]);
+        cell_obs<OBS, GRID_N>(T, OC, cellv[k], goalv[k], stage + (uint32_t)(lane * kQuad + k) * (uint32_t)(gn * gn), o32[k], o32b[k]);
       }
     }
     if constexpr (OBS == GPT_OBS_GRID && GRID_N > 0)
