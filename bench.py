@@ -217,8 +217,8 @@ def run_b200(args):
         e2e_steps = max(1, args.e2e_steps)
     else:
         e2e_steps = 1 if args.quick else max(3, min(args.steps, 100))
-    host_actions = np.random.default_rng(99 + rank).integers(0, wl["n_act"], size=(SLOTS, b)).astype(np.int8)
-    pinned = env.host_action_buffer()
+    host_actions = env.pinned_actions(SLOTS)          # the steps' inputs live in pinned host memory
+    host_actions[:] = np.random.default_rng(99 + rank).integers(0, wl["n_act"], size=(SLOTS, b)).astype(np.int8)
     for i in range(3):
         env.step_host(host_actions[i % SLOTS])
     if world > 1:
@@ -226,8 +226,7 @@ def run_b200(args):
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     for i in range(e2e_steps):
-        np.copyto(pinned, host_actions[i % SLOTS])     # the step's inputs start in ordinary host memory
-        obs, rew, term, trunc, _ = env.step_host(pinned)
+        obs, rew, term, trunc, _ = env.step_host(host_actions[i % SLOTS])   # H2D actions, step, D2H results
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)

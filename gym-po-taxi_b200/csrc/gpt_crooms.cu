@@ -366,6 +366,7 @@ static int action_kind(const gpt_config* c) {
 }
 
 int crooms_create(gpt_env* env, const gpt_config* c) {
+  if (c->track_stats) return fail(GPT_E_ARG, "crooms: track_stats is implemented for the Taxi and ROOMS families only");
   if (!(c->c_cell_size > 0)) return fail(GPT_E_ARG, "crooms: cell_size must be > 0");
   const int kind = c->rooms_obs_kind;
   if ((kind == GPT_OBS_HANSEN || kind == GPT_OBS_VEC_HANSEN || kind == GPT_OBS_VEC_HANSEN_GOAL) && c->rooms_obs_n != 4 && c->rooms_obs_n != 8)
@@ -515,6 +516,7 @@ int crooms_launch(gpt_env* env, const LaunchArgs& a) {
 }
 
 int tag_create(gpt_env* env, const gpt_config* c) {
+  if (c->track_stats) return fail(GPT_E_ARG, "tag: track_stats is implemented for the Taxi and ROOMS families only");
   add_array(env, "agent", GPT_ROLE_STATE, GPT_DT_F64, 2);
   add_array(env, "target", GPT_ROLE_STATE, GPT_DT_F64, 2);
   add_array(env, "elapsed", GPT_ROLE_STATE, GPT_DT_I32, 1);

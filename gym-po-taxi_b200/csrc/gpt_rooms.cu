@@ -175,6 +175,7 @@ int rooms_create(gpt_env* env, const gpt_config* c) {
   add_array(env, "pos", GPT_ROLE_STATE, GPT_DT_U16, 1);
   if (rgoal) add_array(env, "goal", GPT_ROLE_STATE, GPT_DT_U16, 1);
   add_array(env, "elapsed", GPT_ROLE_STATE, GPT_DT_I32, 1);
+  if (c->track_stats) add_array(env, "ep_return", GPT_ROLE_STATE, GPT_DT_F32, 1);
   add_array(env, "obs", GPT_ROLE_OUTPUT, odt, ocols);
   add_array(env, "reward", GPT_ROLE_OUTPUT, GPT_DT_F32, 1);
   add_array(env, "terminated", GPT_ROLE_OUTPUT, GPT_DT_U8, 1);
@@ -189,15 +190,15 @@ int rooms_create(gpt_env* env, const gpt_config* c) {
 }
 
 
-static void* pick_kernel(int obs, int grid_n, bool rgoal, bool replay) {
+static void* pick_kernel(int obs, int grid_n, bool rgoal, bool replay, bool stats) {
   switch (obs) {
-    case GPT_OBS_ROOM: case GPT_OBS_ROOM_GOAL: case GPT_OBS_MDP: case GPT_OBS_MDP_GOAL: return rooms_pick_table(obs, rgoal, replay);
-    case GPT_OBS_VEC_MDP: case GPT_OBS_VEC_MDP_GOAL: case GPT_OBS_HANSEN: return rooms_pick_vec(obs, rgoal, replay);
-    case GPT_OBS_VEC_HANSEN: case GPT_OBS_VEC_HANSEN_GOAL: return rooms_pick_vhansen(obs, rgoal, replay);
+    case GPT_OBS_ROOM: case GPT_OBS_ROOM_GOAL: case GPT_OBS_MDP: case GPT_OBS_MDP_GOAL: return rooms_pick_table(obs, rgoal, replay, stats);
+    case GPT_OBS_VEC_MDP: case GPT_OBS_VEC_MDP_GOAL: case GPT_OBS_HANSEN: return rooms_pick_vec(obs, rgoal, replay, stats);
+    case GPT_OBS_VEC_HANSEN: case GPT_OBS_VEC_HANSEN_GOAL: return rooms_pick_vhansen(obs, rgoal, replay, stats);
     case GPT_OBS_GRID:
-      if (grid_n == 3 || grid_n == 5) return rooms_pick_grid_small(grid_n, rgoal, replay);
-      if (grid_n == 7 || grid_n == 9) return rooms_pick_grid_large(grid_n, rgoal, replay);
-      return rooms_pick_grid_any(rgoal, replay);
+      if (grid_n == 3 || grid_n == 5) return rooms_pick_grid_small(grid_n, rgoal, replay, stats);
+      if (grid_n == 7 || grid_n == 9) return rooms_pick_grid_large(grid_n, rgoal, replay, stats);
+      return rooms_pick_grid_any(rgoal, replay, stats);
   }
   return nullptr;
 }
@@ -239,6 +240,12 @@ int rooms_launch(gpt_env* env, const LaunchArgs& a) {
     P.rp_reset_goal = (const int32_t*)env->ptr("replay_reset_goal");
     if (!P.rp_u || !P.rp_reset_agent || !P.rp_reset_goal) return fail(GPT_E_UNBOUND, "rooms: replay arrays must be bound in replay mode");
   }
+  if (c.track_stats) {
+    P.ep_return = (float*)env->ptr("ep_return");
+    P.stats = env->d_stats;
+    if (!P.ep_return) return fail(GPT_E_UNBOUND, "rooms: ep_return must be bound when track_stats=1");
+  }
+  P.num_envs = reset ? 0 : c.num_envs;   // a reset() does not count as finished episodes
   P.blob = env->d_blob;
   P.blob_bytes = env->blob_bytes;
   P.nb8_off = env->rl.nb8_off;
@@ -289,7 +296,7 @@ int rooms_launch(gpt_env* env, const LaunchArgs& a) {
   if (nblocks <= 0) return GPT_OK;
   size_t smem = env->blob_bytes;
   if (grid) smem = P.stage_off + (size_t)warps * kQuadStride * P.grid_n * P.grid_n;
-  void* k = pick_kernel(c.rooms_obs_kind, P.grid_n, rgoal, replay);
+  void* k = pick_kernel(c.rooms_obs_kind, P.grid_n, rgoal, replay, c.track_stats != 0);
   if (!k) return fail(GPT_E_ARG, "rooms: no kernel for this obs kind");
   if (smem > 40 * 1024) {  // static + dynamic shared memory above 48 KB needs the opt-in
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

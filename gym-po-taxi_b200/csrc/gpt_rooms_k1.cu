@@ -3,11 +3,11 @@
 
 namespace gpt {
 
-void* rooms_pick_vec(int obs, bool rgoal, bool replay) {
+void* rooms_pick_vec(int obs, bool rgoal, bool replay, bool stats) {
   switch (obs) {
-    case GPT_OBS_VEC_MDP: return pick_rr<GPT_OBS_VEC_MDP, 0>(rgoal, replay);
-    case GPT_OBS_VEC_MDP_GOAL: return pick_rr<GPT_OBS_VEC_MDP_GOAL, 0>(rgoal, replay);
-    case GPT_OBS_HANSEN: return pick_rr<GPT_OBS_HANSEN, 0>(rgoal, replay);
+    case GPT_OBS_VEC_MDP: return pick_rr<GPT_OBS_VEC_MDP, 0>(rgoal, replay, stats);
+    case GPT_OBS_VEC_MDP_GOAL: return pick_rr<GPT_OBS_VEC_MDP_GOAL, 0>(rgoal, replay, stats);
+    case GPT_OBS_HANSEN: return pick_rr<GPT_OBS_HANSEN, 0>(rgoal, replay, stats);
   }
   return nullptr;
 }

@@ -32,6 +32,9 @@ struct RoomsParams {
   float* reward;
   uint8_t* terminated;
   uint8_t* truncated;
+  float* ep_return;   // running return per env (track_stats only)
+  double* stats;      // device float64[8] (track_stats only)
+  int64_t num_envs;   // rows >= num_envs are padding: excluded from the statistics
   const double* rp_u;
   const int32_t* rp_reset_agent;
   const int32_t* rp_reset_goal;
@@ -261,8 +264,8 @@ __device__ __noinline__ uint32_t rooms_respawn(const RoomsParams& P, const uint1
   return cell | (gcell << 16);   // values, not references: no local-memory round trip at the call site
 }
 
-template <int OBS, bool RGOAL, bool REPLAY, int GRID_N>
-__global__ void __launch_bounds__(RoomsShape<OBS, GRID_N>::kThreads, RoomsShape<OBS, GRID_N>::kMinBlocks) rooms_step_kernel(const __grid_constant__ RoomsParams P) {
+template <int OBS, bool RGOAL, bool REPLAY, int GRID_N, bool STATS>
+__global__ void __launch_bounds__(RoomsShape<OBS, GRID_N>::kThreads, STATS ? 1 : RoomsShape<OBS, GRID_N>::kMinBlocks) rooms_step_kernel(const __grid_constant__ RoomsParams P) {
   constexpr int QPT = RoomsShape<OBS, GRID_N>::kQpt;
   constexpr int kEnvsPerWarp = kWarp * kQuad * QPT;
   // fixed goal + non-window obs: the observation is a pure function of the agent cell -> one table lookup
@@ -285,6 +288,8 @@ __global__ void __launch_bounds__(RoomsShape<OBS, GRID_N>::kThreads, RoomsShape<
   uint2 pos4[QPT], goal4[QPT];
   int4 e4[QPT];
   uint32_t a4[QPT];
+  float4 ret4[STATS ? QPT : 1];
+  EpisodeAcc acc;
 #pragma unroll
   for (int j = 0; j < QPT; ++j) {
     const int64_t q = base + j * kQuadStride;
@@ -293,6 +298,7 @@ __global__ void __launch_bounds__(RoomsShape<OBS, GRID_N>::kThreads, RoomsShape<
     if (RGOAL) goal4[j] = ld_stream(reinterpret_cast<const uint2*>(P.goal + q));
     e4[j] = ld_stream(reinterpret_cast<const int4*>(P.elapsed + q));
     a4[j] = ld_stream(reinterpret_cast<const uint32_t*>(P.actions + q));
+    if constexpr (STATS) ret4[j] = __ldcs(reinterpret_cast<const float4*>(P.ep_return + q));
   }
 
   stage_tables_wait(&bar);
@@ -365,6 +371,15 @@ __global__ void __launch_bounds__(RoomsShape<OBS, GRID_N>::kThreads, RoomsShape<
       trw |= (trunc ? 1u : 0u) << (8 * k);
       again |= ((at_goal | trunc) ? 1u : 0u) << k;
       goalv[k] = gcell;
+      if constexpr (STATS) {
+        float& ret = k == 0 ? ret4[j].x : (k == 1 ? ret4[j].y : (k == 2 ? ret4[j].z : ret4[j].w));
+        ret += rv[k];
+        if (env < P.num_envs) {
+          acc.steps += 1.f;
+          if (at_goal | trunc) acc.finish(ret, ev[k]);
+        }
+        ret = (at_goal | trunc) ? 0.f : ret;
+      }
     }
     // ---- rare: respawn finished envs (one divergence point per quad, not per env) ----
     if (again) {
@@ -411,23 +426,29 @@ __global__ void __launch_bounds__(RoomsShape<OBS, GRID_N>::kThreads, RoomsShape<
     st_stream(reinterpret_cast<uint32_t*>(P.terminated + q), tw);
     st_stream(reinterpret_cast<uint32_t*>(P.truncated + q), trw);
     store_obs<OBS>(P.obs, q, wbase + j * kQuadStride, P.hansen_n, gn, lane, stage, o32, o32b);
+    if constexpr (STATS) st_stream(reinterpret_cast<float4*>(P.ep_return + q), ret4[j]);
   }
+  if constexpr (STATS) acc.flush(P.stats);
 }
 
-template <int OBS, int GRID_N>
-static void* pick_rr(bool rgoal, bool replay) {
+template <int OBS, int GRID_N, bool STATS>
+static void* pick_rr2(bool rgoal, bool replay) {
   using K = void (*)(const RoomsParams);
-  K k = rgoal ? (replay ? (K)rooms_step_kernel<OBS, true, true, GRID_N> : (K)rooms_step_kernel<OBS, true, false, GRID_N>)
-              : (replay ? (K)rooms_step_kernel<OBS, false, true, GRID_N> : (K)rooms_step_kernel<OBS, false, false, GRID_N>);
+  K k = rgoal ? (replay ? (K)rooms_step_kernel<OBS, true, true, GRID_N, STATS> : (K)rooms_step_kernel<OBS, true, false, GRID_N, STATS>)
+              : (replay ? (K)rooms_step_kernel<OBS, false, true, GRID_N, STATS> : (K)rooms_step_kernel<OBS, false, false, GRID_N, STATS>);
   return (void*)k;
+}
+template <int OBS, int GRID_N>
+static void* pick_rr(bool rgoal, bool replay, bool stats) {
+  return stats ? pick_rr2<OBS, GRID_N, true>(rgoal, replay) : pick_rr2<OBS, GRID_N, false>(rgoal, replay);
 }
 
 // kernel instantiations live in gpt_rooms_k*.cu so that they compile in parallel
-void* rooms_pick_table(int obs, bool rgoal, bool replay);   // ROOM, ROOM_GOAL, MDP, MDP_GOAL
-void* rooms_pick_vec(int obs, bool rgoal, bool replay);     // VEC_MDP, VEC_MDP_GOAL, HANSEN
-void* rooms_pick_vhansen(int obs, bool rgoal, bool replay); // VEC_HANSEN, VEC_HANSEN_GOAL
-void* rooms_pick_grid_small(int n, bool rgoal, bool replay);  // 3, 5
-void* rooms_pick_grid_large(int n, bool rgoal, bool replay);  // 7, 9
-void* rooms_pick_grid_any(bool rgoal, bool replay);           // run-time n <= 15
+void* rooms_pick_table(int obs, bool rgoal, bool replay, bool stats);   // ROOM, ROOM_GOAL, MDP, MDP_GOAL
+void* rooms_pick_vec(int obs, bool rgoal, bool replay, bool stats);     // VEC_MDP, VEC_MDP_GOAL, HANSEN
+void* rooms_pick_vhansen(int obs, bool rgoal, bool replay, bool stats); // VEC_HANSEN, VEC_HANSEN_GOAL
+void* rooms_pick_grid_small(int n, bool rgoal, bool replay, bool stats);  // 3, 5
+void* rooms_pick_grid_large(int n, bool rgoal, bool replay, bool stats);  // 7, 9
+void* rooms_pick_grid_any(bool rgoal, bool replay, bool stats);           // run-time n <= 15
 
 }  // namespace gpt

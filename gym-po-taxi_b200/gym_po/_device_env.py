@@ -91,6 +91,7 @@ class DeviceVecEnv:
         self._terminated = self._arrays["terminated"][:b].view(torch.bool)
         self._truncated = self._arrays["truncated"][:b].view(torch.bool)
         self._host = None
+        self._pinned_user = []
 
     def _shape_obs(self, obs):
         return obs
@@ -208,20 +209,47 @@ class DeviceVecEnv:
         """The pinned action buffer ``step_host`` uploads from (fill it in place to skip a host copy)."""
         return self._ensure_host()["actions"]
 
+    def pinned_actions(self, n_slots: int) -> np.ndarray:
+        """``[n_slots, num_envs(,cols)]`` numpy array backed by page-locked memory.  ``step_host(arr[i])`` uploads
+        straight from it (no intermediate host copy)."""
+        self._ensure_host()
+        shape = (n_slots,) + tuple(self._host["actions"].shape)
+        t = torch.zeros(shape, dtype=self._action_dtype).pin_memory()
+        self._pinned_user.append(t)
+        return t.numpy()
+
     def host_bytes_per_step(self):
         """(h2d, d2h) bytes one ``step_host`` call moves over PCIe."""
         hn = self._ensure_host()
         return hn["actions"].nbytes, sum(hn[k].nbytes for k in ("obs", "reward", "terminated", "truncated"))
+
+    def _pinned_pointer(self, a: np.ndarray):
+        """Address of ``a`` if it is a C-contiguous slice of a buffer from :meth:`pinned_actions`, else None."""
+        if not (isinstance(a, np.ndarray) and a.flags.c_contiguous and a.dtype == self._host_np["actions"].dtype
+                and a.shape == self._host_np["actions"].shape):
+            return None
+        addr = a.ctypes.data
+        for t in self._pinned_user:
+            lo = t.data_ptr()
+            if lo <= addr and addr + a.nbytes <= lo + t.numel() * t.element_size():
+                return addr
+        return None
 
     def step_host(self, actions: np.ndarray):
         """numpy in / numpy out through ``gpt_step_host``: pinned host buffers, chunked
         H2D -> fused step -> D2H pipeline.  Returned arrays are views of pinned buffers that the
         next ``step_host`` overwrites."""
         hn = self._ensure_host()
+        io = self._host_io
         if actions is not hn["actions"]:
-            np.copyto(hn["actions"], actions, casting="unsafe")
+            addr = self._pinned_pointer(actions)
+            if addr is not None:
+                io = N.GptHostIO(C.c_void_p(addr), self._host_io.obs, self._host_io.reward, self._host_io.terminated,
+                                 self._host_io.truncated)
+            else:
+                np.copyto(hn["actions"], actions, casting="unsafe")
         with self._on_device():
-            N.check(N.lib.gpt_step_host(self._h, C.byref(self._host_io)))
+            N.check(N.lib.gpt_step_host(self._h, C.byref(io)))
         return (self._shape_obs(hn["obs"]), hn["reward"], hn["terminated"].view(np.bool_),
                 hn["truncated"].view(np.bool_), {})
 

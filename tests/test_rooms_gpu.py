@@ -195,3 +195,40 @@ def test_gpu_count_independence_and_host_path():
         for k in range(4):
             assert torch.equal(w[k][: b // 2], l[k]) and torch.equal(w[k][b // 2:], h[k]), (k, t)
             np.testing.assert_array_equal(w[k].cpu().numpy(), hp[k])
+
+
+@pytest.mark.parametrize("obs_type,goal_xy", [("hansen8", (0, 0)), ("grid", None)])
+def test_episode_statistics_match_returned_rewards(obs_type, goal_xy):
+    """track_stats=1 (Philox mode): the on-device statistics equal what the host accumulates from the
+    returned reward / terminated / truncated tensors (padding rows excluded, reset() not counted)."""
+    from gym_po.envs import RoomsEnv
+    from gym_po.sharding import allreduce_stats
+    b = 5000
+    env = RoomsEnv(b, "2", obs_type=obs_type, obs_n=5, goal_xy=goal_xy, time_limit=17, step_reward=-0.25, wall_reward=-1.0,
+                   goal_reward=4.0, device=DEV, seed=4, track_stats=True)
+    env.reset(seed=4)
+    ret = torch.zeros(b, device=DEV)
+    length = torch.zeros(b, dtype=torch.int64, device=DEV)
+    tot = torch.zeros(5, dtype=torch.float64, device=DEV)
+    gen = torch.Generator(device=DEV).manual_seed(2)
+    for t in range(120):
+        a = torch.randint(0, 8, (env.capacity,), dtype=torch.int8, device=DEV, generator=gen)
+        obs, rew, term, trunc, _ = env.step(a)
+        ret += rew
+        length += 1
+        done = term | trunc
+        r = ret[done].double()
+        tot += torch.stack([done.sum().double(), r.sum(), length[done].sum().double(), (r * r).sum(),
+                            torch.tensor(float(b), dtype=torch.float64, device=DEV)])
+        ret[done] = 0
+        length[done] = 0
+    got = env.stats_tensor().cpu().numpy()
+    tot = tot.cpu().numpy()
+    assert tot[0] > 1000
+    assert got[0] == tot[0] and got[2] == tot[2] and got[4] == tot[4]
+    np.testing.assert_allclose(got[1], tot[1], rtol=1e-5)
+    np.testing.assert_allclose(got[3], tot[3], rtol=1e-5)
+    assert abs(allreduce_stats(env.stats_tensor().clone())["mean_return"] - tot[1] / tot[0]) < 1e-4
+    with pytest.raises(ValueError):
+        from gym_po.envs import CRoomsEnv
+        CRoomsEnv(64, device=DEV, track_stats=True)
