@@ -36,6 +36,10 @@ WORKLOADS = {
                           desc="FourRooms '4' discrete, hansen8 obs, 0.2 action-slip, fixed goal, Philox RNG"),
     "rooms_grid5": dict(alg_bytes=19 + 25, n_act=8, dtype="u8", cpu_family="rooms_grid5",
                         desc="FourRooms '4', 5x5 egocentric window obs, 0.2 action-slip, fixed goal"),
+    "crooms": dict(alg_bytes=70, n_act=0, dtype="f64", cpu_family="crooms",
+                   desc="continuous ROOMS '4' (float64 positions, Gaussian action noise 0.2, wall rejection), vector_mdp obs, yx float32 actions"),
+    "tag": dict(alg_bytes=102, n_act=0, dtype="f64", cpu_family="tag",
+                desc="point-mass Tag (AntTag pursuit rules, float64), yx float32 actions"),
     "rooms_grid9": dict(alg_bytes=19 + 81, n_act=8, dtype="u8", cpu_family="rooms_grid9",
                         desc="FourRooms '4', 9x9 egocentric window obs, 0.2 action-slip, fixed goal"),
 }
@@ -144,6 +148,12 @@ def make_env(workload, b, rank, seed=0):
         return RoomsEnv(b, "4", obs_type="grid", obs_n=5, seed=seed, env_offset=rank * b)
     if workload == "rooms_grid9":
         return RoomsEnv(b, "4", obs_type="grid", obs_n=9, seed=seed, env_offset=rank * b)
+    if workload == "crooms":
+        from gym_po.envs import CRoomsEnv
+        return CRoomsEnv(b, "4", obs_type="vector_mdp", seed=seed, env_offset=rank * b)
+    if workload == "tag":
+        from gym_po.envs import TagVecEnv
+        return TagVecEnv(b, seed=seed, env_offset=rank * b)
     raise KeyError(workload)
 
 
@@ -164,7 +174,10 @@ def run_b200(args):
     env = make_env(args.workload, b, rank)
     cap = env.capacity
     gen = torch.Generator(device=dev).manual_seed(1234 + rank)
-    actions = torch.randint(0, wl["n_act"], (SLOTS, cap), dtype=torch.int8, device=dev, generator=gen)
+    if wl["n_act"]:
+        actions = torch.randint(0, wl["n_act"], (SLOTS, cap), dtype=torch.int8, device=dev, generator=gen)
+    else:
+        actions = torch.rand((SLOTS, cap, 2), device=dev, generator=gen) * 2 - 1
     # rollout storage: outputs of step t go to slot t % SLOTS (like an RL rollout buffer); with the
     # action slots this makes the per-step footprint rotate through > L2-size memory
     out = {}
@@ -218,7 +231,11 @@ def run_b200(args):
     else:
         e2e_steps = 1 if args.quick else max(3, min(args.steps, 100))
     host_actions = env.pinned_actions(SLOTS)          # the steps' inputs live in pinned host memory
-    host_actions[:] = np.random.default_rng(99 + rank).integers(0, wl["n_act"], size=(SLOTS, b)).astype(np.int8)
+    hrng = np.random.default_rng(99 + rank)
+    if wl["n_act"]:
+        host_actions[:] = hrng.integers(0, wl["n_act"], size=(SLOTS, b)).astype(np.int8)
+    else:
+        host_actions[:] = hrng.uniform(-1, 1, size=(SLOTS, b, 2)).astype(np.float32)
     for i in range(3):
         env.step_host(host_actions[i % SLOTS])
     if world > 1:

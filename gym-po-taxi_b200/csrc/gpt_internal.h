@@ -24,7 +24,7 @@ struct HostPath {  // gpt_step_host(): chunked H2D -> step -> D2H pipeline
   cudaStream_t streams[kStreams] = {};
   cudaEvent_t done[kStreams] = {};
   void* d_actions = nullptr;  // device staging for the host actions (capacity rows)
-  int n_chunks = 4;
+  int n_chunks = 2;
   bool ready = false;
 };
 
