@@ -75,9 +75,39 @@ class ClockSampler(threading.Thread):
             self.ok = True
         except Exception:
             self.ok = False
+        self.smi = None
+        if not self.ok:   # fall back to the nvidia-smi query of the profiling recipe
+            try:
+                self.smi = subprocess.Popen(
+                    ["nvidia-smi", f"--id={index}", "--query-gpu=clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
+                     "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+                     "clocks_event_reasons.sw_power_cap", "--format=csv,noheader,nounits", "-lms", "100"],
+                    stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            except Exception:
+                self.smi = None
+
+    def _run_smi(self):
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.smi.stdout:
+            if self._stop_evt.is_set():
+                break
+            if not self.active.is_set():
+                continue
+            f = [x.strip() for x in line.split(",")]
+            try:
+                self.samples.append(int(float(f[0])))
+                self.max_mhz = int(float(f[1]))
+                for n, v in zip(names, f[2:6]):
+                    if v.lower().startswith("active"):
+                        self.reasons.add(n)
+                self.ok = True
+            except Exception:
+                pass
 
     def run(self):
         if not self.ok:
+            if self.smi is not None:
+                self._run_smi()
             return
         while not self._stop_evt.is_set():
             if self.active.is_set():
@@ -93,6 +123,11 @@ class ClockSampler(threading.Thread):
 
     def stop(self):
         self._stop_evt.set()
+        if self.smi is not None:
+            try:
+                self.smi.terminate()
+            except Exception:
+                pass
 
     def summary(self):
         if not self.ok or not self.samples:

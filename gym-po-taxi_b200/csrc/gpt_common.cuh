@@ -33,15 +33,36 @@ __device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
   return c;
 }
 
+// The key is the same for every thread of a launch, so the host expands the ten round keys once
+// (key + r*W) and passes them in the kernel parameters: each round reads its key straight from the
+// constant bank instead of spending two integer adds per round per call.
 struct RngKey {
-  uint32_t seed_lo, seed_hi;   // Philox key
+  uint32_t rk[20];             // rk[2r], rk[2r+1] = Philox key words of round r
   uint32_t step_lo, step_hi;   // step counter (incremented by the host once per launch / per step)
 };
+__host__ __device__ inline void expand_round_keys(RngKey& k, uint64_t seed) {
+  uint32_t x = (uint32_t)seed, y = (uint32_t)(seed >> 32);
+  for (int r = 0; r < 10; ++r) {
+    k.rk[2 * r] = x;
+    k.rk[2 * r + 1] = y;
+    x += 0x9E3779B9u;
+    y += 0xBB67AE85u;
+  }
+}
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, const RngKey& k) {
+  constexpr uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u;
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(M0, c.x), lo0 = M0 * c.x;
+    const uint32_t hi1 = __umulhi(M1, c.z), lo1 = M1 * c.z;
+    c = make_uint4(hi1 ^ c.y ^ k.rk[2 * r], lo1, hi0 ^ c.w ^ k.rk[2 * r + 1], lo0);
+  }
+  return c;
+}
 
 // one Philox block for (global env id, step, stream)
 __device__ __forceinline__ uint4 env_random(const RngKey& k, uint64_t env, uint32_t stream) {
-  return philox4x32_10(make_uint4((uint32_t)env, (uint32_t)(env >> 32), k.step_lo, k.step_hi ^ (stream << 24)),
-                       make_uint2(k.seed_lo, k.seed_hi));
+  return philox4x32_10(make_uint4((uint32_t)env, (uint32_t)(env >> 32), k.step_lo, k.step_hi ^ (stream << 24)), k);
 }
 
 // unbiased-enough bounded integer: floor(u * n / 2^32); bias <= n * 2^-32

@@ -123,10 +123,12 @@ __global__ void __launch_bounds__(128) crooms_step_kernel(const __grid_constant_
           a2 = a2 < n ? a2 : n - 1;
         } else {
           const uint4 rs = env_random(P.rng, (uint64_t)(P.env_offset + env), 3u);
-          const uint32_t* row = T.thr32 + a * n;
-          for (uint32_t s = n >> 1; s > 0; s >>= 1) a2 += row[a2 + s - 1] < rs.x ? s : 0u;
+          const uint32_t* row = T.thr32 + a * 8;   // 8-wide rows in ordinal-direction units (gpt_rooms.cu)
+          a2 = row[3] < rs.x ? 4u : 0u;
+          a2 += row[a2 + 1] < rs.x ? 2u : 0u;
+          a2 += row[a2] < rs.x ? 1u : 0u;
         }
-        const uint32_t d8 = n == 4 ? a2 * 2 : a2;
+        const uint32_t d8 = (REPLAY && n == 4) ? a2 * 2 : a2;
         push = make_double2((double)dir_dy(d8), (double)dir_dx(d8));
       } else if (P.act_kind == kActF32) {
         const float2 a = reinterpret_cast<const float2*>(P.actions)[env];

@@ -102,8 +102,7 @@ inline uint32_t blob_append(std::vector<uint8_t>& blob, const std::vector<T>& v)
 
 inline RngKey make_rng_key(const gpt_env* env) {
   RngKey k;
-  k.seed_lo = (uint32_t)env->cfg.seed;
-  k.seed_hi = (uint32_t)(env->cfg.seed >> 32);
+  expand_round_keys(k, env->cfg.seed);
   k.step_lo = (uint32_t)env->counter;
   k.step_hi = (uint32_t)(env->counter >> 32) & 0x00FFFFFFu;
   return k;

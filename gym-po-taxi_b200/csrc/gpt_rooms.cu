@@ -52,11 +52,17 @@ int rooms_build_tables(gpt_env* env, const gpt_config* c, bool discrete_actions)
     if (n != 4 && n != 8) return fail(GPT_E_ARG, "rooms: n_actions must be 4 (cardinal) or 8 (ordinal)");
     if (!c->rooms_slip_cumsum) return fail(GPT_E_ARG, "rooms: slip_cumsum missing");
     thr64.assign(c->rooms_slip_cumsum, c->rooms_slip_cumsum + n * n);
-    thr32.resize(n * n);
-    for (int i = 0; i < n * n; ++i) {
-      const double t = thr64[i] * 4294967296.0;
-      thr32[i] = t >= 4294967295.0 ? 0xFFFFFFFFu : (t <= 0 ? 0u : (uint32_t)t);  // floor
-    }
+    // Philox-mode thresholds: rows of 8 in ordinal-direction units.  a' = min(#{T_j < u}, n-1) means the
+    // last threshold never counts, i.e. it is +inf (0xFFFFFFFF); a cardinal env stores every threshold
+    // twice so that the count comes out as the ordinal direction 2a'.
+    thr32.assign(n * 8, 0xFFFFFFFFu);
+    const int rep = 8 / n;
+    for (int a = 0; a < n; ++a)
+      for (int j = 0; j + 1 < n; ++j) {
+        const double t = thr64[a * n + j] * 4294967296.0;
+        const uint32_t q32 = t >= 4294967295.0 ? 0xFFFFFFFFu : (t <= 0 ? 0u : (uint32_t)t);  // floor
+        for (int r = 0; r < rep; ++r) thr32[a * 8 + j * rep + r] = q32;
+      }
   }
   // walkable-bit rows padded by the window radius (grid obs)
   std::vector<uint64_t> rows;

@@ -334,8 +334,7 @@ __global__ void __launch_bounds__(RoomsShape<OBS, GRID_N>::kThreads, STATS ? 1 :
     uint4 slip = make_uint4(0, 0, 0, 0);
     if (!REPLAY) {  // one Philox block feeds the slip draws of the 4 envs of this quad
       const uint64_t gq = (uint64_t)(P.env_offset + q) >> 2;
-      slip = philox4x32_10(make_uint4((uint32_t)gq, (uint32_t)(gq >> 32), P.rng.step_lo, P.rng.step_hi),
-                           make_uint2(P.rng.seed_lo, P.rng.seed_hi));
+      slip = philox4x32_10(make_uint4((uint32_t)gq, (uint32_t)(gq >> 32), P.rng.step_lo, P.rng.step_hi), P.rng);
     }
     const uint32_t slipv[4] = {slip.x, slip.y, slip.z, slip.w};
 
@@ -356,12 +355,14 @@ __global__ void __launch_bounds__(RoomsShape<OBS, GRID_N>::kThreads, STATS ? 1 :
         for (uint32_t i = 0; i < n; ++i) a2 += row[i] < u ? 1u : 0u;
         a2 = a2 < n ? a2 : n - 1;
       } else {
-        const uint32_t* row = T.thr32 + a * n;
-        if (n == 8) a2 = row[3] < slipv[k] ? 4u : 0u;
+        // thr32 rows are always 8 wide and already in ORDINAL-direction units (cardinal envs: each
+        // threshold twice), last entry 0xFFFFFFFF (= the clamp), so the 3-step search yields the direction
+        const uint32_t* row = T.thr32 + a * 8;
+        a2 = row[3] < slipv[k] ? 4u : 0u;
         a2 += row[a2 + 1] < slipv[k] ? 2u : 0u;
         a2 += row[a2] < slipv[k] ? 1u : 0u;
       }
-      const uint32_t mv = move[cellv[k] * 8 + (a2 << dir_shift)];   // grid[proposed] == -1 -> stay (rooms.py:212-213, :224-226)
+      const uint32_t mv = move[cellv[k] * 8 + (REPLAY ? (a2 << dir_shift) : a2)];   // grid[proposed] == -1 -> stay (rooms.py:212-213, :224-226)
       const bool blocked = (mv & 0x8000u) != 0;
       cellv[k] = mv & 0x7FFFu;
       const bool at_goal = cellv[k] == gcell;             // (:216)
