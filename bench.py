@@ -36,10 +36,14 @@ WORKLOADS = {
                           desc="FourRooms '4' discrete, hansen8 obs, 0.2 action-slip, fixed goal, Philox RNG"),
     "rooms_grid5": dict(alg_bytes=19 + 25, n_act=8, dtype="u8", cpu_family="rooms_grid5",
                         desc="FourRooms '4', 5x5 egocentric window obs, 0.2 action-slip, fixed goal"),
-    "crooms": dict(alg_bytes=70, n_act=0, dtype="f64", cpu_family="crooms",
-                   desc="continuous ROOMS '4' (float64 positions, Gaussian action noise 0.2, wall rejection), vector_mdp obs, yx float32 actions"),
-    "tag": dict(alg_bytes=102, n_act=0, dtype="f64", cpu_family="tag",
-                desc="point-mass Tag (AntTag pursuit rules, float64), yx float32 actions"),
+    "crooms": dict(alg_bytes=46, n_act=0, dtype="f32", cpu_family="crooms",
+                   desc="continuous ROOMS '4' (float32 fast mode, Gaussian action noise 0.2, wall rejection), vector_mdp obs, yx float32 actions"),
+    "tag": dict(alg_bytes=62, n_act=0, dtype="f32", cpu_family="tag",
+                desc="point-mass Tag (AntTag pursuit rules, float32 fast mode), yx float32 actions"),
+    "crooms_f64": dict(alg_bytes=70, n_act=0, dtype="f64", cpu_family="crooms",
+                       desc="continuous ROOMS '4' (float64 parity mode), vector_mdp obs, yx float32 actions"),
+    "tag_f64": dict(alg_bytes=102, n_act=0, dtype="f64", cpu_family="tag",
+                    desc="point-mass Tag (float64 parity mode), yx float32 actions"),
     "rooms_grid9": dict(alg_bytes=19 + 81, n_act=8, dtype="u8", cpu_family="rooms_grid9",
                         desc="FourRooms '4', 9x9 egocentric window obs, 0.2 action-slip, fixed goal"),
 }
@@ -183,12 +187,13 @@ def make_env(workload, b, rank, seed=0):
         return RoomsEnv(b, "4", obs_type="grid", obs_n=5, seed=seed, env_offset=rank * b)
     if workload == "rooms_grid9":
         return RoomsEnv(b, "4", obs_type="grid", obs_n=9, seed=seed, env_offset=rank * b)
-    if workload == "crooms":
+    if workload in ("crooms", "crooms_f64"):
         from gym_po.envs import CRoomsEnv
-        return CRoomsEnv(b, "4", obs_type="vector_mdp", seed=seed, env_offset=rank * b)
-    if workload == "tag":
+        return CRoomsEnv(b, "4", obs_type="vector_mdp", seed=seed, env_offset=rank * b,
+                         precision="float64" if workload.endswith("f64") else "float32")
+    if workload in ("tag", "tag_f64"):
         from gym_po.envs import TagVecEnv
-        return TagVecEnv(b, seed=seed, env_offset=rank * b)
+        return TagVecEnv(b, seed=seed, env_offset=rank * b, precision="float64" if workload.endswith("f64") else "float32")
     raise KeyError(workload)
 
 

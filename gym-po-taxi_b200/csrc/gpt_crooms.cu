@@ -8,7 +8,10 @@
 // bit-identical.  TAG = the pursuit rules of AntTagEnv (ant_tag.py:105-123, :144-153) on a point mass
 // that moves with the CROOMS motion model (see oracle/tag.py and DESIGN.md).
 //
-// HBM layout: agent double2 [cap] | goal double2 [cap] (random-goal envs) | velocity double2 [cap]
+// Precision is a template parameter: float64 (default; bit-exact parity with numpy) or float32 (fast mode:
+// half the state bytes, single-precision Box-Muller; checked against the oracle within 1e-5 relative).
+//
+// HBM layout: agent real2 [cap] | goal real2 [cap] (random-goal envs) | velocity real2 [cap]
 // (use_velocity) | elapsed int32 | action (int8 | float32x2 | float64x2)  ->  the same state arrays,
 // obs, reward float32, terminated uint8, truncated uint8.  One thread handles 4 consecutive envs.
 #include "gpt_rooms_kernel.cuh"
@@ -17,10 +20,20 @@ namespace gpt {
 
 enum : int { kActI8 = 0, kActF32 = 1, kActF64 = 2 };
 
+template <typename R> struct RealTraits;
+template <> struct RealTraits<double> {
+  using V2 = double2;
+  static __device__ __forceinline__ V2 make(double a, double b) { return make_double2(a, b); }
+};
+template <> struct RealTraits<float> {
+  using V2 = float2;
+  static __device__ __forceinline__ V2 make(float a, float b) { return make_float2(a, b); }
+};
+
 struct CRoomsParams {
-  double2* agent;
-  double2* goal;
-  double2* velocity;
+  void* agent;      // real2 [cap]
+  void* goal;       // real2 [cap] (random-goal envs)
+  void* velocity;   // real2 [cap] (use_velocity)
   int32_t* elapsed;
   const void* actions;
   void* obs;
@@ -54,10 +67,28 @@ __device__ __forceinline__ double2 normal_pair(uint4 r) {
   return make_double2(rad * c, rad * s);
 }
 
-__device__ __forceinline__ double clipd(double v, double lo, double hi) { return fmin(fmax(v, lo), hi); }
+// float32 mode: 24-bit uniforms, tails reach 5.8 sigma
+__device__ __forceinline__ float2 normal_pair_f(uint4 r) {
+  const float u1 = ((float)(r.x >> 8) + 1.0f) * (1.0f / 16777216.0f);   // (0,1]
+  const float u2 = (float)(r.y >> 8) * (1.0f / 16777216.0f);            // [0,1)
+  const float rad = sqrtf(-2.0f * logf(u1));
+  float s, c;
+  sincospif(2.0f * u2, &s, &c);
+  return make_float2(rad * c, rad * s);
+}
+template <typename R> __device__ __forceinline__ typename RealTraits<R>::V2 normal2(uint4 r);
+template <> __device__ __forceinline__ double2 normal2<double>(uint4 r) { return normal_pair(r); }
+template <> __device__ __forceinline__ float2 normal2<float>(uint4 r) { return normal_pair_f(r); }
 
-template <int OBS, bool REPLAY>
+template <typename R> __device__ __forceinline__ R clipd(R v, R lo, R hi) { return fmin(fmax(v, lo), hi); }
+
+template <typename R, int OBS, bool REPLAY>
 __global__ void __launch_bounds__(128) crooms_step_kernel(const __grid_constant__ CRoomsParams P) {
+  using V2 = typename RealTraits<R>::V2;
+  V2* const agent_p = reinterpret_cast<V2*>(P.agent);
+  V2* const goal_p = reinterpret_cast<V2*>(P.goal);
+  V2* const vel_p = reinterpret_cast<V2*>(P.velocity);
+  const R cell_size = (R)P.cell_size;
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ uint64_t bar;
   stage_tables_begin(smem, P.blob, P.blob_bytes, &bar);
@@ -100,16 +131,16 @@ __global__ void __launch_bounds__(128) crooms_step_kernel(const __grid_constant_
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
     const int64_t env = q + k;
-    double2 pos = make_double2(0, 0), vel = make_double2(0, 0);
-    double2 gpos = make_double2(P.goal_y, P.goal_x);
+    V2 pos = RealTraits<R>::make(0, 0), vel = RealTraits<R>::make(0, 0);
+    V2 gpos = RealTraits<R>::make((R)P.goal_y, (R)P.goal_x);
     bool again = reset_all;
     if (!reset_all) {
-      pos = P.agent[env];
-      if (P.rgoal) gpos = P.goal[env];
-      if (P.use_velocity) vel = P.velocity[env];
+      pos = agent_p[env];
+      if (P.rgoal) gpos = goal_p[env];
+      if (P.use_velocity) vel = vel_p[env];
       ev[k] += 1;
       // ---- noisy action (crooms.py:175-178 / :188-196) ----
-      double2 push;
+      V2 push;
       uint4 r0 = make_uint4(0, 0, 0, 0);
       if (!REPLAY) r0 = env_random(P.rng, (uint64_t)(P.env_offset + env), 0u);
       if (P.act_kind == kActI8) {
@@ -129,61 +160,64 @@ __global__ void __launch_bounds__(128) crooms_step_kernel(const __grid_constant_
           a2 += row[a2] < rs.x ? 1u : 0u;
         }
         const uint32_t d8 = (REPLAY && n == 4) ? a2 * 2 : a2;
-        push = make_double2((double)dir_dy(d8), (double)dir_dx(d8));
+        push = RealTraits<R>::make((R)dir_dy(d8), (R)dir_dx(d8));
       } else if (P.act_kind == kActF32) {
         const float2 a = reinterpret_cast<const float2*>(P.actions)[env];
-        push = make_double2((double)a.x, (double)a.y);
+        push = RealTraits<R>::make((R)a.x, (R)a.y);
       } else {
-        push = reinterpret_cast<const double2*>(P.actions)[env];
+        const double2 a = reinterpret_cast<const double2*>(P.actions)[env];
+        push = RealTraits<R>::make((R)a.x, (R)a.y);
       }
       if (P.has_noise) {
-        double2 z;
+        V2 z;
         if (REPLAY) {
-          z = P.rp_noise[env];                 // already scaled by action_std (numpy normal(scale=std))
+          const double2 zz = P.rp_noise[env];  // already scaled by action_std (numpy normal(scale=std))
+          z = RealTraits<R>::make((R)zz.x, (R)zz.y);
         } else {
-          z = normal_pair(r0);
-          z.x *= P.action_std;
-          z.y *= P.action_std;
+          z = normal2<R>(r0);
+          z.x *= (R)P.action_std;
+          z.y *= (R)P.action_std;
         }
         push.x = push.x + z.x;
         push.y = push.y + z.y;
       }
-      push.x = push.x * P.action_power;
-      push.y = push.y * P.action_power;
+      push.x = push.x * (R)P.action_power;
+      push.y = push.y * (R)P.action_power;
       // ---- _apply_action (crooms.py:300-331) ----
-      double2 target;
+      V2 target;
       if (P.use_velocity) {
-        vel.x = clipd(vel.x + push.x, -5.0, 5.0);
-        vel.y = clipd(vel.y + push.y, -5.0, 5.0);
-        target = make_double2(pos.x + vel.x, pos.y + vel.y);
+        vel.x = clipd<R>(vel.x + push.x, (R)-5.0, (R)5.0);
+        vel.y = clipd<R>(vel.y + push.y, (R)-5.0, (R)5.0);
+        target = RealTraits<R>::make(pos.x + vel.x, pos.y + vel.y);
       } else {
-        target = make_double2(pos.x + push.x, pos.y + push.y);
+        target = RealTraits<R>::make(pos.x + push.x, pos.y + push.y);
       }
-      target.x = clipd(target.x, 0.0, P.max_y);
-      target.y = clipd(target.y, 0.0, P.max_x);
-      const int ty = (int)floor(target.x / P.cell_size), tx = (int)floor(target.y / P.cell_size);
+      target.x = clipd<R>(target.x, (R)0.0, (R)P.max_y);
+      target.y = clipd<R>(target.y, (R)0.0, (R)P.max_x);
+      const int ty = (int)floor(target.x / cell_size), tx = (int)floor(target.y / cell_size);
       const bool blocked = grid[ty * P.w + tx] < 0;
       if (!blocked) {
         pos = target;
       } else {  // stay in the current cell at a jittered position, velocity zeroed (:317-330)
-        const double half = P.cell_size / 2;
-        const double cy = floor(pos.x / P.cell_size) * P.cell_size + half;
-        const double cx = floor(pos.y / P.cell_size) * P.cell_size + half;
-        double2 z;
+        const R half = cell_size / 2;
+        const R cy = floor(pos.x / cell_size) * cell_size + half;
+        const R cx = floor(pos.y / cell_size) * cell_size + half;
+        V2 z;
         if (REPLAY) {
-          z = P.rp_resample[env];              // normal(scale=0.5)
+          const double2 zz = P.rp_resample[env];   // normal(scale=0.5)
+          z = RealTraits<R>::make((R)zz.x, (R)zz.y);
         } else {
-          z = normal_pair(env_random(P.rng, (uint64_t)(P.env_offset + env), 2u));
-          z.x *= 0.5;
-          z.y *= 0.5;
+          z = normal2<R>(env_random(P.rng, (uint64_t)(P.env_offset + env), 2u));
+          z.x *= (R)0.5;
+          z.y *= (R)0.5;
         }
-        pos.x = clipd(cy + z.x, cy - half, cy + half - 1e-8);
-        pos.y = clipd(cx + z.y, cx - half, cx + half - 1e-8);
-        vel = make_double2(0, 0);
+        pos.x = clipd<R>(cy + z.x, cy - half, cy + half - (R)1e-8);
+        pos.y = clipd<R>(cx + z.y, cx - half, cx + half - (R)1e-8);
+        vel = RealTraits<R>::make(0, 0);
       }
       // ---- reward / done (:290-296) ----
-      const double dy = pos.x - gpos.x, dx = pos.y - gpos.y;
-      const bool at_goal = sqrt(dy * dy + dx * dx) <= P.goal_threshold;
+      const R dy = pos.x - gpos.x, dx = pos.y - gpos.y;
+      const bool at_goal = sqrt(dy * dy + dx * dx) <= (R)P.goal_threshold;
       rv[k] = at_goal ? P.r_goal : (blocked ? P.r_wall : P.r_step);
       const bool trunc = ev[k] > P.time_limit;
       tw |= (at_goal ? 1u : 0u) << (8 * k);
@@ -203,25 +237,25 @@ __global__ void __launch_bounds__(128) crooms_step_kernel(const __grid_constant_
       }
       if (P.rgoal) {
         const uint32_t y = fdiv(gc, P.div_w);
-        gpos = make_double2((double)y + 0.5, (double)(gc - y * P.w) + 0.5);
+        gpos = RealTraits<R>::make((R)y + (R)0.5, (R)(gc - y * P.w) + (R)0.5);
       }
       const uint32_t y = fdiv(ac, P.div_w);
-      pos = make_double2((double)y + 0.5, (double)(ac - y * P.w) + 0.5);
-      vel = make_double2(0, 0);
+      pos = RealTraits<R>::make((R)y + (R)0.5, (R)(ac - y * P.w) + (R)0.5);
+      vel = RealTraits<R>::make(0, 0);
     }
-    P.agent[env] = pos;
-    if (P.rgoal) P.goal[env] = gpos;
-    if (P.use_velocity) P.velocity[env] = vel;
+    agent_p[env] = pos;
+    if (P.rgoal) goal_p[env] = gpos;
+    if (P.use_velocity) vel_p[env] = vel;
 
     // ---- observation ----
     if constexpr (OBS == GPT_OBS_VEC_MDP) {
-      reinterpret_cast<double2*>(P.obs)[env] = pos;
+      reinterpret_cast<V2*>(P.obs)[env] = pos;
     } else if constexpr (OBS == GPT_OBS_VEC_MDP_GOAL) {
-      reinterpret_cast<double2*>(P.obs)[2 * env] = pos;
-      reinterpret_cast<double2*>(P.obs)[2 * env + 1] = gpos;
+      reinterpret_cast<V2*>(P.obs)[2 * env] = pos;
+      reinterpret_cast<V2*>(P.obs)[2 * env + 1] = gpos;
     } else {
-      const uint32_t cell = (uint32_t)((int)floor(pos.x / P.cell_size) * P.w + (int)floor(pos.y / P.cell_size));
-      const uint32_t gcell = (uint32_t)((int)floor(gpos.x / P.cell_size) * P.w + (int)floor(gpos.y / P.cell_size));
+      const uint32_t cell = (uint32_t)((int)floor(pos.x / cell_size) * P.w + (int)floor(pos.y / cell_size));
+      const uint32_t gcell = (uint32_t)((int)floor(gpos.x / cell_size) * P.w + (int)floor(gpos.y / cell_size));
       cell_obs<OBS, 0>(T, OC, cell, gcell, stage + (uint32_t)(lane * kQuad + k) * (uint32_t)(gn * gn), o32[k], o32b[k]);
     }
   }
@@ -239,11 +273,11 @@ __global__ void __launch_bounds__(128) crooms_step_kernel(const __grid_constant_
 // Tag
 // ------------------------------------------------------------------------------------------
 struct TagParams {
-  double2* agent;
-  double2* target;
+  void* agent;    // real2 [cap]
+  void* target;   // real2 [cap]
   int32_t* elapsed;
   const void* actions;
-  double2* obs;
+  void* obs;      // real2 [cap]
   float* reward;
   uint8_t* terminated;
   uint8_t* truncated;
@@ -257,10 +291,14 @@ struct TagParams {
   RngKey rng;
 };
 
-constexpr double kCage = 4.5, kVisible = 3.0, kTagRadius = 1.5, kMinSpawn = 5.0, kTargetStep = 0.5, kArena = 5.0;
 
-template <bool REPLAY>
+template <typename R, bool REPLAY>
 __global__ void __launch_bounds__(128) tag_step_kernel(const __grid_constant__ TagParams P) {
+  using V2 = typename RealTraits<R>::V2;
+  V2* const agent_p = reinterpret_cast<V2*>(P.agent);
+  V2* const target_p = reinterpret_cast<V2*>(P.target);
+  V2* const obs_p = reinterpret_cast<V2*>(P.obs);
+  constexpr R kCage = (R)4.5, kVisible = (R)3.0, kTagRadius = (R)1.5, kMinSpawn = (R)5.0, kTargetStep = (R)0.5, kArena = (R)5.0;
   const int64_t first = (int64_t)P.first_tile * kTileEnvs, last = first + (int64_t)P.n_tiles * kTileEnvs;
   const int64_t q = first + ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * kQuad;
   if (q >= last) return;
@@ -275,48 +313,50 @@ __global__ void __launch_bounds__(128) tag_step_kernel(const __grid_constant__ T
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
     const int64_t env = q + k;
-    double2 pos = make_double2(0, 0), tgt = make_double2(0, 0);
+    V2 pos = RealTraits<R>::make(0, 0), tgt = RealTraits<R>::make(0, 0);
     bool again = reset_all;
     if (!reset_all) {
-      pos = P.agent[env];
-      tgt = P.target[env];
+      pos = agent_p[env];
+      tgt = target_p[env];
       ev[k] += 1;
       uint4 r0 = make_uint4(0, 0, 0, 0);
       if (!REPLAY) r0 = env_random(P.rng, (uint64_t)(P.env_offset + env), 0u);
-      double2 push;
+      V2 push;
       if (P.act_kind == kActF32) {
         const float2 a = reinterpret_cast<const float2*>(P.actions)[env];
-        push = make_double2((double)a.x, (double)a.y);
+        push = RealTraits<R>::make((R)a.x, (R)a.y);
       } else {
-        push = reinterpret_cast<const double2*>(P.actions)[env];
+        const double2 a = reinterpret_cast<const double2*>(P.actions)[env];
+        push = RealTraits<R>::make((R)a.x, (R)a.y);
       }
-      double2 z;
+      V2 z;
       if (REPLAY) {
-        z = P.rp_noise[env];
+        const double2 zz = P.rp_noise[env];
+        z = RealTraits<R>::make((R)zz.x, (R)zz.y);
       } else {
-        z = normal_pair(r0);
-        z.x *= P.action_std;
-        z.y *= P.action_std;
+        z = normal2<R>(r0);
+        z.x *= (R)P.action_std;
+        z.y *= (R)P.action_std;
       }
-      push.x = (push.x + z.x) * P.action_power;
-      push.y = (push.y + z.y) * P.action_power;
-      pos.x = clipd(pos.x + push.x, -kArena, kArena);
-      pos.y = clipd(pos.y + push.y, -kArena, kArena);
+      push.x = (push.x + z.x) * (R)P.action_power;
+      push.y = (push.y + z.y) * (R)P.action_power;
+      pos.x = clipd<R>(pos.x + push.x, -kArena, kArena);
+      pos.y = clipd<R>(pos.y + push.y, -kArena, kArena);
       // target moves relative to the agent's NEW position (ant_tag.py:105-123, :139-141)
       uint32_t choice;
       if (REPLAY) choice = (uint32_t)P.rp_choice[env];
       else choice = env_random(P.rng, (uint64_t)(P.env_offset + env), 3u).x >> 30;
-      double vx = pos.x - tgt.x, vy = pos.y - tgt.y;
-      const double nrm = sqrt(vx * vx + vy * vy);
+      R vx = pos.x - tgt.x, vy = pos.y - tgt.y;
+      const R nrm = sqrt(vx * vx + vy * vy);
       vx = vx / nrm;
       vy = vy / nrm;
-      double mx = 0.0, my = 0.0;
+      R mx = 0, my = 0;
       if (choice == 0) { mx = -vx; my = -vy; }
       else if (choice == 1) { mx = vy; my = -vx; }
       else if (choice == 2) { mx = -vy; my = vx; }
-      const double nx = mx * kTargetStep + tgt.x, ny = my * kTargetStep + tgt.y;
-      if (!(fabs(nx) > kCage || fabs(ny) > kCage)) tgt = make_double2(nx, ny);
-      const double dx = pos.x - tgt.x, dy = pos.y - tgt.y;
+      const R nx = mx * kTargetStep + tgt.x, ny = my * kTargetStep + tgt.y;
+      if (!(fabs(nx) > kCage || fabs(ny) > kCage)) tgt = RealTraits<R>::make(nx, ny);
+      const R dx = pos.x - tgt.x, dy = pos.y - tgt.y;
       const bool tagged = sqrt(dx * dx + dy * dy) <= kTagRadius;     // (:147-150)
       rv[k] = tagged ? 1.f : 0.f;
       const bool trunc = ev[k] >= P.time_limit;                       // gymnasium TimeLimit (envs/__init__.py:15-19)
@@ -327,27 +367,28 @@ __global__ void __launch_bounds__(128) tag_step_kernel(const __grid_constant__ T
     if (again) {  // reset_model (ant_tag.py:88-103): target redrawn while within min distance
       ev[k] = 0;
       if (REPLAY) {
-        pos = P.rp_spawn_agent[env];
-        tgt = P.rp_spawn_target[env];
+        const double2 sa = P.rp_spawn_agent[env], st = P.rp_spawn_target[env];
+        pos = RealTraits<R>::make((R)sa.x, (R)sa.y);
+        tgt = RealTraits<R>::make((R)st.x, (R)st.y);
       } else {
         const uint4 r = env_random(P.rng, (uint64_t)(P.env_offset + env), 1u);
-        const double s = 2.0 * kCage / 4294967296.0;
-        pos = make_double2((double)r.x * s - kCage, (double)r.y * s - kCage);
+        const double s = 2.0 * 4.5 / 4294967296.0;
+        pos = RealTraits<R>::make((R)((double)r.x * s - 4.5), (R)((double)r.y * s - 4.5));
         uint32_t attempt = 0;
         do {
           const uint4 t = env_random(P.rng, (uint64_t)(P.env_offset + env), 16u + (attempt >> 1));
-          tgt = (attempt & 1u) ? make_double2((double)t.z * s - kCage, (double)t.w * s - kCage)
-                               : make_double2((double)t.x * s - kCage, (double)t.y * s - kCage);
+          tgt = (attempt & 1u) ? RealTraits<R>::make((R)((double)t.z * s - 4.5), (R)((double)t.w * s - 4.5))
+                               : RealTraits<R>::make((R)((double)t.x * s - 4.5), (R)((double)t.y * s - 4.5));
           ++attempt;
-          const double dx = pos.x - tgt.x, dy = pos.y - tgt.y;
+          const R dx = pos.x - tgt.x, dy = pos.y - tgt.y;
           if (sqrt(dx * dx + dy * dy) > kMinSpawn) break;
         } while (attempt < 400u);
       }
     }
-    P.agent[env] = pos;
-    P.target[env] = tgt;
-    const double dx = pos.x - tgt.x, dy = pos.y - tgt.y;
-    P.obs[env] = sqrt(dx * dx + dy * dy) < kVisible ? tgt : make_double2(0.0, 0.0);   // (:153, :83-85)
+    agent_p[env] = pos;
+    target_p[env] = tgt;
+    const R dx = pos.x - tgt.x, dy = pos.y - tgt.y;
+    obs_p[env] = sqrt(dx * dx + dy * dy) < kVisible ? tgt : RealTraits<R>::make(0, 0);   // (:153, :83-85)
   }
   st_stream(reinterpret_cast<int4*>(P.elapsed + q), make_int4(ev[0], ev[1], ev[2], ev[3]));
   if (!reset_all) {
@@ -379,13 +420,14 @@ int crooms_create(gpt_env* env, const gpt_config* c) {
       (kind == GPT_OBS_ROOM_GOAL || kind == GPT_OBS_MDP_GOAL))
     return fail(GPT_E_ARG, "crooms: goal-indexed observations need the fixed goal inside the grid");
   const int ak = action_kind(c);
-  add_array(env, "agent", GPT_ROLE_STATE, GPT_DT_F64, 2);
-  if (rgoal) add_array(env, "goal", GPT_ROLE_STATE, GPT_DT_F64, 2);
-  if (c->c_use_velocity) add_array(env, "velocity", GPT_ROLE_STATE, GPT_DT_F64, 2);
+  const int rdt = c->c_state_f32 ? GPT_DT_F32 : GPT_DT_F64;
+  add_array(env, "agent", GPT_ROLE_STATE, rdt, 2);
+  if (rgoal) add_array(env, "goal", GPT_ROLE_STATE, rdt, 2);
+  if (c->c_use_velocity) add_array(env, "velocity", GPT_ROLE_STATE, rdt, 2);
   add_array(env, "elapsed", GPT_ROLE_STATE, GPT_DT_I32, 1);
   switch (kind) {
-    case GPT_OBS_VEC_MDP: add_array(env, "obs", GPT_ROLE_OUTPUT, GPT_DT_F64, 2); break;
-    case GPT_OBS_VEC_MDP_GOAL: add_array(env, "obs", GPT_ROLE_OUTPUT, GPT_DT_F64, 4); break;
+    case GPT_OBS_VEC_MDP: add_array(env, "obs", GPT_ROLE_OUTPUT, rdt, 2); break;
+    case GPT_OBS_VEC_MDP_GOAL: add_array(env, "obs", GPT_ROLE_OUTPUT, rdt, 4); break;
     case GPT_OBS_ROOM: case GPT_OBS_ROOM_GOAL: case GPT_OBS_MDP: case GPT_OBS_MDP_GOAL: case GPT_OBS_HANSEN:
       add_array(env, "obs", GPT_ROLE_OUTPUT, GPT_DT_I32, 1); break;
     case GPT_OBS_VEC_HANSEN: case GPT_OBS_VEC_HANSEN_GOAL: add_array(env, "obs", GPT_ROLE_OUTPUT, GPT_DT_U8, c->rooms_obs_n); break;
@@ -407,9 +449,10 @@ int crooms_create(gpt_env* env, const gpt_config* c) {
 }
 
 template <int OBS>
-static void* pick_c(bool replay) {
+static void* pick_c(bool replay, bool f32) {
   using K = void (*)(const CRoomsParams);
-  return replay ? (void*)(K)crooms_step_kernel<OBS, true> : (void*)(K)crooms_step_kernel<OBS, false>;
+  if (f32) return replay ? (void*)(K)crooms_step_kernel<float, OBS, true> : (void*)(K)crooms_step_kernel<float, OBS, false>;
+  return replay ? (void*)(K)crooms_step_kernel<double, OBS, true> : (void*)(K)crooms_step_kernel<double, OBS, false>;
 }
 
 int crooms_launch(gpt_env* env, const LaunchArgs& a) {
@@ -417,9 +460,9 @@ int crooms_launch(gpt_env* env, const LaunchArgs& a) {
   const bool rgoal = c.rooms_goal_y < 0;
   const bool replay = c.rng_mode == GPT_RNG_REPLAY;
   CRoomsParams P{};
-  P.agent = (double2*)env->ptr("agent");
-  P.goal = rgoal ? (double2*)env->ptr("goal") : nullptr;
-  P.velocity = c.c_use_velocity ? (double2*)env->ptr("velocity") : nullptr;
+  P.agent = env->ptr("agent");
+  P.goal = rgoal ? env->ptr("goal") : nullptr;
+  P.velocity = c.c_use_velocity ? env->ptr("velocity") : nullptr;
   P.elapsed = (int32_t*)env->ptr("elapsed");
   P.actions = a.actions;
   P.obs = env->ptr("obs");
@@ -494,16 +537,16 @@ int crooms_launch(gpt_env* env, const LaunchArgs& a) {
   if (grid) smem = P.stage_off + (size_t)warps * kQuadStride * P.grid_n * P.grid_n;
   void* k = nullptr;
   switch (c.rooms_obs_kind) {
-    case GPT_OBS_ROOM: k = pick_c<GPT_OBS_ROOM>(replay); break;
-    case GPT_OBS_ROOM_GOAL: k = pick_c<GPT_OBS_ROOM_GOAL>(replay); break;
-    case GPT_OBS_MDP: k = pick_c<GPT_OBS_MDP>(replay); break;
-    case GPT_OBS_MDP_GOAL: k = pick_c<GPT_OBS_MDP_GOAL>(replay); break;
-    case GPT_OBS_VEC_MDP: k = pick_c<GPT_OBS_VEC_MDP>(replay); break;
-    case GPT_OBS_VEC_MDP_GOAL: k = pick_c<GPT_OBS_VEC_MDP_GOAL>(replay); break;
-    case GPT_OBS_HANSEN: k = pick_c<GPT_OBS_HANSEN>(replay); break;
-    case GPT_OBS_VEC_HANSEN: k = pick_c<GPT_OBS_VEC_HANSEN>(replay); break;
-    case GPT_OBS_VEC_HANSEN_GOAL: k = pick_c<GPT_OBS_VEC_HANSEN_GOAL>(replay); break;
-    case GPT_OBS_GRID: k = pick_c<GPT_OBS_GRID>(replay); break;
+    case GPT_OBS_ROOM: k = pick_c<GPT_OBS_ROOM>(replay, c.c_state_f32 != 0); break;
+    case GPT_OBS_ROOM_GOAL: k = pick_c<GPT_OBS_ROOM_GOAL>(replay, c.c_state_f32 != 0); break;
+    case GPT_OBS_MDP: k = pick_c<GPT_OBS_MDP>(replay, c.c_state_f32 != 0); break;
+    case GPT_OBS_MDP_GOAL: k = pick_c<GPT_OBS_MDP_GOAL>(replay, c.c_state_f32 != 0); break;
+    case GPT_OBS_VEC_MDP: k = pick_c<GPT_OBS_VEC_MDP>(replay, c.c_state_f32 != 0); break;
+    case GPT_OBS_VEC_MDP_GOAL: k = pick_c<GPT_OBS_VEC_MDP_GOAL>(replay, c.c_state_f32 != 0); break;
+    case GPT_OBS_HANSEN: k = pick_c<GPT_OBS_HANSEN>(replay, c.c_state_f32 != 0); break;
+    case GPT_OBS_VEC_HANSEN: k = pick_c<GPT_OBS_VEC_HANSEN>(replay, c.c_state_f32 != 0); break;
+    case GPT_OBS_VEC_HANSEN_GOAL: k = pick_c<GPT_OBS_VEC_HANSEN_GOAL>(replay, c.c_state_f32 != 0); break;
+    case GPT_OBS_GRID: k = pick_c<GPT_OBS_GRID>(replay, c.c_state_f32 != 0); break;
   }
   if (!k) return fail(GPT_E_ARG, "crooms: no kernel for this obs kind");
   if (smem > 40 * 1024) {  // static + dynamic shared memory above 48 KB needs the opt-in
@@ -519,10 +562,11 @@ int crooms_launch(gpt_env* env, const LaunchArgs& a) {
 
 int tag_create(gpt_env* env, const gpt_config* c) {
   if (c->track_stats) return fail(GPT_E_ARG, "tag: track_stats is implemented for the Taxi and ROOMS families only");
-  add_array(env, "agent", GPT_ROLE_STATE, GPT_DT_F64, 2);
-  add_array(env, "target", GPT_ROLE_STATE, GPT_DT_F64, 2);
+  const int rdt = c->c_state_f32 ? GPT_DT_F32 : GPT_DT_F64;
+  add_array(env, "agent", GPT_ROLE_STATE, rdt, 2);
+  add_array(env, "target", GPT_ROLE_STATE, rdt, 2);
   add_array(env, "elapsed", GPT_ROLE_STATE, GPT_DT_I32, 1);
-  add_array(env, "obs", GPT_ROLE_OUTPUT, GPT_DT_F64, 2);
+  add_array(env, "obs", GPT_ROLE_OUTPUT, rdt, 2);
   add_array(env, "reward", GPT_ROLE_OUTPUT, GPT_DT_F32, 1);
   add_array(env, "terminated", GPT_ROLE_OUTPUT, GPT_DT_U8, 1);
   add_array(env, "truncated", GPT_ROLE_OUTPUT, GPT_DT_U8, 1);
@@ -541,18 +585,18 @@ int tag_launch(gpt_env* env, const LaunchArgs& a) {
   const gpt_config& c = env->cfg;
   const bool replay = c.rng_mode == GPT_RNG_REPLAY;
   TagParams P{};
-  P.agent = (double2*)env->ptr("agent");
-  P.target = (double2*)env->ptr("target");
+  P.agent = env->ptr("agent");
+  P.target = env->ptr("target");
   P.elapsed = (int32_t*)env->ptr("elapsed");
   P.actions = a.actions;
-  P.obs = (double2*)env->ptr("obs");
+  P.obs = env->ptr("obs");
   P.reward = (float*)env->ptr("reward");
   P.terminated = (uint8_t*)env->ptr("terminated");
   P.truncated = (uint8_t*)env->ptr("truncated");
   if (!P.agent || !P.target || !P.elapsed || !P.obs || !P.reward || !P.terminated || !P.truncated)
     return fail(GPT_E_UNBOUND, "tag: state/output arrays must be bound before reset/step");
   if (a.mode == kModeStep && !P.actions) return fail(GPT_E_ARG, "tag: actions is NULL");
-  P.obs += a.out_row;
+  P.obs = (uint8_t*)P.obs + a.out_row * (c.c_state_f32 ? sizeof(float2) : sizeof(double2));
   P.reward += a.out_row;
   P.terminated += a.out_row;
   P.truncated += a.out_row;
@@ -577,8 +621,13 @@ int tag_launch(gpt_env* env, const LaunchArgs& a) {
   const int64_t quads = (int64_t)a.n_tiles * (kTileEnvs / kQuad);
   const int nblocks = (int)((quads + threads - 1) / threads);
   if (nblocks <= 0) return GPT_OK;
-  if (replay) tag_step_kernel<true><<<nblocks, threads, 0, a.stream>>>(P);
-  else tag_step_kernel<false><<<nblocks, threads, 0, a.stream>>>(P);
+  if (c.c_state_f32) {
+    if (replay) tag_step_kernel<float, true><<<nblocks, threads, 0, a.stream>>>(P);
+    else tag_step_kernel<float, false><<<nblocks, threads, 0, a.stream>>>(P);
+  } else {
+    if (replay) tag_step_kernel<double, true><<<nblocks, threads, 0, a.stream>>>(P);
+    else tag_step_kernel<double, false><<<nblocks, threads, 0, a.stream>>>(P);
+  }
   env->launches += 1;
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return cuda_fail(e, "tag_step_kernel launch");

@@ -235,7 +235,7 @@ __device__ __forceinline__ void store_obs(void* obs, int64_t q, int64_t warp_qua
 #define GPT_ROOMS_QPT_GRID 4
 #endif
 #ifndef GPT_ROOMS_MINB_SCALAR
-#define GPT_ROOMS_MINB_SCALAR 10
+#define GPT_ROOMS_MINB_SCALAR 8
 #endif
 #ifndef GPT_ROOMS_MINB_GRID
 #define GPT_ROOMS_MINB_GRID 1

@@ -43,6 +43,7 @@ class GptConfig(C.Structure):
         # continuous
         ("c_cell_size", C.c_double), ("c_action_std", C.c_double), ("c_action_power", C.c_double),
         ("c_goal_threshold", C.c_double), ("c_use_velocity", C.c_int32), ("c_action_f64", C.c_int32),
+        ("c_state_f32", C.c_int32), ("c_pad", C.c_int32),
     ]
 
 

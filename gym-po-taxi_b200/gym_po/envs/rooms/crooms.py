@@ -34,11 +34,14 @@ class CRoomsEnv(DeviceVecEnv):
                  goal_xy: Optional[Sequence[int]] = (0, 0), step_reward: float = 0.0, wall_reward: float = 0.0,
                  goal_reward: float = 1.0, goal_threshold: float = 0.5, render_mode: Optional[str] = None, *,
                  device=None, rng_mode: str = "philox", seed: Optional[int] = None, env_offset: int = 0,
-                 track_stats: bool = False, action_dtype=torch.float32, **kwargs):
+                 track_stats: bool = False, action_dtype=torch.float32, precision: str = "float64", **kwargs):
         assert layout in LAYOUTS
         if agent_xy is not None:  # raises in the reference as well (crooms.py:232-235)
             raise ValueError("agent_xy is not supported (it raises in the reference as well)")
         self.metadata = dict(self.metadata, name=f"CRooms__{layout}__{action_type}__{obs_type}")
+        if precision not in ("float64", "float32"):
+            raise ValueError("precision must be 'float64' (bit-exact vs the reference) or 'float32' (fast)")
+        self._precision = precision
         self.num_envs = int(num_envs)
         self.grid = np_to_grid(layout_to_np(LAYOUTS[layout]))
         self.gridshape = np.array(self.grid.shape)
@@ -59,6 +62,7 @@ class CRoomsEnv(DeviceVecEnv):
             thr = slip_cumsum(acts.shape[0], action_failure_probability)
             cfg.rooms_slip_cumsum = thr.ctypes.data_as(C.POINTER(C.c_double))
             keep.append(thr)
+        cfg.c_state_f32 = int(precision == "float32")
         self.use_velocity = bool(use_velocity)
         self.action_space = batch_space(self.single_action_space, self.num_envs)
         self.observation_space = batch_space(self.single_observation_space, self.num_envs)
@@ -101,14 +105,14 @@ class CRoomsEnv(DeviceVecEnv):
     @property
     def goal_yx(self) -> torch.Tensor:
         if self.fixed_goal is not None:
-            g = torch.tensor(self.fixed_goal, device=self.device, dtype=torch.float64) + 0.5
+            g = torch.tensor(self.fixed_goal, device=self.device, dtype=self._arrays["agent"].dtype) + 0.5
             return g.expand(self.num_envs, 2).clone()
         return self._arrays["goal"][: self.num_envs]
 
     @property
     def agent_yx_velocity(self) -> torch.Tensor:
         if not self.use_velocity:
-            return torch.zeros((self.num_envs, 2), dtype=torch.float64, device=self.device)
+            return torch.zeros((self.num_envs, 2), dtype=self._arrays["agent"].dtype, device=self.device)
         return self._arrays["velocity"][: self.num_envs]
 
     @property
@@ -121,11 +125,11 @@ class CRoomsEnv(DeviceVecEnv):
 
     def set_state(self, agent, goal, velocity, elapsed):
         b = self.num_envs
-        self._arrays["agent"][:b].copy_(torch.as_tensor(np.asarray(agent, dtype=np.float64)))
+        self._arrays["agent"][:b].copy_(torch.as_tensor(np.asarray(agent, dtype=np.float64)).to(self._arrays["agent"].dtype))
         if self.fixed_goal is None:
-            self._arrays["goal"][:b].copy_(torch.as_tensor(np.asarray(goal, dtype=np.float64)))
+            self._arrays["goal"][:b].copy_(torch.as_tensor(np.asarray(goal, dtype=np.float64)).to(self._arrays["agent"].dtype))
         if self.use_velocity:
-            self._arrays["velocity"][:b].copy_(torch.as_tensor(np.asarray(velocity, dtype=np.float64)))
+            self._arrays["velocity"][:b].copy_(torch.as_tensor(np.asarray(velocity, dtype=np.float64)).to(self._arrays["agent"].dtype))
         self._arrays["elapsed"][:b].copy_(torch.as_tensor(np.asarray(elapsed)).to(torch.int32))
 
     def seed(self, seed: Optional[int] = None):

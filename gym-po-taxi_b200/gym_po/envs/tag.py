@@ -28,7 +28,10 @@ class TagVecEnv(DeviceVecEnv):
 
     def __init__(self, num_envs: int, time_limit: int = 500, action_std: float = 0.2, action_power: float = 1.0,
                  render_mode: Optional[str] = None, *, device=None, rng_mode: str = "philox", seed: Optional[int] = None,
-                 env_offset: int = 0, track_stats: bool = False, action_dtype=torch.float32):
+                 env_offset: int = 0, track_stats: bool = False, action_dtype=torch.float32, precision: str = "float64"):
+        if precision not in ("float64", "float32"):
+            raise ValueError("precision must be 'float64' or 'float32'")
+        self._precision = precision
         self.num_envs = int(num_envs)
         self.time_limit = time_limit
         self.render_mode = render_mode
@@ -41,6 +44,7 @@ class TagVecEnv(DeviceVecEnv):
         cfg.time_limit = int(time_limit)
         cfg.c_action_std, cfg.c_action_power = action_std, action_power
         cfg.c_action_f64 = int(action_dtype == torch.float64)
+        cfg.c_state_f32 = int(self._precision == "float32")
         self._create(cfg, device=device, rng_mode=rng_mode, seed=seed, env_offset=env_offset, track_stats=track_stats)
 
     @property
@@ -60,8 +64,8 @@ class TagVecEnv(DeviceVecEnv):
 
     def set_state(self, agent, target, elapsed):
         b = self.num_envs
-        self._arrays["agent"][:b].copy_(torch.as_tensor(np.asarray(agent, dtype=np.float64)))
-        self._arrays["target"][:b].copy_(torch.as_tensor(np.asarray(target, dtype=np.float64)))
+        self._arrays["agent"][:b].copy_(torch.as_tensor(np.asarray(agent, dtype=np.float64)).to(self._arrays["agent"].dtype))
+        self._arrays["target"][:b].copy_(torch.as_tensor(np.asarray(target, dtype=np.float64)).to(self._arrays["agent"].dtype))
         self._arrays["elapsed"][:b].copy_(torch.as_tensor(np.asarray(elapsed)).to(torch.int32))
 
     def reset(self, *, seed: Optional[int] = None, options: Optional[dict] = None):

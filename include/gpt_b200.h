@@ -65,8 +65,8 @@ extern "C" {
 #define GPT_OBS_ROOM_GOAL 1     /* grid[a] + n_rooms*grid[g]                int32 [B]      */
 #define GPT_OBS_MDP 2           /* dense cell id                            int32 [B]      */
 #define GPT_OBS_MDP_GOAL 3      /* id(a) + n_cells*id(g)                    int32 [B]      */
-#define GPT_OBS_VEC_MDP 4       /* (y,x)          uint8 [B,2]  (CROOMS: float64 [B,2])      */
-#define GPT_OBS_VEC_MDP_GOAL 5  /* (y,x,gy,gx)    uint8 [B,4]  (CROOMS: float64 [B,4])      */
+#define GPT_OBS_VEC_MDP 4       /* (y,x)          uint8 [B,2]  (CROOMS: real [B,2])      */
+#define GPT_OBS_VEC_MDP_GOAL 5  /* (y,x,gy,gx)    uint8 [B,4]  (CROOMS: real [B,4])      */
 #define GPT_OBS_HANSEN 6        /* sum(empty_i 2^i) * goal multiplier       int32 [B]      observations.py:44-71 */
 #define GPT_OBS_VEC_HANSEN 7    /* 0 wall / 1 empty per neighbour           uint8 [B,n]    observations.py:106-131 */
 #define GPT_OBS_VEC_HANSEN_GOAL 8 /* ... and 2 = goal                        uint8 [B,n]    */
@@ -132,6 +132,8 @@ typedef struct gpt_config {
   double c_cell_size, c_action_std, c_action_power, c_goal_threshold;
   int32_t c_use_velocity;
   int32_t c_action_f64; /* continuous (yx) actions are float32 [B,2] (0) or float64 [B,2] (1) */
+  int32_t c_state_f32;  /* 0: float64 positions (bit-exact vs the numpy reference); 1: float32 fast mode */
+  int32_t c_pad;
 } gpt_config;
 
 typedef struct gpt_array_desc {

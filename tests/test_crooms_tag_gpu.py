@@ -157,3 +157,85 @@ def test_tag_philox_invariants():
         vis = d < 3.0
         assert bool((obs[~vis] == 0).all()) and bool((obs[vis] == env.target_xy[vis]).all())
         assert bool((rew[term] == 1.0).all()) and bool((rew[~term] == 0.0).all())
+
+
+# ---- float32 fast mode: tolerance-checked against the float64 oracle ------------------------------
+# Stated tolerance: |gpu - oracle| <= 1e-5 * max(1, |oracle|) per coordinate after ONE step from an injected
+# (float32-representable) state with replayed draws, on every env whose discrete decisions (reward,
+# terminated, truncated) agree; decisions may legitimately flip when a float32 rounding moves a position
+# across a cell boundary / threshold — those envs are counted and must be rarer than 2e-4.
+F32_RTOL = 1e-5
+F32_FLIP_RATE = 2e-4
+
+
+def _close(g, o):
+    o = np.asarray(o, dtype=np.float64)
+    return np.abs(g.astype(np.float64) - o) <= F32_RTOL * np.maximum(1.0, np.abs(o))
+
+
+def test_crooms_float32_mode_within_tolerance():
+    from gym_po.envs import CRoomsEnv
+    b = 100_000
+    kw = dict(layout="8", obs_type="vector_mdp", action_type="yx", use_velocity=True, goal_xy=None, time_limit=12,
+              wall_reward=-0.3, step_reward=-0.01)
+    orc = oracle.CRoomsOracle(b, draws=oracle.GeneratorDraws(seed=3), **kw)
+    env = CRoomsEnv(b, device=DEV, rng_mode="replay", precision="float32", **kw)
+    assert env.agent_yx.dtype == torch.float32
+    o = orc.reset()
+    env.set_replay(**orc.draws)
+    np.testing.assert_array_equal(env.reset().cpu().numpy(), o.astype(np.float32))
+    rng = np.random.default_rng(1)
+    flips = total = 0
+    for t in range(40):
+        st = orc.state      # make the oracle start from the float32-rounded state the GPU holds
+        st = {k: (v.astype(np.float32).astype(np.float64) if v.dtype.kind == "f" else v) for k, v in st.items()}
+        orc.set_state(**st)
+        env.set_state(**st)
+        a = rng.uniform(-1, 1, (b, 2)).astype(np.float32)
+        oo, orew, oterm, otrunc, _ = orc.step(a.astype(np.float64))
+        env.set_replay(**orc.draws)
+        go, grew, gterm, gtrunc, _ = env.step(torch.as_tensor(a, device=DEV))
+        same = (grew.cpu().numpy() == orew) & (gterm.cpu().numpy() == oterm) & (gtrunc.cpu().numpy() == otrunc)
+        flips += int((~same).sum())
+        total += b
+        assert _close(go.cpu().numpy()[same], oo[same]).all(), f"step {t}"
+        assert _close(env.agent_yx_velocity.cpu().numpy()[same], orc.velocity[same]).all()
+    assert flips / total < F32_FLIP_RATE, flips / total
+
+
+def test_tag_float32_mode_within_tolerance_and_philox():
+    from gym_po.envs import TagVecEnv
+    b = 100_000
+    orc = oracle.TagOracle(b, time_limit=50, draws=oracle.GeneratorDraws(seed=5))
+    env = TagVecEnv(b, time_limit=50, device=DEV, rng_mode="replay", precision="float32")
+    orc.reset()
+    env.set_replay(**orc.draws)
+    env.reset()
+    rng = np.random.default_rng(2)
+    flips = total = 0
+    for t in range(60):
+        st = orc.state
+        st = {k: (v.astype(np.float32).astype(np.float64) if v.dtype.kind == "f" else v) for k, v in st.items()}
+        orc.set_state(**st)
+        env.set_state(**st)
+        a = np.clip(orc.target - orc.agent, -1, 1).astype(np.float32)
+        oo, orew, oterm, otrunc, _ = orc.step(a.astype(np.float64))
+        env.set_replay(**orc.draws)
+        go, grew, gterm, gtrunc, _ = env.step(torch.as_tensor(a, device=DEV))
+        vis_same = ((go.cpu().numpy() != 0).any(-1)) == ((oo != 0).any(-1))
+        same = (gterm.cpu().numpy() == oterm) & (gtrunc.cpu().numpy() == otrunc) & vis_same
+        flips += int((~same).sum())
+        total += b
+        assert _close(go.cpu().numpy()[same], oo[same]).all(), f"step {t}"
+        moved_same = same & ((env.target_xy.cpu().numpy() == st["target"].astype(np.float32)).all(-1) == (orc.target == st["target"]).all(-1))
+        assert _close(env.agent_xy.cpu().numpy()[same], orc.agent[same]).all()
+        assert _close(env.target_xy.cpu().numpy()[moved_same], orc.target[moved_same]).all()
+    assert flips / total < F32_FLIP_RATE, flips / total
+    # Philox mode, float32: invariants
+    env = TagVecEnv(1 << 20, device=DEV, seed=1, precision="float32")
+    obs, _ = env.reset(seed=1)
+    assert obs.dtype == torch.float32
+    assert bool(((env.agent_xy - env.target_xy).norm(dim=-1) > 5.0).all())
+    for _ in range(30):
+        obs, rew, term, trunc, _ = env.step(torch.rand((env.capacity, 2), device=DEV) * 2 - 1)
+        assert bool((env.agent_xy.abs() <= 5.0).all()) and bool((env.target_xy.abs() <= 4.5).all())
