@@ -140,6 +140,16 @@ __device__ __forceinline__ void stage_tables_begin(void* smem_dst, const void* g
 __device__ __forceinline__ void stage_tables_wait(uint64_t* bar) { mbar_wait(bar, 0); }
 
 // ------------------------------------------------------------------------------------------
+// Programmatic dependent launch (PDL): consecutive step kernels on one stream are data dependent
+// (step N+1 reads the state step N wrote), but the launch latency, CTA scheduling and the TMA staging
+// of the static tables of step N+1 need not wait.  Every kernel signals launch_dependents as soon as it
+// starts and calls pdl_wait() before its first access to per-env memory; pdl_wait() returns once the
+// preceding grid has completed and its writes are visible.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+// ------------------------------------------------------------------------------------------
 // episode statistics: per-thread partial sums -> warp shuffle reduce -> one atomicAdd per warp and field
 // stats[0] episodes, [1] sum of returns, [2] sum of lengths, [3] sum of squared returns, [4] env-steps
 // ------------------------------------------------------------------------------------------

@@ -91,7 +91,9 @@ __global__ void __launch_bounds__(128) crooms_step_kernel(const __grid_constant_
   const R cell_size = (R)P.cell_size;
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ uint64_t bar;
+  pdl_launch_dependents();
   stage_tables_begin(smem, P.blob, P.blob_bytes, &bar);
+  pdl_wait();
 
   const uint32_t lane = threadIdx.x & 31u;
   const uint32_t warp = threadIdx.x >> 5;
@@ -554,7 +556,7 @@ int crooms_launch(gpt_env* env, const LaunchArgs& a) {
     if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(crooms)");
   }
   void* args[] = {(void*)&P};
-  cudaError_t e = cudaLaunchKernel(k, dim3(nblocks), dim3(threads), args, smem, a.stream);
+  cudaError_t e = launch_pdl(k, dim3(nblocks), dim3(threads), smem, a.stream, args);
   env->launches += 1;
   if (e != cudaSuccess) return cuda_fail(e, "crooms_step_kernel launch");
   return GPT_OK;

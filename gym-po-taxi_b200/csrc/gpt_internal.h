@@ -3,6 +3,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <cstdlib>
+#include <cstring>
 #include <string>
 #include <vector>
 
@@ -89,6 +91,23 @@ int taxi_launch(gpt_env* env, const LaunchArgs& a);
 int rooms_launch(gpt_env* env, const LaunchArgs& a);
 int crooms_launch(gpt_env* env, const LaunchArgs& a);
 int tag_launch(gpt_env* env, const LaunchArgs& a);
+
+// Launch with the programmatic-stream-serialization attribute (see pdl_wait in gpt_common.cuh).
+// GPT_NO_PDL=1 falls back to a plain launch (A/B measurements).
+inline cudaError_t launch_pdl(const void* func, dim3 grid, dim3 block, size_t smem, cudaStream_t stream, void** args) {
+  static const bool no_pdl = getenv("GPT_NO_PDL") != nullptr;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = no_pdl ? 0 : 1;
+  return cudaLaunchKernelExC(&cfg, func, args);
+}
 
 inline uint32_t align16(uint32_t x) { return (x + 15u) & ~15u; }
 

@@ -309,7 +309,7 @@ int rooms_launch(gpt_env* env, const LaunchArgs& a) {
     if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(rooms)");
   }
   void* args[] = {(void*)&P};
-  cudaError_t e = cudaLaunchKernel(k, dim3(nblocks), dim3(threads), args, smem, a.stream);
+  cudaError_t e = launch_pdl(k, dim3(nblocks), dim3(threads), smem, a.stream, args);
   env->launches += 1;
   if (e != cudaSuccess) return cuda_fail(e, "rooms_step_kernel launch");
   if (reset) {

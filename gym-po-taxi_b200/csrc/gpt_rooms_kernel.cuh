@@ -272,6 +272,7 @@ __global__ void __launch_bounds__(RoomsShape<OBS, GRID_N>::kThreads, STATS ? 1 :
   constexpr bool kObsTable = !RGOAL && OBS != GPT_OBS_GRID;
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ uint64_t bar;
+  pdl_launch_dependents();
   stage_tables_begin(smem, P.blob, P.blob_bytes, &bar);
 
   const uint32_t lane = threadIdx.x & 31u;
@@ -285,6 +286,7 @@ __global__ void __launch_bounds__(RoomsShape<OBS, GRID_N>::kThreads, STATS ? 1 :
 
   // reset() is not a separate code path: the host poisons `elapsed` so that every env truncates and
   // launches this same kernel (gpt_rooms.cu), which keeps the hot loop free of mode branches.
+  pdl_wait();   // the previous step's writes are complete and visible from here on
   uint2 pos4[QPT], goal4[QPT];
   int4 e4[QPT];
   uint32_t a4[QPT];

@@ -148,7 +148,9 @@ template <bool HANSEN, bool REPLAY>
 __global__ void __launch_bounds__(256) taxi_arith_kernel(const __grid_constant__ TaxiParams P) {
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ uint64_t bar;
+  pdl_launch_dependents();
   stage_tables_begin(smem, P.blob, P.blob_bytes, &bar);
+  pdl_wait();
 
   const uint32_t lane = threadIdx.x & 31u;
   const int32_t tile = P.first_tile + (int32_t)(blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5));
@@ -221,6 +223,7 @@ template <bool HANSEN, bool REPLAY, bool STATS, int QPT, int THREADS>
 __global__ void __launch_bounds__(THREADS, (STATS || QPT > 2) ? 1 : 1280 / THREADS) taxi_table_kernel(const __grid_constant__ TaxiParams P) {
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ uint64_t bar;
+  pdl_launch_dependents();
   stage_tables_begin(smem, P.blob, P.blob_bytes, &bar);
 
   constexpr int kEnvsPerWarp = kWarp * kQuad * QPT;
@@ -232,6 +235,7 @@ __global__ void __launch_bounds__(THREADS, (STATS || QPT > 2) ? 1 : 1280 / THREA
   // reset() is not a separate code path: the host poisons `elapsed` so that every env truncates and
   // launches this same kernel (taxi_launch), which keeps the hot loop free of mode branches.
 
+  pdl_wait();   // the previous step's writes are complete and visible from here on
   int4 s4[QPT], e4[QPT];
   uint32_t nd4[QPT], a4[QPT];
   float4 ret4[QPT];
@@ -539,9 +543,9 @@ int taxi_launch(gpt_env* env, const LaunchArgs& a) {
     cudaError_t e = cudaFuncSetAttribute((const void*)k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(taxi)");
   }
-  k<<<grid, threads, smem, a.stream>>>(P);
+  void* args[] = {(void*)&P};
+  cudaError_t e = launch_pdl((const void*)k, dim3(grid), dim3(threads), smem, a.stream, args);
   env->launches += 1;
-  cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return cuda_fail(e, "taxi step kernel launch");
   if (table_reset) {
     e = cudaMemsetAsync(P.terminated, 0, (size_t)env->capacity, a.stream);
