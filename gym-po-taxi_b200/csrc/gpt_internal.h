@@ -75,6 +75,7 @@ int taxi_create(gpt_env* env, const gpt_config* cfg);
 int rooms_create(gpt_env* env, const gpt_config* cfg);
 int crooms_create(gpt_env* env, const gpt_config* cfg);
 int tag_create(gpt_env* env, const gpt_config* cfg);
+int car_create(gpt_env* env, const gpt_config* cfg);
 
 // per-family: launch one fused kernel.  `out_row` offsets the OUTPUT arrays (gpt_step_many);
 // `first_tile`/`n_tiles` restrict the launch to a tile range (gpt_step_host chunks); when
@@ -91,6 +92,7 @@ int taxi_launch(gpt_env* env, const LaunchArgs& a);
 int rooms_launch(gpt_env* env, const LaunchArgs& a);
 int crooms_launch(gpt_env* env, const LaunchArgs& a);
 int tag_launch(gpt_env* env, const LaunchArgs& a);
+int car_launch(gpt_env* env, const LaunchArgs& a);
 
 // Launch with the programmatic-stream-serialization attribute (see pdl_wait in gpt_common.cuh).
 // GPT_NO_PDL=1 falls back to a plain launch (A/B measurements).

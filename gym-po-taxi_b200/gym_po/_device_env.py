@@ -168,8 +168,9 @@ class DeviceVecEnv:
         if t.device != self.device or t.dtype != self._action_dtype or not t.is_contiguous() or t.shape[1] != self.capacity:
             raise ValueError("step_many needs a contiguous device tensor [T, capacity(,cols)] of the action dtype")
         stride = 0
+        names = [n for n in ("obs", "reward", "terminated", "truncated") if self._descs[n][1] == N.ROLE_OUTPUT]
         if out is not None:
-            for name in ("obs", "reward", "terminated", "truncated"):
+            for name in names:
                 i, _, dt, cols = self._descs[name]
                 o = out[name]
                 if o.shape[0] < t.shape[0] or o.shape[1] != self.capacity or not o.is_contiguous():
@@ -181,7 +182,7 @@ class DeviceVecEnv:
                 N.check(N.lib.gpt_step_many(self._h, C.c_void_p(t.data_ptr()), t.shape[0], stride, self._stream()))
         finally:
             if out is not None:
-                for name in ("obs", "reward", "terminated", "truncated"):
+                for name in names:
                     i = self._descs[name][0]
                     a = self._arrays[name]
                     N.check(N.lib.gpt_bind(self._h, i, C.c_void_p(a.data_ptr()), a.shape[0]))

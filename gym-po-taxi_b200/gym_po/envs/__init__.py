@@ -2,6 +2,7 @@ from .extended_taxi import (TaxiVecEnv, HansenTaxiVecEnv, ExtendedHansenTaxiVecE
                             ExtendedTaxiVecEnv, TAXI_MAP)
 from .rooms import RoomsEnv, CRoomsEnv  # noqa: F401
 from .tag import TagVecEnv  # noqa: F401
+from .car_flag import CarVecEnv, DiscreteActionCarVecEnv  # noqa: F401
 
-__all__ = ["RoomsEnv", "CRoomsEnv", "TagVecEnv", "TaxiVecEnv", "HansenTaxiVecEnv", "ExtendedHansenTaxiVecEnv", "ExtendedTaxiVecEnv", "EXTENDED_TAXI_MAP",
+__all__ = ["RoomsEnv", "CRoomsEnv", "TagVecEnv", "CarVecEnv", "DiscreteActionCarVecEnv", "TaxiVecEnv", "HansenTaxiVecEnv", "ExtendedHansenTaxiVecEnv", "ExtendedTaxiVecEnv", "EXTENDED_TAXI_MAP",
            "TAXI_MAP"]

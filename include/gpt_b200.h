@@ -8,6 +8,7 @@
  *     RoomsEnv.reset / .step            gym_po/envs/rooms/rooms.py:177-189, :198-222
  *     CRoomsEnv.reset / .step           gym_po/envs/rooms/crooms.py:251-266, :276-298
  *     AntTagEnv pursuit rules           gym_po/envs/ant_tag.py:105-123, :144-153
+ *     CarVecEnv.reset / .step           gym_po/envs/car_flag.py:87-95, :114-141
  * Each entry point below says which of those it replaces.  The Python host classes in
  * gym-po-taxi_b200/gym_po/ bind these symbols with ctypes.
  *
@@ -55,6 +56,7 @@ extern "C" {
 #define GPT_FAMILY_ROOMS 1  /* RoomsEnv              rooms/rooms.py:71-226 */
 #define GPT_FAMILY_CROOMS 2 /* CRoomsEnv             rooms/crooms.py:91-338 */
 #define GPT_FAMILY_TAG 3    /* point-mass Tag built from AntTagEnv's pursuit rules, ant_tag.py:105-153 */
+#define GPT_FAMILY_CAR 4    /* CarVecEnv / DiscreteActionCarVecEnv   car_flag.py:23-144, :286-303 */
 
 /* random-number modes */
 #define GPT_RNG_PHILOX 0 /* Philox4x32-10, key = seed, counter = (global env id, step, stream) */
@@ -133,7 +135,9 @@ typedef struct gpt_config {
   int32_t c_use_velocity;
   int32_t c_action_f64; /* continuous (yx) actions are float32 [B,2] (0) or float64 [B,2] (1) */
   int32_t c_state_f32;  /* 0: float64 positions (bit-exact vs the numpy reference); 1: float32 fast mode */
-  int32_t c_pad;
+  int32_t car_num_actions;          /* CAR: 0 = continuous force [B,1] (float32, or float64 if c_action_f64); n > 0 =
+                                       DiscreteActionCarVecEnv with n evenly spaced forces */
+  const double* car_action_table;   /* CAR: [car_num_actions] = np.linspace(-1, 1, n) (car_flag.py:291) */
 } gpt_config;
 
 typedef struct gpt_array_desc {

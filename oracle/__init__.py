@@ -31,3 +31,4 @@ from .taxi import TaxiOracle, TAXI_MAP, EXTENDED_TAXI_MAP  # noqa: F401
 from .rooms import RoomsOracle, load_layout, LAYOUT_NAMES  # noqa: F401
 from .crooms import CRoomsOracle  # noqa: F401
 from .tag import tag_move_target, TagOracle  # noqa: F401
+from .car import CarOracle  # noqa: F401

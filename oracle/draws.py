@@ -9,6 +9,7 @@ over PCG64).  The call sites and their order are:
 * cell sampling        ``choice(valid_states, b)``                            rooms/rooms.py:160-162,170-172
 * Gaussian noise       ``normal(scale=s, size=shape)``                        rooms/crooms.py:178,194,324
 * tag target           ``integers(4)``                                        ant_tag.py:109
+* car respawn          ``uniform(-0.2, 0.2, (b,1))``, ``choice([-1,1], b)`` x2  car_flag.py:100-110
 """
 from __future__ import annotations
 
@@ -43,6 +44,9 @@ class GeneratorDraws:
 
     def normal(self, scale, size):
         return self.gen.normal(scale=scale, size=size)
+
+    def uniform(self, low, high, size):
+        return self.gen.uniform(low, high, size)
 
 
 class RecordedDraws:
@@ -85,6 +89,9 @@ class RecordedDraws:
 
     def normal(self, scale, size):
         return self._next("normal", size).reshape(size)
+
+    def uniform(self, low, high, size):
+        return self._next("uniform", size).reshape(size)
 
     @property
     def exhausted(self):

@@ -71,13 +71,13 @@ class TagOracle:
         idx = np.flatnonzero(mask)
         if idx.size == 0:
             return
-        agent = self.rng.gen.uniform(-CAGE, CAGE, (idx.size, 2))
-        target = self.rng.gen.uniform(-CAGE, CAGE, (idx.size, 2))
+        agent = self.rng.uniform(-CAGE, CAGE, (idx.size, 2))
+        target = self.rng.uniform(-CAGE, CAGE, (idx.size, 2))
         while True:
             close = np.linalg.norm(agent - target, axis=-1) <= MIN_SPAWN_DISTANCE
             if not close.any():
                 break
-            target[close] = self.rng.gen.uniform(-CAGE, CAGE, (int(close.sum()), 2))
+            target[close] = self.rng.uniform(-CAGE, CAGE, (int(close.sum()), 2))
         self.agent[idx], self.target[idx] = agent, target
         self.elapsed[idx] = 0
         self.draws["spawn_agent"][idx] = agent

@@ -72,6 +72,10 @@ CASES = [
     ("rooms32b_grid5_defgoal", "RoomsEnv", {"layout": "32b", "obs_type": "grid", "obs_n": 5, "time_limit": 30}, 8, 150),
     ("rooms32_vghansen8_defgoal", "RoomsEnv", {"layout": "32", "obs_type": "vector_goal_hansen8", "time_limit": 30}, 8, 150),
     ("crooms32_vghansen8_defgoal", "CRoomsEnv", {"layout": "32", "obs_type": "vector_goal_hansen8", "time_limit": 30}, 0, 150),
+    # car-flag.  n_act -1 = float32 forces [B,1] steered towards the flags, -2 = float64 forces
+    ("car_f32", "CarVecEnv", {"time_limit": 60}, -1, 400),
+    ("car_f64", "CarVecEnv", {"time_limit": 45}, -2, 300),
+    ("car_discrete5", "DiscreteActionCarVecEnv", {"num_actions": 5, "time_limit": 50}, 5, 300),
     ("crooms_vmdp", "CRoomsEnv", {"layout": "4", "obs_type": "vector_mdp"}, 0, 500),
     ("crooms_hansen8_ord", "CRoomsEnv", {"layout": "4", "obs_type": "hansen8", "action_type": "ordinal"}, 8, 500),
     ("crooms_vel_rg", "CRoomsEnv", {"layout": "8", "obs_type": "vector_mdp_goal", "use_velocity": True, "goal_xy": None,
@@ -109,7 +113,11 @@ def pack_log(log):
 
 
 def run_case(E, name, cls, kwargs, n_act, T, seed=0):
-    env = getattr(E, cls)(B, **kwargs)
+    if cls == "DiscreteActionCarVecEnv":
+        kw = dict(kwargs)
+        env = E.DiscreteActionCarVecEnv(kw.pop("num_actions"), B, **kw)
+    else:
+        env = getattr(E, cls)(B, **kwargs)
     rec = RecordingGenerator(make_generator(seed))
     if cls == "CRoomsEnv":
         env.rng = rec            # crooms.py:168, :246-249 — own generator
@@ -124,7 +132,17 @@ def run_case(E, name, cls, kwargs, n_act, T, seed=0):
     arng = np.random.default_rng(1)
     A, O, R, D, TR = [], [], [], [], []
     for _ in range(T):
-        a = arng.uniform(-1, 1, (B, 2)) if n_act == 0 else arng.integers(n_act, size=B)
+        if n_act < 0:      # car: random force magnitudes (some beyond the clip range), mostly pushing outwards
+            a = arng.uniform(-1.4, 1.4, (B, 1))
+            if len(A) % 3:
+                a = np.sign(env.s[:, :1] + 1e-3) * np.abs(a)
+            a = a.astype(np.float32 if n_act == -1 else np.float64)
+        elif cls == "DiscreteActionCarVecEnv":   # outermost force towards the nearer flag 2 steps out of 3
+            a = arng.integers(n_act, size=B)
+            if len(A) % 3:
+                a = np.where(env.s[:, 0] >= 0, n_act - 1, 0)
+        else:
+            a = arng.uniform(-1, 1, (B, 2)) if n_act == 0 else arng.integers(n_act, size=B)
         o, r, d, tr, _ = env.step(a.copy())
         feed(o); feed(r); feed(d); feed(tr)
         A.append(a); O.append(np.array(o, copy=True)); R.append(r.copy()); D.append(d.copy()); TR.append(tr.copy())
@@ -134,6 +152,8 @@ def run_case(E, name, cls, kwargs, n_act, T, seed=0):
                  "state_elapsed": env.elapsed}
     elif cls == "RoomsEnv":
         state = {"state_agent": env.agent_yx, "state_goal": env.goal_yx, "state_elapsed": env.elapsed}
+    elif "Car" in cls:
+        state = {"state_s": env.s, "state_elapsed": env.elapsed, "state_heavens": env.heavens, "state_priests": env.priests}
     else:
         state = {"state_s": env.s, "state_elapsed": env.elapsed, "state_ndrop": env.n_dropoffs_completed}
     kinds, sizes, vals = pack_log(rec.log)
@@ -143,7 +163,8 @@ def run_case(E, name, cls, kwargs, n_act, T, seed=0):
     A = np.array(A)
     np.savez_compressed(
         os.path.join(HERE, name + ".npz"), meta=json.dumps(meta),
-        actions=A.astype(np.int8) if n_act else A, obs0=narrow(obs0), obs=narrow(np.array(O)),
+        actions=A.astype(np.int8) if n_act > 0 else A, obs0=obs0 if "Car" in cls else narrow(obs0),
+        obs=np.array(O) if "Car" in cls else narrow(np.array(O)),
         rew=np.array(R, np.float32), term=np.array(D, bool), trunc=np.array(TR, bool),
         log_kind=kinds, log_size=sizes, log_val=vals, **{k: np.asarray(v) for k, v in state.items()})
     return meta

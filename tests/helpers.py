@@ -31,7 +31,8 @@ def recorded_draws(fx):
         kind = KINDS[int(k)]
         v = fx["log_val"][pos:pos + int(n)]
         pos += int(n)
-        log.append((kind, v.astype(np.int64) if kind in INT_KINDS else v))
+        integral = kind in INT_KINDS and np.array_equal(v, np.round(v))   # choice([-0.5, 0.5]) stays float
+        log.append((kind, v.astype(np.int64) if integral else v))
     return RecordedDraws(log)
 
 
@@ -56,6 +57,8 @@ def make_oracle(meta, draws=None, num_envs=None):
         return oracle.RoomsOracle(b, draws=draws, **kw)
     if cls == "CRoomsEnv":
         return oracle.CRoomsOracle(b, draws=draws, **kw)
+    if cls in ("CarVecEnv", "DiscreteActionCarVecEnv"):
+        return oracle.CarOracle(b, draws=draws, **kw)
     raise KeyError(cls)
 
 
