@@ -44,6 +44,8 @@ WORKLOADS = {
                        desc="continuous ROOMS '4' (float64 parity mode), vector_mdp obs, yx float32 actions"),
     "tag_f64": dict(alg_bytes=102, n_act=0, dtype="f64", cpu_family="tag",
                     desc="point-mass Tag (float64 parity mode), yx float32 actions"),
+    "car": dict(alg_bytes=44, n_act=0, act_cols=1, dtype="f32", cpu_family="car",
+                desc="car-flag (heaven/hell with priest), float32 forces; obs is the live float32 state row"),
     "rooms_grid9": dict(alg_bytes=19 + 81, n_act=8, dtype="u8", cpu_family="rooms_grid9",
                         desc="FourRooms '4', 9x9 egocentric window obs, 0.2 action-slip, fixed goal"),
 }
@@ -191,6 +193,9 @@ def make_env(workload, b, rank, seed=0):
         from gym_po.envs import CRoomsEnv
         return CRoomsEnv(b, "4", obs_type="vector_mdp", seed=seed, env_offset=rank * b,
                          precision="float64" if workload.endswith("f64") else "float32")
+    if workload == "car":
+        from gym_po.envs import CarVecEnv
+        return CarVecEnv(b, seed=seed, env_offset=rank * b)
     if workload in ("tag", "tag_f64"):
         from gym_po.envs import TagVecEnv
         return TagVecEnv(b, seed=seed, env_offset=rank * b, precision="float64" if workload.endswith("f64") else "float32")
@@ -217,7 +222,8 @@ def run_b200(args):
     if wl["n_act"]:
         actions = torch.randint(0, wl["n_act"], (SLOTS, cap), dtype=torch.int8, device=dev, generator=gen)
     else:
-        actions = torch.rand((SLOTS, cap, 2), device=dev, generator=gen) * 2 - 1
+        cols = wl.get("act_cols", 2)
+        actions = torch.rand((SLOTS, cap, cols) if cols > 1 else (SLOTS, cap), device=dev, generator=gen) * 2 - 1
     # rollout storage: outputs of step t go to slot t % SLOTS (like an RL rollout buffer); with the
     # action slots this makes the per-step footprint rotate through > L2-size memory
     out = {}
@@ -275,7 +281,7 @@ def run_b200(args):
     if wl["n_act"]:
         host_actions[:] = hrng.integers(0, wl["n_act"], size=(SLOTS, b)).astype(np.int8)
     else:
-        host_actions[:] = hrng.uniform(-1, 1, size=(SLOTS, b, 2)).astype(np.float32)
+        host_actions[:] = hrng.uniform(-1, 1, size=host_actions.shape).astype(np.float32)
     for i in range(3):
         env.step_host(host_actions[i % SLOTS])
     if world > 1:

@@ -32,6 +32,8 @@ def make_env(family, b, seed):
         return oracle.RoomsOracle(b, "4", obs_type="grid", obs_n=9, draws=draws), 8
     if family == "crooms":
         return oracle.CRoomsOracle(b, "4", obs_type="vector_mdp", draws=draws), 0
+    if family == "car":
+        return oracle.CarOracle(b, draws=draws), -1
     if family == "tag":
         return oracle.TagOracle(b, draws=draws), 0
     raise KeyError(family)
@@ -51,7 +53,10 @@ def main():
     rng = np.random.default_rng(1234 + a.seed)
     # de-synchronise episode phases exactly like the GPU arm (otherwise every env truncates on the same step)
     env.elapsed[:] = rng.integers(0, env.time_limit + 1, size=a.envs)
-    acts = rng.integers(n_act, size=(8, a.envs)) if n_act else rng.uniform(-1, 1, size=(8, a.envs, 2)).astype(np.float32)
+    if n_act > 0:
+        acts = rng.integers(n_act, size=(8, a.envs))
+    else:
+        acts = rng.uniform(-1, 1, size=(8, a.envs, 2 if n_act == 0 else 1)).astype(np.float32)
     for t in range(a.warmup):
         env.step(acts[t % 8])
     while time.monotonic() < a.start_at:

@@ -53,12 +53,12 @@ def test_golden_trajectory_free_running(name):
 def test_lockstep_vs_oracle(mode, b):
     from gym_po.envs import CarVecEnv, DiscreteActionCarVecEnv
     if mode == "discrete7":
-        orc = oracle.CarOracle(b, time_limit=33, num_actions=7, draws=oracle.GeneratorDraws(seed=4))
-        env = DiscreteActionCarVecEnv(7, b, time_limit=33, device=DEV, rng_mode="replay")
+        orc = oracle.CarOracle(b, time_limit=110, num_actions=7, draws=oracle.GeneratorDraws(seed=4))
+        env = DiscreteActionCarVecEnv(7, b, time_limit=110, device=DEV, rng_mode="replay")
     else:
         dt = np.float32 if mode == "f32" else np.float64
-        orc = oracle.CarOracle(b, time_limit=33, draws=oracle.GeneratorDraws(seed=4))
-        env = CarVecEnv(b, time_limit=33, device=DEV, rng_mode="replay", action_dtype=torch.float32 if mode == "f32" else torch.float64)
+        orc = oracle.CarOracle(b, time_limit=110, draws=oracle.GeneratorDraws(seed=4))
+        env = CarVecEnv(b, time_limit=110, device=DEV, rng_mode="replay", action_dtype=torch.float32 if mode == "f32" else torch.float64)
     rng = np.random.default_rng(8)
 
     def act(t):
@@ -79,7 +79,7 @@ def test_lockstep_vs_oracle(mode, b):
     g_obs, _ = env.reset()
     np.testing.assert_array_equal(g_obs.cpu().numpy(), o_obs)
     n_term = 0
-    for t in range(200):
+    for t in range(260):
         a = act(t)
         o = orc.step(a)
         env.set_replay(**orc.draws)
