@@ -52,7 +52,7 @@ struct gpt_env {
   // ---- rooms / crooms ----
   struct RoomsLayout {
     uint32_t nb8_off = 0, yx_off = 0, room_off = 0, sid_off = 0, valid_off = 0, thr32_off = 0, thr64_off = 0,
-             rows_off = 0, grid_off = 0, move_off = 0, obstab_off = 0;
+             rows_off = 0, grid_off = 0, move_off = 0, obstab_off = 0, alias_off = 0, moveobs_off = 0;
     int32_t n_valid = 0, n_rooms = 0, n_cells = 0;
   } rl;
   int32_t action_dtype = GPT_DT_I8, action_cols = 1;

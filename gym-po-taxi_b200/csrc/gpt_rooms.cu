@@ -132,8 +132,56 @@ int rooms_build_tables(gpt_env* env, const gpt_config* c, bool discrete_actions)
       else obstab[i] = lo;
     }
   }
+  // merged table for 16-bit observations: next | on-goal<<14 | blocked<<15 | obs(next)<<16
+  std::vector<uint32_t> moveobs;
+  const bool merged = !obstab.empty() && (kind == GPT_OBS_ROOM || kind == GPT_OBS_ROOM_GOAL || kind == GPT_OBS_MDP ||
+                                          kind == GPT_OBS_HANSEN || kind == GPT_OBS_VEC_MDP);
+  if (merged) {
+    if (nc > 0x3FFF) return fail(GPT_E_ARG, "rooms: grid too large for the merged move table");
+    const int gy = c->rooms_goal_y, gx = c->rooms_goal_x;
+    const int gcell = (gy < h && gx >= 0 && gx < w) ? gy * w + gx : -1;
+    moveobs.resize((size_t)nc * 8);
+    for (size_t i = 0; i < moveobs.size(); ++i) {
+      const uint32_t nxt = move[i] & 0x7FFFu;
+      if (obstab[nxt] > 0xFFFFu) return fail(GPT_E_ARG, "rooms: internal: observation does not fit 16 bits");
+      moveobs[i] = nxt | ((int)nxt == gcell ? 0x4000u : 0u) | (move[i] & 0x8000u) | (obstab[nxt] << 16);
+    }
+    move.clear();   // the merged kernels never read the plain move table
+  }
+  // Walker alias tables for the slip (Philox mode): per intended action, n columns of {threshold, dir | alias<<8}
+  std::vector<uint32_t> alias;
+  if (discrete_actions) {
+    const int n = c->rooms_n_actions, shift = n == 4 ? 1 : 0;
+    alias.assign((size_t)n * 8 * 2, 0u);
+    for (int a = 0; a < n; ++a) {
+      std::vector<double> q(n);
+      for (int j = 0; j < n; ++j) {
+        const double hi = j == n - 1 ? 1.0 : thr64[a * n + j];   // the last threshold never counts (= clamp to n-1)
+        const double lo = j == 0 ? 0.0 : thr64[a * n + j - 1];
+        q[j] = (hi > lo ? hi - lo : 0.0) * n;
+      }
+      std::vector<int> small, large, al(n);
+      std::vector<double> pr(n, 1.0);
+      for (int j = 0; j < n; ++j) { al[j] = j; (q[j] < 1.0 ? small : large).push_back(j); }
+      while (!small.empty() && !large.empty()) {
+        const int sidx = small.back(), lidx = large.back();
+        small.pop_back();
+        pr[sidx] = q[sidx];
+        al[sidx] = lidx;
+        q[lidx] = (q[lidx] + q[sidx]) - 1.0;
+        if (q[lidx] < 1.0) { large.pop_back(); small.push_back(lidx); }
+      }
+      for (int j = 0; j < n; ++j) {
+        const double t = pr[j] * 4294967296.0;
+        alias[((size_t)a * 8 + j) * 2] = t >= 4294967295.0 ? 0xFFFFFFFFu : (t <= 0 ? 0u : (uint32_t)t);
+        alias[((size_t)a * 8 + j) * 2 + 1] = (uint32_t)(j << shift) | ((uint32_t)(al[j] << shift) << 8);
+      }
+    }
+  }
   std::vector<uint8_t> blob;
   env->rl.move_off = blob_append(blob, move);
+  env->rl.moveobs_off = blob_append(blob, moveobs);
+  env->rl.alias_off = blob_append(blob, alias);
   env->rl.obstab_off = blob_append(blob, obstab);
   env->rl.nb8_off = blob_append(blob, nb8);
   env->rl.room_off = blob_append(blob, room);
@@ -263,6 +311,9 @@ int rooms_launch(gpt_env* env, const LaunchArgs& a) {
   P.rows_off = env->rl.rows_off;
   P.move_off = env->rl.move_off;
   P.obstab_off = env->rl.obstab_off;
+  P.moveobs_off = env->rl.moveobs_off;
+  P.alias_off = env->rl.alias_off;
+  P.log2n = c.rooms_n_actions == 4 ? 2u : 3u;
   P.stage_off = (env->blob_bytes + 127u) & ~127u;
   P.env_offset = c.env_offset;
   P.first_tile = a.first_tile;

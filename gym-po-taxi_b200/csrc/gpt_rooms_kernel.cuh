@@ -39,7 +39,8 @@ struct RoomsParams {
   const int32_t* rp_reset_agent;
   const int32_t* rp_reset_goal;
   const uint8_t* blob;
-  uint32_t blob_bytes, nb8_off, room_off, sid_off, valid_off, thr32_off, thr64_off, rows_off, stage_off, move_off, obstab_off;
+  uint32_t blob_bytes, nb8_off, room_off, sid_off, valid_off, thr32_off, thr64_off, rows_off, stage_off, move_off, obstab_off, alias_off, moveobs_off;
+  uint32_t log2n;   // log2(n_actions)
   int64_t env_offset;
   int32_t first_tile, n_tiles, mode;
   int32_t w, n_actions, n_valid, n_rooms, time_limit;
@@ -270,6 +271,10 @@ __global__ void __launch_bounds__(RoomsShape<OBS, GRID_N>::kThreads, STATS ? 1 :
   constexpr int kEnvsPerWarp = kWarp * kQuad * QPT;
   // fixed goal + non-window obs: the observation is a pure function of the agent cell -> one table lookup
   constexpr bool kObsTable = !RGOAL && OBS != GPT_OBS_GRID;
+  // ... and when it also fits 16 bits it rides in the move-table entry: ONE lookup yields next cell, blocked,
+  // on-goal and the observation of the next cell
+  constexpr bool kMerged = kObsTable && (OBS == GPT_OBS_ROOM || OBS == GPT_OBS_ROOM_GOAL || OBS == GPT_OBS_MDP ||
+                                         OBS == GPT_OBS_HANSEN || OBS == GPT_OBS_VEC_MDP);
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ uint64_t bar;
   pdl_launch_dependents();
@@ -314,6 +319,9 @@ __global__ void __launch_bounds__(RoomsShape<OBS, GRID_N>::kThreads, STATS ? 1 :
   T.rows = reinterpret_cast<const uint64_t*>(smem + P.rows_off);
   const uint16_t* move = reinterpret_cast<const uint16_t*>(smem + P.move_off);     // [cell*8 + dir] next cell | blocked << 15
   const uint32_t* obstab = reinterpret_cast<const uint32_t*>(smem + P.obstab_off); // [cell] or [cell*2] packed observation
+  const uint32_t* moveobs = reinterpret_cast<const uint32_t*>(smem + P.moveobs_off); // [cell*8 + dir] next | goal<<14 | blocked<<15 | obs<<16
+  const uint2* alias = reinterpret_cast<const uint2*>(smem + P.alias_off);         // [a*8 + column] {threshold, dir | alias_dir<<8}
+  const uint32_t col_shift = 32u - P.log2n;
   const int gn = GRID_N > 0 ? GRID_N : P.grid_n;
   ObsCtx OC;
   OC.w = P.w; OC.n_rooms = P.n_rooms; OC.n_valid = P.n_valid; OC.hansen_n = P.hansen_n; OC.gn = gn; OC.div_w = P.div_w;
@@ -357,17 +365,27 @@ __global__ void __launch_bounds__(RoomsShape<OBS, GRID_N>::kThreads, STATS ? 1 :
         for (uint32_t i = 0; i < n; ++i) a2 += row[i] < u ? 1u : 0u;
         a2 = a2 < n ? a2 : n - 1;
       } else {
-        // thr32 rows are always 8 wide and already in ORDINAL-direction units (cardinal envs: each
-        // threshold twice), last entry 0xFFFFFFFF (= the clamp), so the 3-step search yields the direction
-        const uint32_t* row = T.thr32 + a * 8;
-        a2 = row[3] < slipv[k] ? 4u : 0u;
-        a2 += row[a2 + 1] < slipv[k] ? 2u : 0u;
-        a2 += row[a2] < slipv[k] ? 1u : 0u;
+        // Walker alias table per intended action: the top log2(n) bits of the draw pick a column, the
+        // remaining bits decide between the column's own direction and its alias — one 8-byte lookup and one
+        // compare instead of a 3-step threshold search.  Entries are already in ordinal-direction units.
+        const uint32_t u = slipv[k];
+        const uint2 e = alias[a * 8 + (u >> col_shift)];
+        a2 = ((u << P.log2n) < e.x) ? (e.y & 0xFFu) : (e.y >> 8);
       }
-      const uint32_t mv = move[cellv[k] * 8 + (REPLAY ? (a2 << dir_shift) : a2)];   // grid[proposed] == -1 -> stay (rooms.py:212-213, :224-226)
-      const bool blocked = (mv & 0x8000u) != 0;
-      cellv[k] = mv & 0x7FFFu;
-      const bool at_goal = cellv[k] == gcell;             // (:216)
+      const uint32_t d8 = REPLAY ? (a2 << dir_shift) : a2;
+      bool blocked, at_goal;
+      if constexpr (kMerged) {
+        const uint32_t m = moveobs[cellv[k] * 8 + d8];
+        cellv[k] = m & 0x3FFFu;
+        blocked = (m & 0x8000u) != 0;
+        at_goal = (m & 0x4000u) != 0;
+        o32[k] = m >> 16;
+      } else {
+        const uint32_t mv = move[cellv[k] * 8 + d8];   // grid[proposed] == -1 -> stay (rooms.py:212-213, :224-226)
+        blocked = (mv & 0x8000u) != 0;
+        cellv[k] = mv & 0x7FFFu;
+        at_goal = cellv[k] == gcell;                     // (:216)
+      }
       rv[k] = at_goal ? P.r_goal : (blocked ? P.r_wall : P.r_step);
       const bool trunc = ev[k] > P.time_limit;            // (:220)
       tw |= (at_goal ? 1u : 0u) << (8 * k);
@@ -399,6 +417,7 @@ __global__ void __launch_bounds__(RoomsShape<OBS, GRID_N>::kThreads, STATS ? 1 :
             cellv[i] = fresh & 0xFFFFu;
             goalv[i] = fresh >> 16;
             ev[i] = 0;
+            if constexpr (kMerged) o32[i] = obstab[fresh & 0xFFFFu];
           }
         }
       }
@@ -406,7 +425,9 @@ __global__ void __launch_bounds__(RoomsShape<OBS, GRID_N>::kThreads, STATS ? 1 :
     // ---- observation of the (post-reset) state ------------------------------------------------
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      if constexpr (kObsTable) {
+      if constexpr (kMerged) {
+        // observation already taken from the move-table entry (or refreshed by the respawn above)
+      } else if constexpr (kObsTable) {
         if (obs_two_words) {
           const uint2 o = reinterpret_cast<const uint2*>(obstab)[cellv[k]];
           o32[k] = o.x;
