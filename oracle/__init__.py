@@ -32,3 +32,4 @@ from .rooms import RoomsOracle, load_layout, LAYOUT_NAMES  # noqa: F401
 from .crooms import CRoomsOracle  # noqa: F401
 from .tag import tag_move_target, TagOracle  # noqa: F401
 from .car import CarOracle  # noqa: F401
+from .msrooms import MSRoomsOracle  # noqa: F401

@@ -72,6 +72,12 @@ CASES = [
     ("rooms32b_grid5_defgoal", "RoomsEnv", {"layout": "32b", "obs_type": "grid", "obs_n": 5, "time_limit": 30}, 8, 150),
     ("rooms32_vghansen8_defgoal", "RoomsEnv", {"layout": "32", "obs_type": "vector_goal_hansen8", "time_limit": 30}, 8, 150),
     ("crooms32_vghansen8_defgoal", "CRoomsEnv", {"layout": "32", "obs_type": "vector_goal_hansen8", "time_limit": 30}, 0, 150),
+    # multistory FourRooms (needs the Appendix-C signature repair to import at all)
+    ("msrooms_mdp_1floor", "MultistoryFourRoomsEnv", {"grid_z": 1}, 4, 300),
+    ("msrooms_hansen8_3floors", "MultistoryFourRoomsEnv", {"grid_z": 3, "obs_type": "hansen8", "action_type": "ordinal", "time_limit": 150}, 8, 400),
+    ("msrooms_vghansen_rg", "MultistoryFourRoomsEnv", {"grid_z": 2, "obs_type": "vector_goal_hansen", "goal_xyz": None, "time_limit": 40}, 4, 300),
+    ("msrooms_vmdp_goal_rg", "MultistoryFourRoomsEnv", {"grid_z": 2, "obs_type": "vector_mdp_goal", "goal_xyz": None, "time_limit": 30,
+                                                        "step_reward": -0.1, "wall_reward": -1.0}, 4, 300),
     # car-flag.  n_act -1 = float32 forces [B,1] steered towards the flags, -2 = float64 forces
     ("car_f32", "CarVecEnv", {"time_limit": 60}, -1, 400),
     ("car_f64", "CarVecEnv", {"time_limit": 45}, -2, 300),
@@ -152,6 +158,8 @@ def run_case(E, name, cls, kwargs, n_act, T, seed=0):
                  "state_elapsed": env.elapsed}
     elif cls == "RoomsEnv":
         state = {"state_agent": env.agent_yx, "state_goal": env.goal_yx, "state_elapsed": env.elapsed}
+    elif cls == "MultistoryFourRoomsEnv":
+        state = {"state_agent": env.agent_zyx, "state_goal": env.goal_zyx, "state_elapsed": env.elapsed}
     elif "Car" in cls:
         state = {"state_s": env.s, "state_elapsed": env.elapsed, "state_heavens": env.heavens, "state_priests": env.priests}
     else:

@@ -57,6 +57,10 @@ def make_oracle(meta, draws=None, num_envs=None):
         return oracle.RoomsOracle(b, draws=draws, **kw)
     if cls == "CRoomsEnv":
         return oracle.CRoomsOracle(b, draws=draws, **kw)
+    if cls == "MultistoryFourRoomsEnv":
+        if "goal_xyz" in kw and kw["goal_xyz"] is not None:
+            kw["goal_xyz"] = tuple(kw["goal_xyz"])
+        return oracle.MSRoomsOracle(b, draws=draws, **kw)
     if cls in ("CarVecEnv", "DiscreteActionCarVecEnv"):
         return oracle.CarOracle(b, draws=draws, **kw)
     raise KeyError(cls)
