@@ -46,6 +46,8 @@ WORKLOADS = {
                     desc="point-mass Tag (float64 parity mode), yx float32 actions"),
     "car": dict(alg_bytes=44, n_act=0, act_cols=1, dtype="f32", cpu_family="car",
                 desc="car-flag (heaven/hell with priest), float32 forces; obs is the live float32 state row"),
+    "msrooms": dict(alg_bytes=23, n_act=4, dtype="int32", cpu_family="msrooms",
+                    desc="multistory FourRooms (3 floors, stairs), mdp obs, 1/3 action-slip, cardinal actions, fixed goal, Philox RNG"),
     "rooms_grid9": dict(alg_bytes=19 + 81, n_act=8, dtype="u8", cpu_family="rooms_grid9",
                         desc="FourRooms '4', 9x9 egocentric window obs, 0.2 action-slip, fixed goal"),
 }
@@ -193,6 +195,9 @@ def make_env(workload, b, rank, seed=0):
         from gym_po.envs import CRoomsEnv
         return CRoomsEnv(b, "4", obs_type="vector_mdp", seed=seed, env_offset=rank * b,
                          precision="float64" if workload.endswith("f64") else "float32")
+    if workload == "msrooms":
+        from gym_po.envs import MultistoryFourRoomsEnv
+        return MultistoryFourRoomsEnv(b, grid_z=3, seed=seed, env_offset=rank * b)
     if workload == "car":
         from gym_po.envs import CarVecEnv
         return CarVecEnv(b, seed=seed, env_offset=rank * b)

@@ -89,6 +89,7 @@ static int launch(gpt_env* env, const LaunchArgs& a) {
     case GPT_FAMILY_CROOMS: return crooms_launch(env, a);
     case GPT_FAMILY_TAG: return tag_launch(env, a);
     case GPT_FAMILY_CAR: return car_launch(env, a);
+    case GPT_FAMILY_MSROOMS: return msrooms_launch(env, a);
   }
   return fail(GPT_E_ARG, "unknown family");
 }
@@ -202,6 +203,7 @@ int gpt_create(const gpt_config* cfg, gpt_env** out) {
     case GPT_FAMILY_CROOMS: rc = crooms_create(env, cfg); break;
     case GPT_FAMILY_TAG: rc = tag_create(env, cfg); break;
     case GPT_FAMILY_CAR: rc = car_create(env, cfg); break;
+    case GPT_FAMILY_MSROOMS: rc = msrooms_create(env, cfg); break;
     default: rc = fail(GPT_E_ARG, "gpt_create: unknown family");
   }
   if (rc == GPT_OK) {

@@ -55,6 +55,13 @@ struct gpt_env {
              rows_off = 0, grid_off = 0, move_off = 0, obstab_off = 0, alias_off = 0, moveobs_off = 0;
     int32_t n_valid = 0, n_rooms = 0, n_cells = 0;
   } rl;
+  // ---- multistory rooms ----
+  struct MsLayout {
+    uint32_t move_off = 0, moveobs_off = 0, obstab_off = 0, info_off = 0, sid_off = 0, h3_off = 0, vh_off = 0, alias_off = 0,
+             thr64_off = 0, avalid_off = 0, gvalid_off = 0;
+    int32_t n_agent = 0, n_goal = 0, n_free = 0, room_n = 0, n_cells = 0, obs_bytes = 4;
+    bool merged = false;
+  } ms;
   int32_t action_dtype = GPT_DT_I8, action_cols = 1;
 
   int find(const char* name) const;
@@ -76,6 +83,7 @@ int rooms_create(gpt_env* env, const gpt_config* cfg);
 int crooms_create(gpt_env* env, const gpt_config* cfg);
 int tag_create(gpt_env* env, const gpt_config* cfg);
 int car_create(gpt_env* env, const gpt_config* cfg);
+int msrooms_create(gpt_env* env, const gpt_config* cfg);
 
 // per-family: launch one fused kernel.  `out_row` offsets the OUTPUT arrays (gpt_step_many);
 // `first_tile`/`n_tiles` restrict the launch to a tile range (gpt_step_host chunks); when
@@ -93,6 +101,11 @@ int rooms_launch(gpt_env* env, const LaunchArgs& a);
 int crooms_launch(gpt_env* env, const LaunchArgs& a);
 int tag_launch(gpt_env* env, const LaunchArgs& a);
 int car_launch(gpt_env* env, const LaunchArgs& a);
+int msrooms_launch(gpt_env* env, const LaunchArgs& a);
+
+// Walker alias tables for the action slip (Philox mode), shared by ROOMS and MSROOMS: per intended action, n
+// columns of {threshold (x 2^32), dir | alias_dir << 8} in ordinal-direction units, rows padded to 8 columns.
+std::vector<uint32_t> build_slip_alias(int n_actions, const double* cumsum_rows);
 
 // Launch with the programmatic-stream-serialization attribute (see pdl_wait in gpt_common.cuh).
 // GPT_NO_PDL=1 falls back to a plain launch (A/B measurements).

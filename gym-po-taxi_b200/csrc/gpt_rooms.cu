@@ -10,6 +10,37 @@ namespace gpt {
 static const int kDY[8] = {-1, -1, 0, 1, 1, 1, 0, -1};
 static const int kDX[8] = {0, 1, 1, 1, 0, -1, -1, -1};
 
+// Walker alias tables for the slip (Philox mode): per intended action, n columns of {threshold, dir | alias<<8}
+std::vector<uint32_t> build_slip_alias(int n, const double* thr64) {
+  const int shift = n == 4 ? 1 : 0;
+  std::vector<uint32_t> alias((size_t)n * 8 * 2, 0u);
+  for (int a = 0; a < n; ++a) {
+    std::vector<double> q(n);
+    for (int j = 0; j < n; ++j) {
+      const double hi = j == n - 1 ? 1.0 : thr64[a * n + j];   // the last threshold never counts (= clamp to n-1)
+      const double lo = j == 0 ? 0.0 : thr64[a * n + j - 1];
+      q[j] = (hi > lo ? hi - lo : 0.0) * n;
+    }
+    std::vector<int> small, large, al(n);
+    std::vector<double> pr(n, 1.0);
+    for (int j = 0; j < n; ++j) { al[j] = j; (q[j] < 1.0 ? small : large).push_back(j); }
+    while (!small.empty() && !large.empty()) {
+      const int sidx = small.back(), lidx = large.back();
+      small.pop_back();
+      pr[sidx] = q[sidx];
+      al[sidx] = lidx;
+      q[lidx] = (q[lidx] + q[sidx]) - 1.0;
+      if (q[lidx] < 1.0) { large.pop_back(); small.push_back(lidx); }
+    }
+    for (int j = 0; j < n; ++j) {
+      const double t = pr[j] * 4294967296.0;
+      alias[((size_t)a * 8 + j) * 2] = t >= 4294967295.0 ? 0xFFFFFFFFu : (t <= 0 ? 0u : (uint32_t)t);
+      alias[((size_t)a * 8 + j) * 2 + 1] = (uint32_t)(j << shift) | ((uint32_t)(al[j] << shift) << 8);
+    }
+  }
+  return alias;
+}
+
 int rooms_build_tables(gpt_env* env, const gpt_config* c, bool discrete_actions) {
   const int h = c->rooms_h, w = c->rooms_w;
   if (h < 3 || w < 3 || h > 255 || w > 255 || (int64_t)h * w >= 32768) return fail(GPT_E_ARG, "rooms: grid shape out of range");
@@ -148,36 +179,8 @@ int rooms_build_tables(gpt_env* env, const gpt_config* c, bool discrete_actions)
     }
     move.clear();   // the merged kernels never read the plain move table
   }
-  // Walker alias tables for the slip (Philox mode): per intended action, n columns of {threshold, dir | alias<<8}
   std::vector<uint32_t> alias;
-  if (discrete_actions) {
-    const int n = c->rooms_n_actions, shift = n == 4 ? 1 : 0;
-    alias.assign((size_t)n * 8 * 2, 0u);
-    for (int a = 0; a < n; ++a) {
-      std::vector<double> q(n);
-      for (int j = 0; j < n; ++j) {
-        const double hi = j == n - 1 ? 1.0 : thr64[a * n + j];   // the last threshold never counts (= clamp to n-1)
-        const double lo = j == 0 ? 0.0 : thr64[a * n + j - 1];
-        q[j] = (hi > lo ? hi - lo : 0.0) * n;
-      }
-      std::vector<int> small, large, al(n);
-      std::vector<double> pr(n, 1.0);
-      for (int j = 0; j < n; ++j) { al[j] = j; (q[j] < 1.0 ? small : large).push_back(j); }
-      while (!small.empty() && !large.empty()) {
-        const int sidx = small.back(), lidx = large.back();
-        small.pop_back();
-        pr[sidx] = q[sidx];
-        al[sidx] = lidx;
-        q[lidx] = (q[lidx] + q[sidx]) - 1.0;
-        if (q[lidx] < 1.0) { large.pop_back(); small.push_back(lidx); }
-      }
-      for (int j = 0; j < n; ++j) {
-        const double t = pr[j] * 4294967296.0;
-        alias[((size_t)a * 8 + j) * 2] = t >= 4294967295.0 ? 0xFFFFFFFFu : (t <= 0 ? 0u : (uint32_t)t);
-        alias[((size_t)a * 8 + j) * 2 + 1] = (uint32_t)(j << shift) | ((uint32_t)(al[j] << shift) << 8);
-      }
-    }
-  }
+  if (discrete_actions) alias = build_slip_alias(c->rooms_n_actions, thr64.data());
   std::vector<uint8_t> blob;
   env->rl.move_off = blob_append(blob, move);
   env->rl.moveobs_off = blob_append(blob, moveobs);

@@ -14,7 +14,7 @@ LIB_PATH = os.environ.get("GPT_B200_LIB", os.path.join(_HERE, "..", "lib", "libg
 ABI_VERSION = 1
 ENV_ALIGN = 512
 
-FAMILY_TAXI, FAMILY_ROOMS, FAMILY_CROOMS, FAMILY_TAG, FAMILY_CAR = 0, 1, 2, 3, 4
+FAMILY_TAXI, FAMILY_ROOMS, FAMILY_CROOMS, FAMILY_TAG, FAMILY_CAR, FAMILY_MSROOMS = 0, 1, 2, 3, 4, 5
 RNG_PHILOX, RNG_REPLAY = 0, 1
 (OBS_ROOM, OBS_ROOM_GOAL, OBS_MDP, OBS_MDP_GOAL, OBS_VEC_MDP, OBS_VEC_MDP_GOAL, OBS_HANSEN, OBS_VEC_HANSEN,
  OBS_VEC_HANSEN_GOAL, OBS_GRID) = range(10)
@@ -45,6 +45,9 @@ class GptConfig(C.Structure):
         ("c_goal_threshold", C.c_double), ("c_use_velocity", C.c_int32), ("c_action_f64", C.c_int32),
         ("c_state_f32", C.c_int32), ("car_num_actions", C.c_int32),
         ("car_action_table", C.POINTER(C.c_double)),
+        # multistory rooms
+        ("ms_floors", C.c_int32), ("ms_goal_cell", C.c_int32), ("ms_up_y", C.c_int32), ("ms_up_x", C.c_int32),
+        ("ms_down_y", C.c_int32), ("ms_down_x", C.c_int32),
     ]
 
 

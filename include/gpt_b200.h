@@ -9,6 +9,7 @@
  *     CRoomsEnv.reset / .step           gym_po/envs/rooms/crooms.py:251-266, :276-298
  *     AntTagEnv pursuit rules           gym_po/envs/ant_tag.py:105-123, :144-153
  *     CarVecEnv.reset / .step           gym_po/envs/car_flag.py:87-95, :114-141
+ *     MultistoryFourRoomsEnv.reset/.step gym_po/envs/rooms/msrooms.py:371-383, :392-428
  * Each entry point below says which of those it replaces.  The Python host classes in
  * gym-po-taxi_b200/gym_po/ bind these symbols with ctypes.
  *
@@ -57,6 +58,7 @@ extern "C" {
 #define GPT_FAMILY_CROOMS 2 /* CRoomsEnv             rooms/crooms.py:91-338 */
 #define GPT_FAMILY_TAG 3    /* point-mass Tag built from AntTagEnv's pursuit rules, ant_tag.py:105-153 */
 #define GPT_FAMILY_CAR 4    /* CarVecEnv / DiscreteActionCarVecEnv   car_flag.py:23-144, :286-303 */
+#define GPT_FAMILY_MSROOMS 5 /* MultistoryFourRoomsEnv              rooms/msrooms.py:257-428 */
 
 /* random-number modes */
 #define GPT_RNG_PHILOX 0 /* Philox4x32-10, key = seed, counter = (global env id, step, stream) */
@@ -138,6 +140,18 @@ typedef struct gpt_config {
   int32_t car_num_actions;          /* CAR: 0 = continuous force [B,1] (float32, or float64 if c_action_f64); n > 0 =
                                        DiscreteActionCarVecEnv with n evenly spaced forces */
   const double* car_action_table;   /* CAR: [car_num_actions] = np.linspace(-1, 1, n) (car_flag.py:291) */
+
+  /* ---- MSROOMS (multistory FourRooms) ----
+   * uses rooms_h / rooms_w / rooms_grid = ONE floor's map [h*w], 0 wall, > 0 walkable (FR_MAP convention,
+   * msrooms.py:50-66), rooms_n_actions, rooms_slip_cumsum, rooms_obs_kind (not GPT_OBS_GRID), rooms_obs_n and the
+   * three rewards.  Cells are flat ids z*h*w + y*w + x.  Observation dtypes: scalar kinds int32 [B] (ROOM_GOAL may
+   * be negative, like the reference), VEC_MDP uint8 [B,3] (z,y,x), VEC_MDP_GOAL uint8 [B,6], VEC_HANSEN* uint8 [B,n]
+   * with 0 wall / 2 walkable / 3 goal (msrooms.py:131-160). */
+  int32_t ms_floors;                /* grid_z */
+  int32_t ms_goal_cell;             /* fixed goal (flat cell id), or -1 = random goal on the top floor every episode */
+  int32_t ms_up_y, ms_up_x;         /* stair-up cell of every floor but the top one (msrooms.py:21-24: (1,11)) */
+  int32_t ms_down_y, ms_down_x;     /* stair-down cell of every floor but the bottom one ((11,1)); taking the stairs up
+                                       lands on the stair-down cell of the floor above and vice versa (:419-428) */
 } gpt_config;
 
 typedef struct gpt_array_desc {

@@ -32,6 +32,8 @@ def make_env(family, b, seed):
         return oracle.RoomsOracle(b, "4", obs_type="grid", obs_n=9, draws=draws), 8
     if family == "crooms":
         return oracle.CRoomsOracle(b, "4", obs_type="vector_mdp", draws=draws), 0
+    if family == "msrooms":
+        return oracle.MSRoomsOracle(b, grid_z=3, draws=draws), 4
     if family == "car":
         return oracle.CarOracle(b, draws=draws), -1
     if family == "tag":

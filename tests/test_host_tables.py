@@ -95,3 +95,15 @@ def test_reset_law_is_a_distribution_and_matches_monte_carlo():
     # tiny case, exact by enumeration: 2 trials over 2 categories -> counts (2,0),(1,1),(0,2) w.p. 1/4,1/2,1/4
     np.testing.assert_allclose(argmax_multinomial_law(2, 2), [0.75, 0.25], atol=1e-12)
     np.testing.assert_allclose(argmax_multinomial_law(3, 2), [0.5, 0.5], atol=1e-12)
+
+
+def test_msrooms_host_map_matches_oracle():
+    """FR_MAP (built from room rectangles) and the multistory walk grid equal the oracle's, which is pinned
+    against the real reference; spawn / goal cell lists follow msrooms.py:306-313."""
+    from gym_po.envs.rooms import msrooms as M
+    from oracle import msrooms as O
+    np.testing.assert_array_equal(M.FR_MAP, O.FR_MAP)
+    for floors in (1, 2, 5):
+        np.testing.assert_array_equal(M.multistory_grid(M.FR_MAP, floors), O.multistory_grid(O.FR_MAP, floors))
+    assert tuple(O.UP_YX) == M.UPSTAIRS_YX and tuple(O.DOWN_YX) == M.DOWNSTAIRS_YX
+    assert M.END_XYZ == O.END_XYZ
