@@ -61,6 +61,14 @@ class GptHostIO(C.Structure):
                 ("terminated", C.c_void_p), ("truncated", C.c_void_p)]
 
 
+class GptWrapIO(C.Structure):
+    _fields_ = [("reward", C.c_void_p), ("terminated", C.c_void_p), ("truncated", C.c_void_p), ("ep_return", C.c_void_p),
+                ("ep_length", C.c_void_p), ("last_return", C.c_void_p), ("last_length", C.c_void_p),
+                ("disc_return", C.c_void_p), ("norm_reward", C.c_void_p)]
+
+
+WRAP_RECORD, WRAP_NORMALIZE = 1, 2
+
 #: every symbol include/gpt_b200.h declares: name -> (restype, argtypes)
 SIGNATURES = {
     "gpt_create": (C.c_int, [C.POINTER(GptConfig), C.POINTER(C.c_void_p)]),
@@ -81,6 +89,11 @@ SIGNATURES = {
     "gpt_set_env_offset": (C.c_int, [C.c_void_p, C.c_int64]),
     "gpt_stats_ptr": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
     "gpt_stats_reset": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "gpt_wrap_create": (C.c_int, [C.c_int, C.c_int64, C.c_int, C.c_double, C.c_double, C.POINTER(C.c_void_p)]),
+    "gpt_wrap_destroy": (C.c_int, [C.c_void_p]),
+    "gpt_wrap_step": (C.c_int, [C.c_void_p, C.POINTER(GptWrapIO), C.c_void_p]),
+    "gpt_wrap_state_ptr": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int32)]),
+    "gpt_wrap_launch_count": (C.c_int64, [C.c_void_p]),
     "gpt_last_error": (C.c_char_p, []),
     "gpt_abi_version": (C.c_int, []),
     "gpt_launch_count": (C.c_int64, [C.c_void_p]),

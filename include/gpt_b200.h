@@ -211,6 +211,37 @@ GPT_API int gpt_set_env_offset(gpt_env* env, int64_t env_offset);
 GPT_API int gpt_stats_ptr(gpt_env* env, void** device_ptr);
 GPT_API int gpt_stats_reset(gpt_env* env, void* stream);
 
+/* --- wrapper layer -----------------------------------------------------
+ * Device-side equivalents of the two gymnasium wrappers the reference's author stacks on the vector envs
+ * (gym_po/tester.py:36-41): RecordEpisodeStatistics and NormalizeReward, fused and family independent.  They
+ * read an env's OUTPUT arrays (reward, terminated, truncated: `capacity` rows) right after gpt_step on the same
+ * stream.  All per-env arrays are caller-owned, capacity = num_envs rounded up to GPT_ENV_ALIGN, zero-initialised
+ * by the caller before the first step. */
+#define GPT_WRAP_RECORD 1    /* RecordEpisodeStatistics */
+#define GPT_WRAP_NORMALIZE 2 /* NormalizeReward(gamma, epsilon) */
+typedef struct gpt_wrap gpt_wrap; /* opaque */
+typedef struct gpt_wrap_io {
+  const float* reward;       /* in  [cap] */
+  const uint8_t* terminated; /* in  [cap] */
+  const uint8_t* truncated;  /* in  [cap] */
+  float* ep_return;          /* RECORD state [cap]: running episode return */
+  int32_t* ep_length;        /* RECORD state [cap]: running episode length */
+  float* last_return;        /* RECORD out   [cap]: info["episode"]["r"] — the finished episode's return where
+                                terminated|truncated, else 0 */
+  int32_t* last_length;      /* RECORD out   [cap]: info["episode"]["l"] */
+  float* disc_return;        /* NORMALIZE state [cap]: returns = returns*gamma*(1-terminated) + reward */
+  float* norm_reward;        /* NORMALIZE out   [cap]: reward / sqrt(var(returns) + epsilon); may alias reward */
+} gpt_wrap_io;
+GPT_API int gpt_wrap_create(int device, int64_t num_envs, int flags, double gamma, double epsilon, gpt_wrap** out);
+GPT_API int gpt_wrap_destroy(gpt_wrap* w);
+/* one accumulate launch (+ one normalise launch with GPT_WRAP_NORMALIZE), asynchronous on `stream` */
+GPT_API int gpt_wrap_step(gpt_wrap* w, const gpt_wrap_io* io, void* stream);
+/* float64 device vector owned by the handle: [0..4] {episodes, sum_return, sum_length, sum_return^2, env_steps}
+ * (same layout as gpt_stats_ptr: all-reduce it across ranks), and at *rms_offset the CURRENT running
+ * {count, mean, var} of the discounted returns. */
+GPT_API int gpt_wrap_state_ptr(gpt_wrap* w, void** device_ptr, int32_t* rms_offset);
+GPT_API int64_t gpt_wrap_launch_count(const gpt_wrap* w);
+
 /* --- diagnostics -------------------------------------------------------------------------- */
 GPT_API const char* gpt_last_error(void);
 GPT_API int gpt_abi_version(void);

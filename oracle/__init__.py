@@ -33,3 +33,4 @@ from .crooms import CRoomsOracle  # noqa: F401
 from .tag import tag_move_target, TagOracle  # noqa: F401
 from .car import CarOracle  # noqa: F401
 from .msrooms import MSRoomsOracle  # noqa: F401
+from .wrappers import RecordEpisodeStatisticsOracle, NormalizeRewardOracle, RunningMeanStd  # noqa: F401
