@@ -75,8 +75,8 @@ class _DeviceWrapper:
     def _launch(self, reward, terminated, truncated):
         """reward / terminated / truncated: views of tensors with ``capacity`` rows (the env's output arrays)."""
         for name, t in (("reward", reward), ("terminated", terminated), ("truncated", truncated)):
-            base = t._base if t._base is not None else t
-            if base.shape[0] < self.capacity or t.data_ptr() != base.data_ptr():
+            if (t.storage_offset() != 0 or not t.is_contiguous()
+                    or t.untyped_storage().nbytes() < self.capacity * t.element_size()):
                 raise ValueError(f"{name} must be the leading view of a tensor with `capacity` rows")
             setattr(self._io, name, t.data_ptr())
         with torch.cuda.device(self.device):
