@@ -161,6 +161,7 @@ class TaxiVecEnv(DeviceVecEnv):
         self.num_envs = int(num_envs)
         self.GOAL_MOVE, self.BAD_MOVE, self.ANY_MOVE = reward_goal, reward_bad, reward_any
         self.rows, self.cols, wall_bits, loc_cells, is_wall = parse_taxi_map(map)
+        self._map_rows = tuple(map)
         self.hansen_encodings = wall_bits.reshape(self.rows, self.cols).astype(int)
         self.nlocs = len(loc_cells)
         self.np_locs = np.concatenate((np.stack(np.divmod(loc_cells, self.cols), -1), [[-1, -1]]))
@@ -260,11 +261,34 @@ class TaxiVecEnv(DeviceVecEnv):
     def reset(self, *, seed: Optional[int] = None, options: Optional[dict] = None):
         """Fully reset all environments -> ``(obs, {})`` (reference :232-242)."""
         self.lastaction = None
+        self._last_actions = None
         return self._reset(seed), {}
 
-    def render(self, idx=None):  # pragma: no cover - out of scope (SURVEY.md §2 row 1)
-        raise NotImplementedError("rendering is not part of the B200 hot path; copy env.s to the host and "
-                                  "render with the reference's cv2 code")
+    def step(self, actions):
+        out = super().step(actions)
+        self._last_actions = actions   # env 0's action is shown by render(); looked up lazily (no sync here)
+        return out
+
+    def render(self, idx=None):
+        """RGB frame of the selected envs (default: env 0), like the reference (:289-342): copies only their encoded
+        states to the host and draws there (gym_po/envs/taxi_render.py).  ``render_mode='human'`` also blits to a
+        pygame window when pygame is importable."""
+        from .taxi_render import render_taxi
+        idx = np.arange(1) if idx is None else np.atleast_1d(np.asarray(idx, dtype=np.int64))
+        s = self.s[torch.as_tensor(idx, device=self.device)].cpu().numpy()
+        name = None
+        last = getattr(self, "_last_actions", None)
+        if last is not None and not bool(self._terminated[0] | self._truncated[0]):   # reference :280
+            name = self.ACTION_NAMES[int(torch.as_tensor(last).reshape(-1)[0])]
+        img = render_taxi(self._map_rows, s, self.nlocs, self.np_locs, self.cols, self.hansen, name)
+        if self.render_mode == "human":  # pragma: no cover - needs a display
+            import pygame
+            if getattr(self, "_viewer", None) is None:
+                pygame.init()
+                self._viewer = pygame.display.set_mode(img.shape[:-1])
+            self._viewer.blit(pygame.surfarray.make_surface(img.swapaxes(0, 1)), (0, 0))
+            pygame.display.update()
+        return img
 
 
 HansenTaxiVecEnv = partial(TaxiVecEnv, hansen_obs=True)

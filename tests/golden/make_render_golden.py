@@ -1,0 +1,41 @@
+"""Generates render_taxi_*.npz by EXECUTING THE REAL REFERENCE's TaxiVecEnv.render (build container only:
+needs /root/reference and cv2).  Each fixture holds, for a handful of moments of a seeded rollout, the encoded
+states, the name of env 0's last action (or '') and the RGB frame the reference drew for idx = arange(k)."""
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(HERE, "..", ".."))
+from oracle.draws import make_generator  # noqa: E402
+from oracle.ref_loader import load_reference  # noqa: E402
+
+CASES = [("render_taxi_5x5", "TaxiVecEnv", 5), ("render_taxi_5x5_hansen", "HansenTaxiVecEnv", 3),
+         ("render_taxi_8x8", "ExtendedTaxiVecEnv", 4), ("render_taxi_8x8_hansen", "ExtendedHansenTaxiVecEnv", 1)]
+
+
+def main():
+    E = load_reference()
+    for name, cls, k in CASES:
+        env = getattr(E, cls)(8, time_limit=15)
+        env._np_random = make_generator(7)
+        env.reset()
+        rng = np.random.default_rng(3)
+        states, names, frames = [], [], []
+        for t in range(60):
+            if t % 7 == 0:
+                states.append(env.s[:k].copy())
+                names.append("" if env.lastaction is None else env.ACTION_NAMES[env.lastaction])
+                frames.append(env.render(idx=np.arange(k)).copy())
+            a = rng.integers(5, size=8)
+            if t % 2:
+                a[:] = 4          # plenty of pickups so that full taxis / passengers under the taxi show up
+            env.step(a)
+        np.savez_compressed(os.path.join(HERE, name + ".npz"), states=np.array(states), names=np.array(names),
+                            frames=np.array(frames), cls=cls)
+        print(name, np.array(frames).shape, sorted(set(names)))
+
+
+if __name__ == "__main__":
+    main()

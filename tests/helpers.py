@@ -15,7 +15,7 @@ INT_KINDS = {"multinomial_argmax", "integers", "choice"}
 
 def golden_names(prefix=""):
     names = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN, "*.npz")))
-    return [n for n in names if n.startswith(prefix) and n not in ("tag_move_target", "layout_grids")]
+    return [n for n in names if n.startswith(prefix) and n not in ("tag_move_target", "layout_grids") and not n.startswith("render_")]
 
 
 def load_golden(name):

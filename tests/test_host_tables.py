@@ -107,3 +107,22 @@ def test_msrooms_host_map_matches_oracle():
         np.testing.assert_array_equal(M.multistory_grid(M.FR_MAP, floors), O.multistory_grid(O.FR_MAP, floors))
     assert tuple(O.UP_YX) == M.UPSTAIRS_YX and tuple(O.DOWN_YX) == M.DOWNSTAIRS_YX
     assert M.END_XYZ == O.END_XYZ
+
+
+@pytest.mark.parametrize("name", ["render_taxi_5x5", "render_taxi_5x5_hansen", "render_taxi_8x8", "render_taxi_8x8_hansen"])
+def test_taxi_render_matches_reference_frames(name):
+    """the host-side renderer reproduces, pixel for pixel, the frames the REAL reference drew
+    (tests/golden/make_render_golden.py) for the same encoded states and last action."""
+    from gym_po.envs.extended_taxi import EXTENDED_TAXI_MAP, TAXI_MAP, parse_taxi_map
+    from gym_po.envs.taxi_render import render_taxi
+    z = np.load(os.path.join(ROOT, "tests", "golden", name + ".npz"))
+    m = EXTENDED_TAXI_MAP if "8x8" in name else TAXI_MAP
+    rows, cols, _, loc_cells, _ = parse_taxi_map(m)
+    np_locs = np.concatenate((np.stack(np.divmod(loc_cells, cols), -1), [[-1, -1]]))
+    seen = set()
+    for s, nm, frame in zip(z["states"], z["names"], z["frames"]):
+        got = render_taxi(m, s, len(loc_cells), np_locs, cols, "hansen" in name, str(nm) or None)
+        assert got.shape == frame.shape and got.dtype == np.uint8
+        np.testing.assert_array_equal(got, frame)
+        seen.add(str(nm))
+    assert len(seen) >= 2

@@ -282,3 +282,30 @@ def test_large_custom_map_uses_arithmetic_kernel():
     for _ in range(60):
         obs, *_ = env.step(torch.randint(0, 5, (1024,), dtype=torch.int8, device=DEV))
     assert int(obs.min()) >= 0 and int(obs.max()) < 9450
+
+
+@pytest.mark.parametrize("hansen", [False, True])
+def test_render_draws_device_state_like_the_reference(hansen):
+    """render(idx) copies the selected envs' states to the host and reproduces the reference
+    frames (fixtures drawn by the real reference for the same states)."""
+    from gym_po.envs import TaxiVecEnv
+    import os
+    from helpers import GOLDEN
+    z = np.load(os.path.join(GOLDEN, "render_taxi_5x5_hansen.npz" if hansen else "render_taxi_5x5.npz"))
+    env = TaxiVecEnv(64, hansen_obs=hansen, device=DEV, seed=0)
+    env.reset(seed=0)
+    for s, nm, frame in zip(z["states"], z["names"], z["frames"]):
+        k = len(s)
+        st = env.get_state()
+        st["s"][:k] = torch.as_tensor(s, device=DEV).to(torch.int32)
+        env.set_state(st["s"].cpu().numpy(), st["elapsed"].cpu().numpy(), st["ndrop"].cpu().numpy())
+        env._last_actions = None if not str(nm) else torch.full((64,), env.ACTION_NAMES.index(str(nm)), dtype=torch.int8)
+        env._terminated[:] = False
+        env._truncated[:] = False
+        np.testing.assert_array_equal(env.render(idx=np.arange(k)), frame)
+    # a real step records env 0's action; a finished episode clears the caption
+    env.step(torch.full((env.capacity,), 2, dtype=torch.int8, device=DEV))
+    a = env.render()
+    env._terminated[0] = True
+    b = env.render()
+    assert a.shape == b.shape == (176, 132, 3) and (a != b).any() and (b[:, -20:] == 0).all()
