@@ -100,6 +100,21 @@ class CarVecEnv(DeviceVecEnv):
     def reset(self, *, seed: Optional[int] = None, options: Optional[dict] = None):
         return self._reset(seed), {}
 
+    def render(self):
+        """Number-line frame of env 0 (reference car_flag.py:146-185): copies its 3 state floats + flag bits to
+        the host and draws there (gym_po/envs/car_render.py)."""
+        from .car_render import render_car
+        s0 = self.s[0].cpu().numpy()
+        img = render_car(float(s0[0]), float(s0[2]), float(self.heavens[0]), float(self.priests[0]))
+        if self.render_mode != "rgb_array" and self.render_mode is not None:  # pragma: no cover - needs a display
+            import pygame
+            if getattr(self, "viewer", None) is None:
+                pygame.init()
+                self.viewer = pygame.display.set_mode(img.shape[:-1])
+            self.viewer.blit(pygame.surfarray.make_surface(img), (0, 0))
+            pygame.display.update()
+        return img
+
 
 class DiscreteActionCarVecEnv(CarVecEnv):
     """Discrete action car environment: evenly spaced forces along the control dimension."""

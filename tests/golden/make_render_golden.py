@@ -35,6 +35,20 @@ def main():
         np.savez_compressed(os.path.join(HERE, name + ".npz"), states=np.array(states), names=np.array(names),
                             frames=np.array(frames), cls=cls)
         print(name, np.array(frames).shape, sorted(set(names)))
+    # car-flag: env 0's number-line frame along a rollout that drives towards the priest, then a flag
+    env = E.CarVecEnv(4, time_limit=400, render_mode="rgb_array")
+    env._np_random = make_generator(11)
+    env.reset()
+    rows = []
+    for t in range(330):
+        target = env.priests[0] if t < 120 else env.heavens[0]
+        env.step(np.full((4, 1), np.sign(target - env.s[0, 0]), dtype=np.float32))
+        if t % 15 == 0:
+            rows.append((env.s[0].copy(), env.heavens[0], env.priests[0], env.render().copy()))
+    np.savez_compressed(os.path.join(HERE, "render_car.npz"), s=np.array([r[0] for r in rows]),
+                        heavens=np.array([r[1] for r in rows]), priests=np.array([r[2] for r in rows]),
+                        frames=np.array([r[3] for r in rows]))
+    print("render_car", len(rows), sorted({float(r[0][2]) for r in rows}), sorted({float(r[1]) for r in rows}))
 
 
 if __name__ == "__main__":

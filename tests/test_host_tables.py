@@ -126,3 +126,11 @@ def test_taxi_render_matches_reference_frames(name):
         np.testing.assert_array_equal(got, frame)
         seen.add(str(nm))
     assert len(seen) >= 2
+
+
+def test_car_render_matches_reference_frames():
+    from gym_po.envs.car_render import render_car
+    z = np.load(os.path.join(ROOT, "tests", "golden", "render_car.npz"))
+    assert len(set(z["s"][:, 2].tolist())) >= 2                      # with and without the priest indicator
+    for s, h, p, frame in zip(z["s"], z["heavens"], z["priests"], z["frames"]):
+        np.testing.assert_array_equal(render_car(float(s[0]), float(s[2]), float(h), float(p)), frame)
