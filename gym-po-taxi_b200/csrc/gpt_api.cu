@@ -322,6 +322,25 @@ int gpt_step_many(gpt_env* env, const void* actions, int32_t n_steps, int64_t ou
   if (n_steps < 0 || out_stride_rows < 0) return fail(GPT_E_ARG, "gpt_step_many: negative argument");
   if (out_stride_rows != 0 && out_stride_rows < env->capacity) return fail(GPT_E_ARG, "gpt_step_many: out_stride_rows < capacity");
   const size_t arow = (size_t)env->action_cols * elem_size(env->action_dtype);
+  if (out_stride_rows) {
+    for (const ArraySlot& s : env->arrays)
+      if (s.desc.role == GPT_ROLE_OUTPUT && s.rows < (int64_t)(n_steps - 1) * out_stride_rows + env->capacity)
+        return fail(GPT_E_ARG, "gpt_step_many: bound output arrays are too small for n_steps*out_stride_rows");
+  }
+  static const bool no_fuse = getenv("GPT_NO_FUSED_STEPS") != nullptr;
+  const bool fuse = !no_fuse && n_steps > 1 && env->cfg.family == GPT_FAMILY_TAXI && taxi_can_fuse(env);
+  if (fuse) {  // one launch for all n_steps: state stays in registers, only actions are read and outputs written per step
+    LaunchArgs a;
+    a.mode = kModeStep;
+    a.actions = actions;
+    a.n_tiles = env->n_tiles;
+    a.stream = (cudaStream_t)stream;
+    a.n_steps = n_steps;
+    a.out_stride_rows = out_stride_rows;
+    int rc = launch(env, a);
+    env->counter += (uint64_t)n_steps;
+    return rc;
+  }
   for (int32_t t = 0; t < n_steps; ++t) {
     LaunchArgs a;
     a.mode = kModeStep;

@@ -95,7 +95,12 @@ struct LaunchArgs {
   int32_t first_tile = 0;
   int32_t n_tiles = 0;
   cudaStream_t stream = nullptr;
+  // fused multi-step launch (gpt_step_many on families whose *_can_fuse() says so): n_steps consecutive steps from
+  // an action stream [n_steps, capacity], outputs of step t at out_row + t*out_stride_rows
+  int32_t n_steps = 1;
+  int64_t out_stride_rows = 0;
 };
+bool taxi_can_fuse(const gpt_env* env);
 int taxi_launch(gpt_env* env, const LaunchArgs& a);
 int rooms_launch(gpt_env* env, const LaunchArgs& a);
 int crooms_launch(gpt_env* env, const LaunchArgs& a);

@@ -357,6 +357,150 @@ __global__ void __launch_bounds__(THREADS, (STATS || QPT > 2) ? 1 : 1280 / THREA
 }
 
 // ------------------------------------------------------------------------------------------
+// fused multi-step kernel: gpt_step_many() with n_steps > 1 (Philox mode, no statistics)
+// ------------------------------------------------------------------------------------------
+// T consecutive steps from an action stream [T, capacity] in ONE launch: the state (s, elapsed, ndrop) is read once,
+// lives in registers for the T steps and is written once; per step only the action byte is read and the outputs
+// (obs, reward, terminated, truncated) are written — 11 B per env-step + 18 B per env per launch instead of 29 B.
+// Results are bit-identical to T single-step launches: Philox counters are (global env id, first step + t).
+struct TaxiMultiParams {
+  TaxiParams p;
+  int32_t n_steps;
+  int64_t act_stride;   // bytes between consecutive steps' action rows (= capacity)
+  int64_t out_stride;   // rows between consecutive steps' outputs (0 = overwrite in place)
+};
+
+// rare branch, out of line: full reset (extended_taxi.py:344-352) or passenger respawn (:354-364) -> new state
+template <int DUMMY>
+__device__ __noinline__ uint32_t taxi_fix(const TaxiParams& P, const uint32_t* cdf, const uint16_t* valid, int64_t env, uint32_t t,
+                                          uint32_t cur, bool full) {
+  const uint64_t ctr = (((uint64_t)P.rng.step_hi << 32) | P.rng.step_lo) + t;
+  const uint64_t ge = (uint64_t)(P.env_offset + env);
+  const uint4 rnd = philox4x32_10(make_uint4((uint32_t)ge, (uint32_t)(ge >> 32), (uint32_t)ctr, (uint32_t)(ctr >> 32) & 0x00FFFFFFu), P.rng);
+  if (full) {
+    int lo = 0, hi = P.n_valid - 1;
+    while (lo < hi) {
+      const int mid = (lo + hi) >> 1;
+      if (rnd.x <= cdf[mid]) hi = mid; else lo = mid + 1;
+    }
+    return valid[lo];
+  }
+  const uint32_t cell = fdiv(cur, P.div_pd);
+  const uint32_t p = bounded(rnd.y, (uint32_t)P.nlocs);
+  uint32_t d = bounded(rnd.z, (uint32_t)P.nlocs - 1);
+  d += d >= p ? 1u : 0u;
+  return (cell * (uint32_t)(P.nlocs + 1) + p) * (uint32_t)P.nlocs + d;
+}
+
+#ifndef GPT_TAXI_MULTI_MINB
+#define GPT_TAXI_MULTI_MINB 8
+#endif
+template <bool HANSEN, int QPT, int THREADS>
+__global__ void __launch_bounds__(THREADS, GPT_TAXI_MULTI_MINB) taxi_table_multi_kernel(const __grid_constant__ TaxiMultiParams M) {
+  const TaxiParams& P = M.p;
+  extern __shared__ __align__(128) uint8_t smem[];
+  __shared__ uint64_t bar;
+  pdl_launch_dependents();
+  stage_tables_begin(smem, P.blob, P.blob_bytes, &bar);
+
+  constexpr int kEnvsPerWarp = kWarp * kQuad * QPT;
+  const uint32_t lane = threadIdx.x & 31u;
+  const int64_t wtile = (int64_t)blockIdx.x * (THREADS / 32) + (threadIdx.x >> 5);
+  const int64_t first = (int64_t)P.first_tile * kTileEnvs, last = first + (int64_t)P.n_tiles * kTileEnvs;
+  const int64_t base = first + wtile * kEnvsPerWarp + lane * kQuad;
+  if (base >= last) return;
+
+  pdl_wait();
+  int32_t sv[QPT][4], ev[QPT][4];
+  uint32_t ndv[QPT][4], a4[QPT];
+#pragma unroll
+  for (int j = 0; j < QPT; ++j) {
+    const int64_t q = base + j * kQuadStride;
+    const int4 s4 = ld_stream(reinterpret_cast<const int4*>(P.s + q));
+    const int4 e4 = ld_stream(reinterpret_cast<const int4*>(P.elapsed + q));
+    const uint32_t nd4 = ld_stream(reinterpret_cast<const uint32_t*>(P.ndrop + q));
+    a4[j] = ld_stream(reinterpret_cast<const uint32_t*>(P.actions + q));
+    sv[j][0] = s4.x; sv[j][1] = s4.y; sv[j][2] = s4.z; sv[j][3] = s4.w;
+    ev[j][0] = e4.x; ev[j][1] = e4.y; ev[j][2] = e4.z; ev[j][3] = e4.w;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) ndv[j][k] = (nd4 >> (8 * k)) & 0xFFu;
+  }
+  stage_tables_wait(&bar);
+  const uint16_t* trans = reinterpret_cast<const uint16_t*>(smem + P.trans_off);
+  const uint16_t* hobs = reinterpret_cast<const uint16_t*>(smem + P.hobs_off);
+  const uint32_t* cdf = reinterpret_cast<const uint32_t*>(smem + P.cdf_off);
+  const uint16_t* valid = reinterpret_cast<const uint16_t*>(smem + P.vs_off);
+
+#pragma unroll 1
+  for (int32_t t = 0; t < M.n_steps; ++t) {
+    // prefetch the next step's action bytes (the only per-step read) before this step's dependent table lookups
+    uint32_t a_next[QPT];
+    const bool more = t + 1 < M.n_steps;
+#pragma unroll
+    for (int j = 0; j < QPT; ++j)
+      a_next[j] = more ? ld_stream(reinterpret_cast<const uint32_t*>(P.actions + (int64_t)(t + 1) * M.act_stride + base + j * kQuadStride)) : 0u;
+    const int64_t orow = (int64_t)t * M.out_stride;
+#pragma unroll
+    for (int j = 0; j < QPT; ++j) {
+      const int64_t q = base + j * kQuadStride;
+      float rv[4];
+      int32_t ov[4];
+      uint32_t tw = 0, trw = 0, fixm = 0;   // fixm bit k: full reset, bit 4+k: passenger respawn
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const uint32_t a = min((a4[j] >> (8 * k)) & 0xFFu, (uint32_t)(kTransCols - 1));
+        const uint32_t ent = trans[(uint32_t)sv[j][k] * kTransCols + a];
+        const uint32_t goal = (ent >> 13) & 1u;
+        ndv[j][k] += goal;
+        sv[j][k] = (int32_t)(ent & kTransState);
+        ev[j][k] += 1;
+        rv[k] = goal ? P.r_goal : ((ent & kTransBad) ? P.r_bad : P.r_any);
+        const uint32_t term = ndv[j][k] == (uint32_t)P.n_dropoffs;
+        const uint32_t trunc = ev[j][k] > P.time_limit;
+        const uint32_t done = term | trunc;
+        fixm |= (done << k) | ((goal & ~done & 1u) << (4 + k));
+        tw |= term << (8 * k);
+        trw |= trunc << (8 * k);
+      }
+      if (fixm) {  // rare: one divergence point per quad
+#pragma unroll 1
+        for (uint32_t m = (fixm | (fixm >> 4)) & 0xFu; m; m &= m - 1) {
+          const int k = __ffs(m) - 1;
+          const bool full = (fixm >> k) & 1u;
+          uint32_t cur = 0;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) cur = i == k ? (uint32_t)sv[j][i] : cur;
+          const uint32_t fresh = taxi_fix<0>(P, cdf, valid, q + k, (uint32_t)t, cur, full);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            if (i == k) {
+              sv[j][i] = (int32_t)fresh;
+              ev[j][i] = full ? 0 : ev[j][i];
+              ndv[j][i] = full ? 0u : ndv[j][i];
+            }
+          }
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) ov[k] = HANSEN ? (int32_t)hobs[sv[j][k]] : sv[j][k];
+      st_stream(reinterpret_cast<int4*>(P.obs + orow + q), make_int4(ov[0], ov[1], ov[2], ov[3]));
+      st_stream(reinterpret_cast<float4*>(P.reward + orow + q), make_float4(rv[0], rv[1], rv[2], rv[3]));
+      st_stream(reinterpret_cast<uint32_t*>(P.terminated + orow + q), tw);
+      st_stream(reinterpret_cast<uint32_t*>(P.truncated + orow + q), trw);
+      a4[j] = a_next[j];
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < QPT; ++j) {
+    const int64_t q = base + j * kQuadStride;
+    st_stream(reinterpret_cast<int4*>(P.s + q), make_int4(sv[j][0], sv[j][1], sv[j][2], sv[j][3]));
+    st_stream(reinterpret_cast<int4*>(P.elapsed + q), make_int4(ev[j][0], ev[j][1], ev[j][2], ev[j][3]));
+    st_stream(reinterpret_cast<uint32_t*>(P.ndrop + q),
+              (ndv[j][0] & 0xFFu) | ((ndv[j][1] & 0xFFu) << 8) | ((ndv[j][2] & 0xFFu) << 16) | ((ndv[j][3] & 0xFFu) << 24));
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------
 int taxi_create(gpt_env* env, const gpt_config* c) {
@@ -447,6 +591,10 @@ int taxi_create(gpt_env* env, const gpt_config* c) {
   return GPT_OK;
 }
 
+bool taxi_can_fuse(const gpt_env* env) {
+  return env->taxi_use_table && env->cfg.rng_mode == GPT_RNG_PHILOX && !env->cfg.track_stats;
+}
+
 int taxi_launch(gpt_env* env, const LaunchArgs& a) {
   const gpt_config& c = env->cfg;
   TaxiParams P{};
@@ -513,6 +661,26 @@ int taxi_launch(gpt_env* env, const LaunchArgs& a) {
   P.div_pd = make_fastdiv((uint32_t)(c.taxi_nlocs + 1) * (uint32_t)c.taxi_nlocs);
   if (a.n_tiles <= 0) return GPT_OK;
   const size_t smem = env->blob_bytes;
+  if (a.n_steps > 1) {  // fused multi-step launch (gpt_step_many); eligibility is checked by taxi_can_fuse()
+    TaxiMultiParams M;
+    M.p = P;
+    M.n_steps = a.n_steps;
+    M.act_stride = env->capacity;
+    M.out_stride = a.out_stride_rows;
+    using KM = void (*)(const TaxiMultiParams);
+    KM km = c.taxi_hansen_obs ? (KM)taxi_table_multi_kernel<true, 2, 128> : (KM)taxi_table_multi_kernel<false, 2, 128>;
+    const int64_t envs_per_cta = 128 * kQuad * 2;
+    const int grid = (int)(((int64_t)a.n_tiles * kTileEnvs + envs_per_cta - 1) / envs_per_cta);
+    if (smem > 40 * 1024) {
+      cudaError_t e = cudaFuncSetAttribute((const void*)km, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(taxi multi)");
+    }
+    void* margs[] = {(void*)&M};
+    cudaError_t e = launch_pdl((const void*)km, dim3(grid), dim3(128), smem, a.stream, margs);
+    env->launches += 1;
+    if (e != cudaSuccess) return cuda_fail(e, "taxi multi-step kernel launch");
+    return GPT_OK;
+  }
   using K = void (*)(const TaxiParams);
   K k;
   int threads, grid;

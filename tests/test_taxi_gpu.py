@@ -309,3 +309,43 @@ def test_render_draws_device_state_like_the_reference(hansen):
     env._terminated[0] = True
     b = env.render()
     assert a.shape == b.shape == (176, 132, 3) and (a != b).any() and (b[:, -20:] == 0).all()
+
+
+@pytest.mark.parametrize("kw", [dict(), dict(hansen_obs=True, num_passengers=3, time_limit=17),
+                                dict(map="ext", time_limit=9)])
+def test_fused_multi_step_launch_equals_single_steps(kw):
+    """gpt_step_many on Taxi runs T steps in ONE launch (state in registers); outputs of every step and the final
+    state must be bit-identical to T single-step launches (Philox counters = (global env id, step))."""
+    from gym_po.envs import EXTENDED_TAXI_MAP, TaxiVecEnv
+    kw = dict(kw)
+    if kw.get("map") == "ext":
+        kw["map"] = EXTENDED_TAXI_MAP
+    b, T = 3000, 37
+    a = TaxiVecEnv(b, device=DEV, seed=9, **kw)
+    c = TaxiVecEnv(b, device=DEV, seed=9, **kw)
+    a.reset(seed=9); c.reset(seed=9)
+    gen = torch.Generator(device=DEV).manual_seed(4)
+    for rep in range(3):
+        acts = torch.randint(0, 5, (T, a.capacity), dtype=torch.int8, device=DEV, generator=gen)
+        if rep == 1:
+            acts[:] = 4                      # deliveries / illegal pickups on every step
+        out = {n: torch.zeros((T,) + tuple(a._arrays[n].shape), dtype=a._arrays[n].dtype, device=DEV)
+               for n in ("obs", "reward", "terminated", "truncated")}
+        l0 = a.launch_count
+        a.step_many(acts, out)
+        assert a.launch_count == l0 + 1      # one fused launch
+        for t in range(T):
+            o = c.step(acts[t])
+            for n, x in zip(("obs", "reward", "terminated", "truncated"), o[:4]):
+                assert torch.equal(out[n][t][:b].view(x.dtype), x), (n, rep, t)
+        sa, sc = a.get_state(), c.get_state()
+        for k in sa:
+            assert torch.equal(sa[k], sc[k]), k
+        assert a.rng_counter == c.rng_counter
+    # in-place outputs (no rollout storage): the arrays hold the LAST step's results
+    acts = torch.randint(0, 5, (5, a.capacity), dtype=torch.int8, device=DEV, generator=gen)
+    a.step_many(acts)
+    for t in range(5):
+        o = c.step(acts[t])
+    for n, x in zip(("obs", "reward"), o[:2]):
+        assert torch.equal(a._arrays[n][:b], x)
