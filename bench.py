@@ -276,6 +276,24 @@ def run_b200(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_max = float(t.item())
 
+    # ---- when step_many ran as fused launches, also time one launch per step (what env.step() costs)
+    single = None
+    if launches < args.steps:
+        env.set_fused_steps(False)
+        run_steps(SLOTS * 4)
+        torch.cuda.synchronize()
+        k1 = min(args.steps, 1000)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        run_steps(k1)
+        e1.record()
+        torch.cuda.synchronize()
+        ts = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(ts, op=dist.ReduceOp.MAX)
+        single = (k1, float(ts.item()))
+        env.set_fused_steps(True)
+
     # ---- end-to-end: public API with HOST buffers (pinned), H2D + step + D2H inside the timed region
     if args.e2e_steps is not None:
         e2e_steps = max(1, args.e2e_steps)
@@ -339,6 +357,12 @@ def run_b200(args):
             "gpu_launches": launches * world,
             "clocks": sampler.summary(),
         }
+        if single is not None:
+            k1, ms1 = single
+            ach1 = wl["alg_bytes"] * cap / (ms1 * 1e-3 / k1) / 1e9
+            line["single_step_launches"] = {"value": total_envs * k1 / (ms1 * 1e-3), "unit": UNIT, "steps": k1, "kernel_us": ms1 * 1e3 / k1,
+                                            "alg_bytes_per_env_step": wl["alg_bytes"], "achieved": ach1, "frac": ach1 / peak,
+                                            "note": "same workload with one launch per step (gpt_step): state read and written every step"}
         traffic_file = os.path.join(ROOT, "profiles", f"traffic_{args.workload}.json")
         if os.path.exists(traffic_file):
             try:

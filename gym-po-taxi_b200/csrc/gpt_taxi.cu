@@ -50,7 +50,8 @@ struct TaxiParams {
   const int8_t* rp_new_d;
   const uint8_t* blob;
   uint32_t blob_bytes, cdf_off, vs_off, rep_shift;
-  uint32_t trans_off, hobs_off;   // table kernel: transition table / hansen obs table offsets in the blob
+  uint32_t trans_off, hobs_off;   // fused kernel: 32-bit transition table / per-state observation table offsets in the blob
+  uint32_t trans16_off, alias_off, single_bytes;   // single-step kernel: compact table, reset alias table, bytes to stage
   FastDiv div_pd;                 // divide by (nlocs+1)*nlocs
   int64_t env_offset;
   int32_t first_tile, n_tiles;
@@ -214,17 +215,196 @@ __global__ void __launch_bounds__(256) taxi_arith_kernel(const __grid_constant__
 
 
 // ------------------------------------------------------------------------------------------
-// table-driven kernel
+// table-driven kernel (both reference maps): single steps AND fused multi-step launches
 // ------------------------------------------------------------------------------------------
-constexpr uint32_t kTransState = 0x1FFFu, kTransGoal = 1u << 13, kTransBad = 1u << 14;
-constexpr int kTransCols = 6;  // actions 0..4 + "no-op" column for out-of-range action bytes
+// trans: [state][8 actions] uint32, one 32-byte row per state.  An entry holds everything the step needs:
+//   bits 31-16  observation of the next state (state id, or the Hansen re-encoding, extended_taxi.py:366-372)
+//   bits 15-5   byte offset of the next state's row (the kernel keeps the state as this offset, so the next lookup
+//               address is one 3-input add: table base + row offset + 4*action)
+//   bit 1 / 0   illegal pickup-dropoff / delivery
+// Action bytes 5..7 are no-op columns; larger bytes wrap modulo 8 (the reference raises IndexError).
+constexpr int kRowShift = 5;
+constexpr uint32_t kTransGoal = 1u, kTransBad = 2u, kTransRow = 0xFFE0u;
+constexpr int kTransCols = 8;
+constexpr int64_t kTableMaxStates = 65536 >> kRowShift;   // row offsets must fit 16 bits
+
+// T consecutive steps from an action stream [T, capacity] in ONE launch (gpt_step_many): the state (s, elapsed,
+// ndrop) is read once, lives in registers for the T steps and is written once; per step only the action byte is
+// read and the outputs are written — 11 B per env-step + 18 B per env per launch instead of 29 B.  Results are
+// bit-identical to T single-step launches: Philox counters are (global env id, first step + t).
+struct TaxiMultiParams {
+  TaxiParams p;
+  int32_t n_steps;
+  int64_t act_stride;   // bytes between consecutive steps' action rows (= capacity)
+  int64_t out_stride;   // rows between consecutive steps' outputs (0 = overwrite in place)
+};
+
+// Rare branch, out of line (one copy per kernel): full reset (extended_taxi.py:344-352) or passenger respawn
+// (:354-364) -> new state id.  `t` = step index inside a fused launch.
+template <bool REPLAY>
+__device__ __noinline__ uint32_t taxi_fix(const TaxiParams& P, const uint2* alias, int64_t env, uint32_t t, uint32_t cur, bool full) {
+  if (REPLAY) {
+    if (full) return (uint32_t)P.rp_reset_state[env];
+    const uint32_t cell = fdiv(cur, P.div_pd);
+    return (cell * (uint32_t)(P.nlocs + 1) + (uint32_t)P.rp_new_p[env]) * (uint32_t)P.nlocs + (uint32_t)P.rp_new_d[env];
+  }
+  const uint64_t ctr = (((uint64_t)P.rng.step_hi << 32) | P.rng.step_lo) + t;
+  const uint64_t ge = (uint64_t)(P.env_offset + env);
+  const uint4 rnd = philox4x32_10(make_uint4((uint32_t)ge, (uint32_t)(ge >> 32), (uint32_t)ctr, (uint32_t)(ctr >> 32) & 0x00FFFFFFu), P.rng);
+  if (full) {  // the law of argmax(multinomial(ns, uniform over valid states)), sampled through its alias table
+    const uint64_t w = (uint64_t)rnd.x * (uint32_t)P.n_valid;
+    const uint2 e = alias[(uint32_t)(w >> 32)];
+    return ((uint32_t)w < e.x) ? (e.y & 0xFFFFu) : (e.y >> 16);
+  }
+  const uint32_t cell = fdiv(cur, P.div_pd);   // taxi cell kept, p uniform, d uniform over the other locations
+  const uint32_t p = bounded(rnd.y, (uint32_t)P.nlocs);
+  uint32_t d = bounded(rnd.z, (uint32_t)P.nlocs - 1);
+  d += d >= p ? 1u : 0u;
+  return (cell * (uint32_t)(P.nlocs + 1) + p) * (uint32_t)P.nlocs + d;
+}
+
+#ifndef GPT_TAXI_MINB_MULTI
+#define GPT_TAXI_MINB_MULTI 6   // measured on B200 (2^22 envs, 8 steps per launch): 5 -> 380 G, 6 -> 405 G, 7 -> 389 G, 8 -> 304 G
+#endif
+template <bool STATS, int QPT, int THREADS>
+__global__ void __launch_bounds__(THREADS, STATS ? 1 : GPT_TAXI_MINB_MULTI) taxi_table_multi_kernel(const __grid_constant__ TaxiMultiParams M) {
+  constexpr bool REPLAY = false;   // replayed draws are per step: replay mode uses the single-step kernel
+  const TaxiParams& P = M.p;
+  const int32_t n_steps = M.n_steps;
+  extern __shared__ __align__(128) uint8_t smem[];
+  __shared__ uint64_t bar;
+  pdl_launch_dependents();
+  stage_tables_begin(smem, P.blob, P.blob_bytes, &bar);
+
+  constexpr int kEnvsPerWarp = kWarp * kQuad * QPT;
+  const uint32_t lane = threadIdx.x & 31u;
+  const int64_t first = (int64_t)P.first_tile * kTileEnvs, last = first + (int64_t)P.n_tiles * kTileEnvs;
+  // reset() is not a separate code path: the host poisons `elapsed` so that every env truncates and
+  // launches this same kernel (taxi_launch), which keeps the hot loop free of mode branches.
+  const uint8_t* trans = smem + P.trans_off;
+  const uint16_t* hobs = reinterpret_cast<const uint16_t*>(smem + P.hobs_off);   // observation per state id (fix path)
+  const uint2* alias = reinterpret_cast<const uint2*>(smem + P.alias_off);
+  EpisodeAcc acc;
+  const int64_t wtile = (int64_t)blockIdx.x * (THREADS / 32) + (threadIdx.x >> 5);
+  const int64_t base = first + wtile * kEnvsPerWarp + lane * kQuad;
+  if (base >= last) return;
+  pdl_wait();   // the previous launch's writes are complete and visible from here on
+  uint32_t off[QPT][4], ndv[QPT][4], a4[QPT];   // off = state id << kRowShift
+  int32_t ev[QPT][4];
+  float ret[STATS ? QPT : 1][4];
+#pragma unroll
+  for (int j = 0; j < QPT; ++j) {
+    const int64_t q = base + j * kQuadStride;
+    const int4 s4 = ld_stream(reinterpret_cast<const int4*>(P.s + q));
+    const int4 e4 = ld_stream(reinterpret_cast<const int4*>(P.elapsed + q));
+    const uint32_t nd4 = ld_stream(reinterpret_cast<const uint32_t*>(P.ndrop + q));
+    a4[j] = ld_stream(reinterpret_cast<const uint32_t*>(P.actions + q));
+    off[j][0] = (uint32_t)s4.x << kRowShift; off[j][1] = (uint32_t)s4.y << kRowShift;
+    off[j][2] = (uint32_t)s4.z << kRowShift; off[j][3] = (uint32_t)s4.w << kRowShift;
+    ev[j][0] = e4.x; ev[j][1] = e4.y; ev[j][2] = e4.z; ev[j][3] = e4.w;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) ndv[j][k] = (nd4 >> (8 * k)) & 0xFFu;
+    if constexpr (STATS) {
+      const float4 r4 = __ldcs(reinterpret_cast<const float4*>(P.ep_return + q));
+      ret[j][0] = r4.x; ret[j][1] = r4.y; ret[j][2] = r4.z; ret[j][3] = r4.w;
+    }
+  }
+  stage_tables_wait(&bar);
+
+#pragma unroll 1
+  for (int32_t t = 0; t < n_steps; ++t) {
+    // prefetch the next step's action bytes (the only per-step read) ahead of this step's dependent table lookups
+    uint32_t a_next[QPT];
+    const bool more = t + 1 < n_steps;
+#pragma unroll
+    for (int j = 0; j < QPT; ++j) {
+      a_next[j] = 0u;
+      if (more) a_next[j] = ld_stream(reinterpret_cast<const uint32_t*>(P.actions + (int64_t)(t + 1) * M.act_stride + base + j * kQuadStride));
+    }
+    const int64_t orow = (int64_t)t * M.out_stride;
+#pragma unroll
+    for (int j = 0; j < QPT; ++j) {
+      const int64_t q = base + j * kQuadStride;
+      float rv[4];
+      int32_t ov[4];
+      uint32_t tw = 0, trw = 0, gw = 0;   // terminated / truncated / delivered, one byte per env
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const uint32_t aoff = (k == 0 ? (a4[j] << 2) : (a4[j] >> (8 * k - 2))) & 0x1Cu;   // 4 * (action & 7)
+        const uint32_t ent = *reinterpret_cast<const uint32_t*>(trans + off[j][k] + aoff);
+        const uint32_t goal = ent & kTransGoal;
+        ndv[j][k] += goal;
+        off[j][k] = ent & kTransRow;
+        ov[k] = (int32_t)(ent >> 16);
+        ev[j][k] += 1;
+        rv[k] = goal ? P.r_goal : ((ent & kTransBad) ? P.r_bad : P.r_any);
+        const uint32_t term = ndv[j][k] == (uint32_t)P.n_dropoffs;      // (:276-279)
+        const uint32_t trunc = ev[j][k] > P.time_limit;
+        tw |= term << (8 * k);
+        trw |= trunc << (8 * k);
+        gw |= goal << (8 * k);
+        if constexpr (STATS) {
+          ret[j][k] += rv[k];
+          if (q + k < P.num_envs) {
+            acc.steps += 1.f;
+            if (term | trunc) acc.finish(ret[j][k], ev[j][k]);
+          }
+          ret[j][k] = (term | trunc) ? 0.f : ret[j][k];
+        }
+      }
+      if (tw | trw | gw) {  // rare: full reset of finished envs, passenger respawn after a delivery (:283-286)
+        const uint32_t donew = tw | trw;
+#pragma unroll 1
+        for (uint32_t m = donew | gw; m; m &= m - 1) {
+          const int k = (__ffs(m) - 1) >> 3;
+          const bool full = (donew >> (8 * k)) & 1u;
+          uint32_t cur = 0;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) cur = i == k ? off[j][i] : cur;
+          const uint32_t fresh = taxi_fix<REPLAY>(P, alias, q + k, (uint32_t)t, cur >> kRowShift, full);
+          const int32_t fobs = (int32_t)hobs[fresh];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            if (i == k) {
+              off[j][i] = fresh << kRowShift;
+              ov[i] = fobs;
+              ev[j][i] = full ? 0 : ev[j][i];
+              ndv[j][i] = full ? 0u : ndv[j][i];
+            }
+          }
+        }
+      }
+      st_stream(reinterpret_cast<int4*>(P.obs + orow + q), make_int4(ov[0], ov[1], ov[2], ov[3]));
+      st_stream(reinterpret_cast<float4*>(P.reward + orow + q), make_float4(rv[0], rv[1], rv[2], rv[3]));
+      st_stream(reinterpret_cast<uint32_t*>(P.terminated + orow + q), tw);
+      st_stream(reinterpret_cast<uint32_t*>(P.truncated + orow + q), trw);
+      a4[j] = a_next[j];
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < QPT; ++j) {
+    const int64_t q = base + j * kQuadStride;
+    st_stream(reinterpret_cast<int4*>(P.s + q), make_int4((int)(off[j][0] >> kRowShift), (int)(off[j][1] >> kRowShift),
+                                                          (int)(off[j][2] >> kRowShift), (int)(off[j][3] >> kRowShift)));
+    st_stream(reinterpret_cast<int4*>(P.elapsed + q), make_int4(ev[j][0], ev[j][1], ev[j][2], ev[j][3]));
+    st_stream(reinterpret_cast<uint32_t*>(P.ndrop + q),
+              (ndv[j][0] & 0xFFu) | ((ndv[j][1] & 0xFFu) << 8) | ((ndv[j][2] & 0xFFu) << 16) | ((ndv[j][3] & 0xFFu) << 24));
+    if constexpr (STATS) st_stream(reinterpret_cast<float4*>(P.ep_return + q), make_float4(ret[j][0], ret[j][1], ret[j][2], ret[j][3]));
+  }
+  if constexpr (STATS) acc.flush(P.stats);
+}
+
+
+// ---- single-step kernel (gpt_step, replay mode, reset): compact 16-bit table, rare envs patched in memory ----
+constexpr uint32_t kT16State = 0x1FFFu, kT16Goal = 1u << 13, kT16Bad = 1u << 14;
+constexpr int kT16Cols = 6;  // actions 0..4 + "no-op" column for out-of-range action bytes
 
 template <bool HANSEN, bool REPLAY, bool STATS, int QPT, int THREADS>
 __global__ void __launch_bounds__(THREADS, (STATS || QPT > 2) ? 1 : 1280 / THREADS) taxi_table_kernel(const __grid_constant__ TaxiParams P) {
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ uint64_t bar;
   pdl_launch_dependents();
-  stage_tables_begin(smem, P.blob, P.blob_bytes, &bar);
+  stage_tables_begin(smem, P.blob, P.single_bytes, &bar);   // the 32-bit table of the fused kernel lies behind
 
   constexpr int kEnvsPerWarp = kWarp * kQuad * QPT;
   const uint32_t lane = threadIdx.x & 31u;
@@ -253,10 +433,9 @@ __global__ void __launch_bounds__(THREADS, (STATS || QPT > 2) ? 1 : 1280 / THREA
   }
 
   stage_tables_wait(&bar);
-  const uint16_t* trans = reinterpret_cast<const uint16_t*>(smem + P.trans_off);
+  const uint16_t* trans = reinterpret_cast<const uint16_t*>(smem + P.trans16_off);
   const uint16_t* hobs = reinterpret_cast<const uint16_t*>(smem + P.hobs_off);
-  const uint32_t* cdf = reinterpret_cast<const uint32_t*>(smem + P.cdf_off);
-  const uint16_t* valid = reinterpret_cast<const uint16_t*>(smem + P.vs_off);
+  const uint2* alias = reinterpret_cast<const uint2*>(smem + P.alias_off);
 
   uint32_t reset_mask = 0u;                                               // bit 4j+k: env needs a full reset
   uint32_t respawn_mask = 0u;                                             // bit 4j+k: new passenger + destination
@@ -273,13 +452,13 @@ __global__ void __launch_bounds__(THREADS, (STATS || QPT > 2) ? 1 : 1280 / THREA
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       {
-        const uint32_t a = min((a4[j] >> (8 * k)) & 0xFFu, (uint32_t)(kTransCols - 1));
-        const uint32_t ent = trans[(uint32_t)sv[k] * kTransCols + a];
+        const uint32_t a = min((a4[j] >> (8 * k)) & 7u, (uint32_t)(kT16Cols - 1));   // bytes wrap modulo 8; 5..7 are no-ops
+        const uint32_t ent = trans[(uint32_t)sv[k] * kT16Cols + a];
         const uint32_t goal = (ent >> 13) & 1u;
         const uint32_t nd = ((nd4[j] >> (8 * k)) & 0xFFu) + goal;
-        sv[k] = (int32_t)(ent & kTransState);
+        sv[k] = (int32_t)(ent & kT16State);
         ev[k] += 1;
-        rv[k] = goal ? P.r_goal : ((ent & kTransBad) ? P.r_bad : P.r_any);
+        rv[k] = goal ? P.r_goal : ((ent & kT16Bad) ? P.r_bad : P.r_any);
         const uint32_t term = nd == (uint32_t)P.n_dropoffs;
         const uint32_t trunc = ev[k] > P.time_limit;
         const uint32_t done = term | trunc;
@@ -319,184 +498,17 @@ __global__ void __launch_bounds__(THREADS, (STATS || QPT > 2) ? 1 : 1280 / THREA
     const int b = __ffs(todo) - 1;
     todo &= todo - 1;
     const int64_t env = base + (b >> 2) * kQuadStride + (b & 3);
-    uint4 rnd = make_uint4(0, 0, 0, 0);
-    if (!REPLAY) rnd = env_random(P.rng, (uint64_t)(P.env_offset + env), 0u);
-    uint32_t fresh;
-    if ((reset_mask >> b) & 1u) {  // _reset_mask (extended_taxi.py:344-352)
-      if (REPLAY) {
-        fresh = (uint32_t)P.rp_reset_state[env];
-      } else {  // inverse CDF of the law of argmax(multinomial(ns, uniform over valid states))
-        int lo = 0, hi = P.n_valid - 1;
-        while (lo < hi) {
-          const int mid = (lo + hi) >> 1;
-          if (rnd.x <= cdf[mid]) hi = mid; else lo = mid + 1;
-        }
-        fresh = valid[lo];
-      }
+    const bool full = (reset_mask >> b) & 1u;
+    int32_t cur = 0;
+#pragma unroll
+    for (int i = 0; i < 4 * QPT; ++i) cur = i == b ? keep_s[i] : cur;
+    const uint32_t fresh = taxi_fix<REPLAY>(P, alias, env, 0u, (uint32_t)cur, full);   // same sampler as the fused kernel
+    if (full) {
       P.elapsed[env] = 0;
       P.ndrop[env] = 0;
-    } else {  // _reset_passenger_and_destination (:354-364): taxi cell kept, p uniform, d uniform over the others
-      int32_t cur = 0;
-#pragma unroll
-      for (int i = 0; i < 4 * QPT; ++i) cur = i == b ? keep_s[i] : cur;
-      const uint32_t cell = fdiv((uint32_t)cur, P.div_pd);
-      uint32_t p, d;
-      if (REPLAY) {
-        p = (uint32_t)P.rp_new_p[env];
-        d = (uint32_t)P.rp_new_d[env];
-      } else {
-        p = bounded(rnd.y, (uint32_t)P.nlocs);
-        d = bounded(rnd.z, (uint32_t)P.nlocs - 1);
-        d += d >= p ? 1u : 0u;
-      }
-      fresh = (cell * (uint32_t)(P.nlocs + 1) + p) * (uint32_t)P.nlocs + d;
     }
     P.s[env] = (int32_t)fresh;
     P.obs[env] = HANSEN ? (int32_t)hobs[fresh] : (int32_t)fresh;
-  }
-}
-
-// ------------------------------------------------------------------------------------------
-// fused multi-step kernel: gpt_step_many() with n_steps > 1 (Philox mode, no statistics)
-// ------------------------------------------------------------------------------------------
-// T consecutive steps from an action stream [T, capacity] in ONE launch: the state (s, elapsed, ndrop) is read once,
-// lives in registers for the T steps and is written once; per step only the action byte is read and the outputs
-// (obs, reward, terminated, truncated) are written — 11 B per env-step + 18 B per env per launch instead of 29 B.
-// Results are bit-identical to T single-step launches: Philox counters are (global env id, first step + t).
-struct TaxiMultiParams {
-  TaxiParams p;
-  int32_t n_steps;
-  int64_t act_stride;   // bytes between consecutive steps' action rows (= capacity)
-  int64_t out_stride;   // rows between consecutive steps' outputs (0 = overwrite in place)
-};
-
-// rare branch, out of line: full reset (extended_taxi.py:344-352) or passenger respawn (:354-364) -> new state
-template <int DUMMY>
-__device__ __noinline__ uint32_t taxi_fix(const TaxiParams& P, const uint32_t* cdf, const uint16_t* valid, int64_t env, uint32_t t,
-                                          uint32_t cur, bool full) {
-  const uint64_t ctr = (((uint64_t)P.rng.step_hi << 32) | P.rng.step_lo) + t;
-  const uint64_t ge = (uint64_t)(P.env_offset + env);
-  const uint4 rnd = philox4x32_10(make_uint4((uint32_t)ge, (uint32_t)(ge >> 32), (uint32_t)ctr, (uint32_t)(ctr >> 32) & 0x00FFFFFFu), P.rng);
-  if (full) {
-    int lo = 0, hi = P.n_valid - 1;
-    while (lo < hi) {
-      const int mid = (lo + hi) >> 1;
-      if (rnd.x <= cdf[mid]) hi = mid; else lo = mid + 1;
-    }
-    return valid[lo];
-  }
-  const uint32_t cell = fdiv(cur, P.div_pd);
-  const uint32_t p = bounded(rnd.y, (uint32_t)P.nlocs);
-  uint32_t d = bounded(rnd.z, (uint32_t)P.nlocs - 1);
-  d += d >= p ? 1u : 0u;
-  return (cell * (uint32_t)(P.nlocs + 1) + p) * (uint32_t)P.nlocs + d;
-}
-
-#ifndef GPT_TAXI_MULTI_MINB
-#define GPT_TAXI_MULTI_MINB 8
-#endif
-template <bool HANSEN, int QPT, int THREADS>
-__global__ void __launch_bounds__(THREADS, GPT_TAXI_MULTI_MINB) taxi_table_multi_kernel(const __grid_constant__ TaxiMultiParams M) {
-  const TaxiParams& P = M.p;
-  extern __shared__ __align__(128) uint8_t smem[];
-  __shared__ uint64_t bar;
-  pdl_launch_dependents();
-  stage_tables_begin(smem, P.blob, P.blob_bytes, &bar);
-
-  constexpr int kEnvsPerWarp = kWarp * kQuad * QPT;
-  const uint32_t lane = threadIdx.x & 31u;
-  const int64_t wtile = (int64_t)blockIdx.x * (THREADS / 32) + (threadIdx.x >> 5);
-  const int64_t first = (int64_t)P.first_tile * kTileEnvs, last = first + (int64_t)P.n_tiles * kTileEnvs;
-  const int64_t base = first + wtile * kEnvsPerWarp + lane * kQuad;
-  if (base >= last) return;
-
-  pdl_wait();
-  int32_t sv[QPT][4], ev[QPT][4];
-  uint32_t ndv[QPT][4], a4[QPT];
-#pragma unroll
-  for (int j = 0; j < QPT; ++j) {
-    const int64_t q = base + j * kQuadStride;
-    const int4 s4 = ld_stream(reinterpret_cast<const int4*>(P.s + q));
-    const int4 e4 = ld_stream(reinterpret_cast<const int4*>(P.elapsed + q));
-    const uint32_t nd4 = ld_stream(reinterpret_cast<const uint32_t*>(P.ndrop + q));
-    a4[j] = ld_stream(reinterpret_cast<const uint32_t*>(P.actions + q));
-    sv[j][0] = s4.x; sv[j][1] = s4.y; sv[j][2] = s4.z; sv[j][3] = s4.w;
-    ev[j][0] = e4.x; ev[j][1] = e4.y; ev[j][2] = e4.z; ev[j][3] = e4.w;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) ndv[j][k] = (nd4 >> (8 * k)) & 0xFFu;
-  }
-  stage_tables_wait(&bar);
-  const uint16_t* trans = reinterpret_cast<const uint16_t*>(smem + P.trans_off);
-  const uint16_t* hobs = reinterpret_cast<const uint16_t*>(smem + P.hobs_off);
-  const uint32_t* cdf = reinterpret_cast<const uint32_t*>(smem + P.cdf_off);
-  const uint16_t* valid = reinterpret_cast<const uint16_t*>(smem + P.vs_off);
-
-#pragma unroll 1
-  for (int32_t t = 0; t < M.n_steps; ++t) {
-    // prefetch the next step's action bytes (the only per-step read) before this step's dependent table lookups
-    uint32_t a_next[QPT];
-    const bool more = t + 1 < M.n_steps;
-#pragma unroll
-    for (int j = 0; j < QPT; ++j)
-      a_next[j] = more ? ld_stream(reinterpret_cast<const uint32_t*>(P.actions + (int64_t)(t + 1) * M.act_stride + base + j * kQuadStride)) : 0u;
-    const int64_t orow = (int64_t)t * M.out_stride;
-#pragma unroll
-    for (int j = 0; j < QPT; ++j) {
-      const int64_t q = base + j * kQuadStride;
-      float rv[4];
-      int32_t ov[4];
-      uint32_t tw = 0, trw = 0, fixm = 0;   // fixm bit k: full reset, bit 4+k: passenger respawn
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const uint32_t a = min((a4[j] >> (8 * k)) & 0xFFu, (uint32_t)(kTransCols - 1));
-        const uint32_t ent = trans[(uint32_t)sv[j][k] * kTransCols + a];
-        const uint32_t goal = (ent >> 13) & 1u;
-        ndv[j][k] += goal;
-        sv[j][k] = (int32_t)(ent & kTransState);
-        ev[j][k] += 1;
-        rv[k] = goal ? P.r_goal : ((ent & kTransBad) ? P.r_bad : P.r_any);
-        const uint32_t term = ndv[j][k] == (uint32_t)P.n_dropoffs;
-        const uint32_t trunc = ev[j][k] > P.time_limit;
-        const uint32_t done = term | trunc;
-        fixm |= (done << k) | ((goal & ~done & 1u) << (4 + k));
-        tw |= term << (8 * k);
-        trw |= trunc << (8 * k);
-      }
-      if (fixm) {  // rare: one divergence point per quad
-#pragma unroll 1
-        for (uint32_t m = (fixm | (fixm >> 4)) & 0xFu; m; m &= m - 1) {
-          const int k = __ffs(m) - 1;
-          const bool full = (fixm >> k) & 1u;
-          uint32_t cur = 0;
-#pragma unroll
-          for (int i = 0; i < 4; ++i) cur = i == k ? (uint32_t)sv[j][i] : cur;
-          const uint32_t fresh = taxi_fix<0>(P, cdf, valid, q + k, (uint32_t)t, cur, full);
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            if (i == k) {
-              sv[j][i] = (int32_t)fresh;
-              ev[j][i] = full ? 0 : ev[j][i];
-              ndv[j][i] = full ? 0u : ndv[j][i];
-            }
-          }
-        }
-      }
-#pragma unroll
-      for (int k = 0; k < 4; ++k) ov[k] = HANSEN ? (int32_t)hobs[sv[j][k]] : sv[j][k];
-      st_stream(reinterpret_cast<int4*>(P.obs + orow + q), make_int4(ov[0], ov[1], ov[2], ov[3]));
-      st_stream(reinterpret_cast<float4*>(P.reward + orow + q), make_float4(rv[0], rv[1], rv[2], rv[3]));
-      st_stream(reinterpret_cast<uint32_t*>(P.terminated + orow + q), tw);
-      st_stream(reinterpret_cast<uint32_t*>(P.truncated + orow + q), trw);
-      a4[j] = a_next[j];
-    }
-  }
-#pragma unroll
-  for (int j = 0; j < QPT; ++j) {
-    const int64_t q = base + j * kQuadStride;
-    st_stream(reinterpret_cast<int4*>(P.s + q), make_int4(sv[j][0], sv[j][1], sv[j][2], sv[j][3]));
-    st_stream(reinterpret_cast<int4*>(P.elapsed + q), make_int4(ev[j][0], ev[j][1], ev[j][2], ev[j][3]));
-    st_stream(reinterpret_cast<uint32_t*>(P.ndrop + q),
-              (ndv[j][0] & 0xFFu) | ((ndv[j][1] & 0xFFu) << 8) | ((ndv[j][2] & 0xFFu) << 16) | ((ndv[j][3] & 0xFFu) << 24));
   }
 }
 
@@ -535,15 +547,19 @@ int taxi_create(gpt_env* env, const gpt_config* c) {
   }
   cdf.back() = 0xFFFFFFFFu;
   std::vector<uint8_t> blob;
-  env->taxi_use_table = ns <= (int64_t)kTransState + 1;
+  env->taxi_use_table = ns <= kTableMaxStates;
   if (env->taxi_use_table) {
     // tabulate the whole step relation with the same rule the arithmetic kernel applies per env
     const int nl = c->taxi_nlocs, cols = c->taxi_cols;
-    std::vector<uint16_t> trans((size_t)ns * kTransCols), hobs((size_t)ns);
+    std::vector<uint32_t> trans((size_t)ns * kTransCols);
+    std::vector<uint16_t> hobs((size_t)ns), trans16((size_t)ns * kT16Cols);
+    for (int64_t st = 0; st < ns; ++st) {   // observation per state: the id itself, or the Hansen re-encoding
+      const int d0 = (int)(st % nl), p0 = (int)((st / nl) % (nl + 1)), cell0 = (int)(st / nl / (nl + 1));
+      hobs[st] = c->taxi_hansen_obs ? (uint16_t)((((celltab[(size_t)cell0 * rep] & 15) * (nl + 1)) + p0) * nl + d0) : (uint16_t)st;
+    }
     for (int64_t st = 0; st < ns; ++st) {
       const int d0 = (int)(st % nl), p0 = (int)((st / nl) % (nl + 1)), cell0 = (int)(st / nl / (nl + 1));
-      hobs[st] = (uint16_t)((((celltab[(size_t)cell0 * rep] & 15) * (nl + 1)) + p0) * nl + d0);
-      for (int a = 0; a < kTransCols; ++a) {
+      for (int a = 0; a < kTransCols; ++a) {   // columns 5..7: no-op
         int cell = cell0, p = p0;
         uint16_t ent = celltab[(size_t)cell * rep];
         if (a < 4 && !((ent >> a) & 1)) {
@@ -559,23 +575,55 @@ int taxi_create(gpt_env* env, const gpt_config* c) {
         if (pickup) p = nl;
         const bool bad = act && !goal && !pickup;
         const int64_t s2 = ((int64_t)cell * (nl + 1) + p) * nl + d0;
-        trans[(size_t)st * kTransCols + a] = (uint16_t)(s2 | (goal ? kTransGoal : 0u) | (bad ? kTransBad : 0u));
+        trans[(size_t)st * kTransCols + a] = ((uint32_t)hobs[s2] << 16) | ((uint32_t)s2 << kRowShift) | (goal ? kTransGoal : 0u) | (bad ? kTransBad : 0u);
+        if (a < kT16Cols) trans16[(size_t)st * kT16Cols + a] = (uint16_t)(s2 | (goal ? kT16Goal : 0u) | (bad ? kT16Bad : 0u));
       }
     }
-    env->taxi_trans_off = blob_append(blob, trans);
+    // blob order: what the single-step kernel stages (compact table, observations, alias) first, the fused
+    // kernel's 32-bit table last
+    env->taxi_trans16_off = blob_append(blob, trans16);
     env->taxi_hobs_off = blob_append(blob, hobs);
+    // Walker alias table of the reset law (Philox mode): column j = {threshold, valid[j] | valid[alias_j] << 16}
+    std::vector<uint32_t> alias((size_t)c->taxi_n_valid * 2, 0u);
+    {
+      const int n = c->taxi_n_valid;
+      std::vector<double> q(n);
+      for (int j = 0; j < n; ++j) {
+        const double hi = j == n - 1 ? 4294967296.0 : (double)cdf[j] + 1.0, lo = j == 0 ? 0.0 : (double)cdf[j - 1] + 1.0;
+        q[j] = (hi > lo ? hi - lo : 0.0) / 4294967296.0 * n;
+      }
+      std::vector<int> small, large, al(n);
+      std::vector<double> pr(n, 1.0);
+      for (int j = 0; j < n; ++j) { al[j] = j; (q[j] < 1.0 ? small : large).push_back(j); }
+      while (!small.empty() && !large.empty()) {
+        const int sidx = small.back(), lidx = large.back();
+        small.pop_back();
+        pr[sidx] = q[sidx];
+        al[sidx] = lidx;
+        q[lidx] = (q[lidx] + q[sidx]) - 1.0;
+        if (q[lidx] < 1.0) { large.pop_back(); small.push_back(lidx); }
+      }
+      for (int j = 0; j < n; ++j) {
+        const double t = pr[j] * 4294967296.0;
+        alias[(size_t)j * 2] = t >= 4294967295.0 ? 0xFFFFFFFFu : (t <= 0 ? 0u : (uint32_t)t);
+        alias[(size_t)j * 2 + 1] = (uint32_t)valid[j] | ((uint32_t)valid[al[j]] << 16);
+      }
+    }
+    env->taxi_alias_off = blob_append(blob, alias);
+    env->taxi_single_bytes = align16((uint32_t)blob.size());
+    env->taxi_trans_off = blob_append(blob, trans);
   } else {
     blob_append(blob, celltab);
+    env->taxi_cdf_off = blob_append(blob, cdf);
+    env->taxi_vs_off = blob_append(blob, valid);
   }
-  env->taxi_cdf_off = blob_append(blob, cdf);
-  env->taxi_vs_off = blob_append(blob, valid);
   if (int rc = upload_blob(env, blob)) return rc;
 
   add_array(env, "s", GPT_ROLE_STATE, GPT_DT_I32, 1);
   add_array(env, "elapsed", GPT_ROLE_STATE, GPT_DT_I32, 1);
   add_array(env, "ndrop", GPT_ROLE_STATE, GPT_DT_U8, 1);
   if (c->track_stats) {
-    if (!env->taxi_use_table) return fail(GPT_E_ARG, "taxi: track_stats needs the table kernel (ns <= 8192)");
+    if (!env->taxi_use_table) return fail(GPT_E_ARG, "taxi: track_stats needs the table kernel (ns <= 2048)");
     add_array(env, "ep_return", GPT_ROLE_STATE, GPT_DT_F32, 1);
   }
   add_array(env, "obs", GPT_ROLE_OUTPUT, GPT_DT_I32, 1);
@@ -592,7 +640,7 @@ int taxi_create(gpt_env* env, const gpt_config* c) {
 }
 
 bool taxi_can_fuse(const gpt_env* env) {
-  return env->taxi_use_table && env->cfg.rng_mode == GPT_RNG_PHILOX && !env->cfg.track_stats;
+  return env->taxi_use_table && env->cfg.rng_mode == GPT_RNG_PHILOX;   // replay draws are per step
 }
 
 int taxi_launch(gpt_env* env, const LaunchArgs& a) {
@@ -660,40 +708,38 @@ int taxi_launch(gpt_env* env, const LaunchArgs& a) {
   P.hobs_off = env->taxi_hobs_off;
   P.div_pd = make_fastdiv((uint32_t)(c.taxi_nlocs + 1) * (uint32_t)c.taxi_nlocs);
   if (a.n_tiles <= 0) return GPT_OK;
-  const size_t smem = env->blob_bytes;
-  if (a.n_steps > 1) {  // fused multi-step launch (gpt_step_many); eligibility is checked by taxi_can_fuse()
-    TaxiMultiParams M;
+  void* args[] = {(void*)&P};
+  const void* kernel;
+  int threads, grid;
+  size_t smem = env->blob_bytes;
+  TaxiMultiParams M;
+  const bool hansen = c.taxi_hansen_obs != 0;
+  P.trans16_off = env->taxi_trans16_off;
+  P.alias_off = env->taxi_alias_off;
+  P.single_bytes = env->taxi_single_bytes;
+  if (env->taxi_use_table && a.n_steps > 1) {  // fused multi-step launch (gpt_step_many)
+    if (replay) return fail(GPT_E_ARG, "taxi: fused multi-step launches need Philox mode");
     M.p = P;
     M.n_steps = a.n_steps;
     M.act_stride = env->capacity;
     M.out_stride = a.out_stride_rows;
     using KM = void (*)(const TaxiMultiParams);
-    KM km = c.taxi_hansen_obs ? (KM)taxi_table_multi_kernel<true, 2, 128> : (KM)taxi_table_multi_kernel<false, 2, 128>;
-    const int64_t envs_per_cta = 128 * kQuad * 2;
-    const int grid = (int)(((int64_t)a.n_tiles * kTileEnvs + envs_per_cta - 1) / envs_per_cta);
-    if (smem > 40 * 1024) {
-      cudaError_t e = cudaFuncSetAttribute((const void*)km, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(taxi multi)");
-    }
-    void* margs[] = {(void*)&M};
-    cudaError_t e = launch_pdl((const void*)km, dim3(grid), dim3(128), smem, a.stream, margs);
-    env->launches += 1;
-    if (e != cudaSuccess) return cuda_fail(e, "taxi multi-step kernel launch");
-    return GPT_OK;
-  }
-  using K = void (*)(const TaxiParams);
-  K k;
-  int threads, grid;
-  const bool hansen = c.taxi_hansen_obs != 0;
-  if (env->taxi_use_table) {
+    KM km = c.track_stats ? (KM)taxi_table_multi_kernel<true, 2, 128> : (KM)taxi_table_multi_kernel<false, 2, 128>;
+    threads = 128;
+    const int64_t envs_per_cta = (int64_t)threads * kQuad * 2;
+    grid = (int)(((int64_t)a.n_tiles * kTileEnvs + envs_per_cta - 1) / envs_per_cta);
+    kernel = (const void*)km;
+    args[0] = (void*)&M;
+  } else if (env->taxi_use_table) {
+    using K = void (*)(const TaxiParams);
     // launch shape: GPT_TAXI_SHAPE = "<quads per thread>x<threads>" (tuning knob; default 2x128)
-    const int shape = env->taxi_shape;
 #define GPT_TAXI_PICK2(S, Q, T)                                                                                  \
   (hansen ? (replay ? (K)taxi_table_kernel<true, true, S, Q, T> : (K)taxi_table_kernel<true, false, S, Q, T>)      \
           : (replay ? (K)taxi_table_kernel<false, true, S, Q, T> : (K)taxi_table_kernel<false, false, S, Q, T>))
 #define GPT_TAXI_PICK(Q, T) (c.track_stats ? GPT_TAXI_PICK2(true, Q, T) : GPT_TAXI_PICK2(false, Q, T))
+    K k;
     int qpt;
-    switch (shape) {  // measured on B200 at 2^22 envs: 2x128 18.9 us, 4x128 19.3 us, 1x256 20.3 us per step
+    switch (env->taxi_shape) {  // measured on B200 at 2^22 envs: 2x128 18.9 us, 4x128 19.3 us, 1x256 20.3 us per step
       case 4128: k = GPT_TAXI_PICK(4, 128); qpt = 4; threads = 128; break;
       default: k = GPT_TAXI_PICK(2, 128); qpt = 2; threads = 128; break;
     }
@@ -701,18 +747,20 @@ int taxi_launch(gpt_env* env, const LaunchArgs& a) {
 #undef GPT_TAXI_PICK2
     const int64_t envs_per_cta = (int64_t)threads * kQuad * qpt;
     grid = (int)(((int64_t)a.n_tiles * kTileEnvs + envs_per_cta - 1) / envs_per_cta);
+    kernel = (const void*)k;
+    smem = env->taxi_single_bytes;
   } else {
+    using K = void (*)(const TaxiParams);
     threads = 256;
     grid = (a.n_tiles + 7) / 8;
-    k = hansen ? (replay ? (K)taxi_arith_kernel<true, true> : (K)taxi_arith_kernel<true, false>)
-               : (replay ? (K)taxi_arith_kernel<false, true> : (K)taxi_arith_kernel<false, false>);
+    kernel = (const void*)(hansen ? (replay ? (K)taxi_arith_kernel<true, true> : (K)taxi_arith_kernel<true, false>)
+                                  : (replay ? (K)taxi_arith_kernel<false, true> : (K)taxi_arith_kernel<false, false>));
   }
   if (smem > 40 * 1024) {  // static + dynamic shared memory above 48 KB needs the opt-in
-    cudaError_t e = cudaFuncSetAttribute((const void*)k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(taxi)");
   }
-  void* args[] = {(void*)&P};
-  cudaError_t e = launch_pdl((const void*)k, dim3(grid), dim3(threads), smem, a.stream, args);
+  cudaError_t e = launch_pdl(kernel, dim3(grid), dim3(threads), smem, a.stream, args);
   env->launches += 1;
   if (e != cudaSuccess) return cuda_fail(e, "taxi step kernel launch");
   if (table_reset) {

@@ -277,6 +277,10 @@ class DeviceVecEnv:
     def rng_counter(self, value: int):
         N.check(N.lib.gpt_set_counter(self._h, int(value)))
 
+    def set_fused_steps(self, enable: bool):
+        """``step_many`` as one fused multi-step launch where the family supports it (Taxi) — on by default."""
+        N.check(N.lib.gpt_set_fused_steps(self._h, int(bool(enable))))
+
     @property
     def launch_count(self) -> int:
         return int(N.lib.gpt_launch_count(self._h))

@@ -197,6 +197,10 @@ GPT_API int gpt_step_dlpack(gpt_env* env, void* managed_actions, void* stream);
 /* T consecutive steps from an action stream [T, capacity]; outputs of step t go to the bound
  * output arrays offset by t*out_stride_rows rows (0 = overwrite in place every step). */
 GPT_API int gpt_step_many(gpt_env* env, const void* actions, int32_t n_steps, int64_t out_stride_rows, void* stream);
+/* Taxi (table kernel, Philox mode) runs gpt_step_many as ONE fused launch: the state stays in registers for the
+ * n_steps steps, only actions are read and outputs written per step; results are bit-identical to n_steps
+ * single-step launches.  gpt_set_fused_steps(env, 0) forces one launch per step (A/B measurements). */
+GPT_API int gpt_set_fused_steps(gpt_env* env, int enable);
 /* end-to-end: H2D(actions) -> fused step -> D2H(obs, reward, terminated, truncated), chunked and
  * pipelined on internal streams; returns after the results are in the host buffers. */
 GPT_API int gpt_step_host(gpt_env* env, const gpt_host_io* io);
