@@ -32,9 +32,9 @@ WORKLOADS = {
                  desc="Taxi POMDP 5x5 (4 locations, time_limit 200), fused step+obs+autoreset, Philox RNG, uniform random actions"),
     "taxi_hansen": dict(alg_bytes=29, state_bytes=18, n_act=5, dtype="int32", cpu_family="taxi",
                         desc="Hansen-obs Taxi 5x5, fused step+obs+autoreset, Philox RNG"),
-    "rooms_hansen8": dict(alg_bytes=23, n_act=8, dtype="int32", cpu_family="rooms_hansen8",
+    "rooms_hansen8": dict(alg_bytes=23, state_bytes=12, n_act=8, dtype="int32", cpu_family="rooms_hansen8",
                           desc="FourRooms '4' discrete, hansen8 obs, 0.2 action-slip, fixed goal, Philox RNG"),
-    "rooms_grid5": dict(alg_bytes=19 + 25, n_act=8, dtype="u8", cpu_family="rooms_grid5",
+    "rooms_grid5": dict(alg_bytes=19 + 25, state_bytes=12, n_act=8, dtype="u8", cpu_family="rooms_grid5",
                         desc="FourRooms '4', 5x5 egocentric window obs, 0.2 action-slip, fixed goal"),
     "crooms": dict(alg_bytes=46, n_act=0, dtype="f32", cpu_family="crooms",
                    desc="continuous ROOMS '4' (float32 fast mode, Gaussian action noise 0.2, wall rejection), vector_mdp obs, yx float32 actions"),
@@ -48,7 +48,7 @@ WORKLOADS = {
                 desc="car-flag (heaven/hell with priest), float32 forces; obs is the live float32 state row"),
     "msrooms": dict(alg_bytes=23, n_act=4, dtype="int32", cpu_family="msrooms",
                     desc="multistory FourRooms (3 floors, stairs), mdp obs, 1/3 action-slip, cardinal actions, fixed goal, Philox RNG"),
-    "rooms_grid9": dict(alg_bytes=19 + 81, n_act=8, dtype="u8", cpu_family="rooms_grid9",
+    "rooms_grid9": dict(alg_bytes=19 + 81, state_bytes=12, n_act=8, dtype="u8", cpu_family="rooms_grid9",
                         desc="FourRooms '4', 9x9 egocentric window obs, 0.2 action-slip, fixed goal"),
 }
 
@@ -337,7 +337,7 @@ def run_b200(args):
         steps_per_launch = args.steps / max(launches, 1)
         alg_bytes = wl["alg_bytes"]
         if steps_per_launch > 1.0:
-            alg_bytes = wl["alg_bytes"] - wl["state_bytes"] + wl["state_bytes"] / steps_per_launch
+            alg_bytes = wl["alg_bytes"] - wl.get("state_bytes", 0) + wl.get("state_bytes", 0) / steps_per_launch
         per_launch_s = ms_max * 1e-3 / max(launches, 1)
         achieved = alg_bytes * steps_per_launch * cap / per_launch_s / 1e9
         line = {

@@ -328,7 +328,8 @@ int gpt_step_many(gpt_env* env, const void* actions, int32_t n_steps, int64_t ou
         return fail(GPT_E_ARG, "gpt_step_many: bound output arrays are too small for n_steps*out_stride_rows");
   }
   static const bool no_fuse = getenv("GPT_NO_FUSED_STEPS") != nullptr;
-  const bool fuse = !no_fuse && !env->no_fused_steps && n_steps > 1 && env->cfg.family == GPT_FAMILY_TAXI && taxi_can_fuse(env);
+  const bool fuse = !no_fuse && !env->no_fused_steps && n_steps > 1 &&
+                    ((env->cfg.family == GPT_FAMILY_TAXI && taxi_can_fuse(env)) || (env->cfg.family == GPT_FAMILY_ROOMS && rooms_can_fuse(env)));
   if (fuse) {  // one launch for all n_steps: state stays in registers, only actions are read and outputs written per step
     LaunchArgs a;
     a.mode = kModeStep;

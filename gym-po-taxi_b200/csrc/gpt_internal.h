@@ -102,6 +102,7 @@ struct LaunchArgs {
   int64_t out_stride_rows = 0;
 };
 bool taxi_can_fuse(const gpt_env* env);
+bool rooms_can_fuse(const gpt_env* env);
 int taxi_launch(gpt_env* env, const LaunchArgs& a);
 int rooms_launch(gpt_env* env, const LaunchArgs& a);
 int crooms_launch(gpt_env* env, const LaunchArgs& a);

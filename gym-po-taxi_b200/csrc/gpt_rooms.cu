@@ -247,7 +247,7 @@ int rooms_create(gpt_env* env, const gpt_config* c) {
 }
 
 
-static void* pick_kernel(int obs, int grid_n, bool rgoal, bool replay, bool stats) {
+static void* pick_kernel(int obs, int grid_n, bool rgoal, bool replay, int stats) {
   switch (obs) {
     case GPT_OBS_ROOM: case GPT_OBS_ROOM_GOAL: case GPT_OBS_MDP: case GPT_OBS_MDP_GOAL: return rooms_pick_table(obs, rgoal, replay, stats);
     case GPT_OBS_VEC_MDP: case GPT_OBS_VEC_MDP_GOAL: case GPT_OBS_HANSEN: return rooms_pick_vec(obs, rgoal, replay, stats);
@@ -259,6 +259,8 @@ static void* pick_kernel(int obs, int grid_n, bool rgoal, bool replay, bool stat
   }
   return nullptr;
 }
+
+bool rooms_can_fuse(const gpt_env* env) { return env->cfg.rng_mode == GPT_RNG_PHILOX && !env->cfg.track_stats; }
 
 int rooms_launch(gpt_env* env, const LaunchArgs& a) {
   const gpt_config& c = env->cfg;
@@ -356,7 +358,12 @@ int rooms_launch(gpt_env* env, const LaunchArgs& a) {
   if (nblocks <= 0) return GPT_OK;
   size_t smem = env->blob_bytes;
   if (grid) smem = P.stage_off + (size_t)warps * kQuadStride * P.grid_n * P.grid_n;
-  void* k = pick_kernel(c.rooms_obs_kind, P.grid_n, rgoal, replay, c.track_stats != 0);
+  const bool multi = a.n_steps > 1;
+  if (multi && (replay || c.track_stats)) return fail(GPT_E_ARG, "rooms: fused multi-step launches need Philox mode without track_stats");
+  P.n_steps = a.n_steps;
+  P.act_stride = env->capacity;
+  P.out_stride = a.out_stride_rows;
+  void* k = pick_kernel(c.rooms_obs_kind, P.grid_n, rgoal, replay, multi ? 2 : (c.track_stats != 0 ? 1 : 0));
   if (!k) return fail(GPT_E_ARG, "rooms: no kernel for this obs kind");
   if (smem > 40 * 1024) {  // static + dynamic shared memory above 48 KB needs the opt-in
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

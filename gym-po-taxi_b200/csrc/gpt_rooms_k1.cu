@@ -3,11 +3,11 @@
 
 namespace gpt {
 
-void* rooms_pick_vec(int obs, bool rgoal, bool replay, bool stats) {
+void* rooms_pick_vec(int obs, bool rgoal, bool replay, int variant) {
   switch (obs) {
-    case GPT_OBS_VEC_MDP: return pick_rr<GPT_OBS_VEC_MDP, 0>(rgoal, replay, stats);
-    case GPT_OBS_VEC_MDP_GOAL: return pick_rr<GPT_OBS_VEC_MDP_GOAL, 0>(rgoal, replay, stats);
-    case GPT_OBS_HANSEN: return pick_rr<GPT_OBS_HANSEN, 0>(rgoal, replay, stats);
+    case GPT_OBS_VEC_MDP: return pick_rr<GPT_OBS_VEC_MDP, 0>(rgoal, replay, variant);
+    case GPT_OBS_VEC_MDP_GOAL: return pick_rr<GPT_OBS_VEC_MDP_GOAL, 0>(rgoal, replay, variant);
+    case GPT_OBS_HANSEN: return pick_rr<GPT_OBS_HANSEN, 0>(rgoal, replay, variant);
   }
   return nullptr;
 }

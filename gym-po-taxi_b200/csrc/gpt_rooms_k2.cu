@@ -3,8 +3,8 @@
 
 namespace gpt {
 
-void* rooms_pick_vhansen(int obs, bool rgoal, bool replay, bool stats) {
-  return obs == GPT_OBS_VEC_HANSEN ? pick_rr<GPT_OBS_VEC_HANSEN, 0>(rgoal, replay, stats) : pick_rr<GPT_OBS_VEC_HANSEN_GOAL, 0>(rgoal, replay, stats);
+void* rooms_pick_vhansen(int obs, bool rgoal, bool replay, int variant) {
+  return obs == GPT_OBS_VEC_HANSEN ? pick_rr<GPT_OBS_VEC_HANSEN, 0>(rgoal, replay, variant) : pick_rr<GPT_OBS_VEC_HANSEN_GOAL, 0>(rgoal, replay, variant);
 }
 
 }  // namespace gpt

@@ -3,8 +3,8 @@
 
 namespace gpt {
 
-void* rooms_pick_grid_small(int n, bool rgoal, bool replay, bool stats) {
-  return n == 3 ? pick_rr<GPT_OBS_GRID, 3>(rgoal, replay, stats) : pick_rr<GPT_OBS_GRID, 5>(rgoal, replay, stats);
+void* rooms_pick_grid_small(int n, bool rgoal, bool replay, int variant) {
+  return n == 3 ? pick_rr<GPT_OBS_GRID, 3>(rgoal, replay, variant) : pick_rr<GPT_OBS_GRID, 5>(rgoal, replay, variant);
 }
 
 }  // namespace gpt

@@ -3,8 +3,8 @@
 
 namespace gpt {
 
-void* rooms_pick_grid_large(int n, bool rgoal, bool replay, bool stats) {
-  return n == 7 ? pick_rr<GPT_OBS_GRID, 7>(rgoal, replay, stats) : pick_rr<GPT_OBS_GRID, 9>(rgoal, replay, stats);
+void* rooms_pick_grid_large(int n, bool rgoal, bool replay, int variant) {
+  return n == 7 ? pick_rr<GPT_OBS_GRID, 7>(rgoal, replay, variant) : pick_rr<GPT_OBS_GRID, 9>(rgoal, replay, variant);
 }
 
 }  // namespace gpt

@@ -3,6 +3,6 @@
 
 namespace gpt {
 
-void* rooms_pick_grid_any(bool rgoal, bool replay, bool stats) { return pick_rr<GPT_OBS_GRID, 0>(rgoal, replay, stats); }
+void* rooms_pick_grid_any(bool rgoal, bool replay, int variant) { return pick_rr<GPT_OBS_GRID, 0>(rgoal, replay, variant); }
 
 }  // namespace gpt

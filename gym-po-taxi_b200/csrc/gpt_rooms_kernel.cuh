@@ -47,6 +47,10 @@ struct RoomsParams {
   int32_t hansen_n, grid_n, goal_cell, goal_y, goal_x;
   FastDiv div_w;
   float r_step, r_wall, r_goal;
+  // fused multi-step launch (gpt_step_many, MULTI kernels): n_steps consecutive steps, the state stays in registers
+  int32_t n_steps;
+  int64_t act_stride;   // bytes between consecutive steps' action rows (= capacity)
+  int64_t out_stride;   // rows between consecutive steps' outputs (0 = overwrite in place)
   RngKey rng;
 };
 
@@ -252,21 +256,33 @@ template <int GRID_N> struct RoomsShape<GPT_OBS_GRID, GRID_N> {
 // Rare path, deliberately out of line (one copy per kernel instead of one per unrolled env):
 // _reset_some (rooms.py:191-196) — new goal first (random-goal envs), then new agent cell.
 template <bool RGOAL, bool REPLAY>
-__device__ __noinline__ uint32_t rooms_respawn(const RoomsParams& P, const uint16_t* valid, int64_t env, uint32_t gcell) {
+__device__ __noinline__ uint32_t rooms_respawn(const RoomsParams& P, const uint16_t* valid, int64_t env, uint32_t gcell, uint32_t t) {
   uint32_t cell;
   if (REPLAY) {
     if (RGOAL) gcell = (uint32_t)P.rp_reset_goal[env];
     cell = (uint32_t)P.rp_reset_agent[env];
   } else {
-    const uint4 r = env_random(P.rng, (uint64_t)(P.env_offset + env), 1u);
+    const uint64_t ctr = (((uint64_t)P.rng.step_hi << 32) | P.rng.step_lo) + t;   // step index inside a fused launch
+    const uint64_t ge = (uint64_t)(P.env_offset + env);
+    const uint4 r = philox4x32_10(make_uint4((uint32_t)ge, (uint32_t)(ge >> 32), (uint32_t)ctr,
+                                             ((uint32_t)(ctr >> 32) & 0x00FFFFFFu) ^ (1u << 24)), P.rng);
     if (RGOAL) gcell = valid[bounded(r.y, (uint32_t)P.n_valid)];
     cell = valid[bounded(r.x, (uint32_t)P.n_valid)];
   }
   return cell | (gcell << 16);   // values, not references: no local-memory round trip at the call site
 }
 
-template <int OBS, bool RGOAL, bool REPLAY, int GRID_N, bool STATS>
-__global__ void __launch_bounds__(RoomsShape<OBS, GRID_N>::kThreads, STATS ? 1 : RoomsShape<OBS, GRID_N>::kMinBlocks) rooms_step_kernel(const __grid_constant__ RoomsParams P) {
+#ifndef GPT_ROOMS_MINB_MULTI
+#define GPT_ROOMS_MINB_MULTI 6
+#endif
+// MULTI: gpt_step_many as ONE launch — pos / goal / elapsed are read once, live in registers for P.n_steps steps and
+// are written once; per step only the action byte is read and the outputs are written.  Bit-identical to n_steps
+// single-step launches (Philox counters = (global env / quad id, first step + t)).
+template <int OBS, bool RGOAL, bool REPLAY, int GRID_N, bool STATS, bool MULTI = false>
+__global__ void __launch_bounds__(RoomsShape<OBS, GRID_N>::kThreads,
+                                  STATS ? 1 : (MULTI ? (RoomsShape<OBS, GRID_N>::kMinBlocks > 1 ? GPT_ROOMS_MINB_MULTI : 1) : RoomsShape<OBS, GRID_N>::kMinBlocks))
+rooms_step_kernel(const __grid_constant__ RoomsParams P) {
+  static_assert(!MULTI || (!REPLAY && !STATS), "fused launches: Philox mode, no in-kernel statistics");
   constexpr int QPT = RoomsShape<OBS, GRID_N>::kQpt;
   constexpr int kEnvsPerWarp = kWarp * kQuad * QPT;
   // fixed goal + non-window obs: the observation is a pure function of the agent cell -> one table lookup
@@ -330,12 +346,36 @@ __global__ void __launch_bounds__(RoomsShape<OBS, GRID_N>::kThreads, STATS ? 1 :
   constexpr bool kObs8 = OBS == GPT_OBS_VEC_HANSEN || OBS == GPT_OBS_VEC_HANSEN_GOAL;
   const bool obs_two_words = kObs8 && P.hansen_n == 8;
 
+  // state of the thread's envs, kept in registers (across the steps of a fused launch)
+  uint32_t cellq[QPT][4], goalq[QPT][4];
+  int32_t evq[QPT][4];
+#pragma unroll
+  for (int j = 0; j < QPT; ++j) {
+    cellq[j][0] = pos4[j].x & 0xFFFFu; cellq[j][1] = pos4[j].x >> 16; cellq[j][2] = pos4[j].y & 0xFFFFu; cellq[j][3] = pos4[j].y >> 16;
+    goalq[j][0] = goal4[j].x & 0xFFFFu; goalq[j][1] = goal4[j].x >> 16; goalq[j][2] = goal4[j].y & 0xFFFFu; goalq[j][3] = goal4[j].y >> 16;
+    evq[j][0] = e4[j].x; evq[j][1] = e4[j].y; evq[j][2] = e4[j].z; evq[j][3] = e4[j].w;
+  }
+  const int32_t n_steps = MULTI ? P.n_steps : 1;
+  const size_t obs_row = OBS == GPT_OBS_GRID ? (size_t)(gn * gn)
+                         : (OBS == GPT_OBS_VEC_MDP ? 2 : ((OBS == GPT_OBS_VEC_HANSEN || OBS == GPT_OBS_VEC_HANSEN_GOAL) ? (size_t)P.hansen_n : 4));
+#pragma unroll 1
+  for (int32_t t = 0; t < n_steps; ++t) {
+  uint32_t a_next[QPT];
+  const bool more = MULTI && t + 1 < n_steps;
+#pragma unroll
+  for (int j = 0; j < QPT; ++j) {   // prefetch the next step's action bytes (the only per-step read)
+    a_next[j] = 0u;
+    if (more) a_next[j] = ld_stream(reinterpret_cast<const uint32_t*>(P.actions + (int64_t)(t + 1) * P.act_stride + base + j * kQuadStride));
+  }
+  const int64_t orow = MULTI ? (int64_t)t * P.out_stride : 0;
+  const uint64_t ctr = (((uint64_t)P.rng.step_hi << 32) | P.rng.step_lo) + (uint32_t)t;
+  const uint32_t ctr_lo = (uint32_t)ctr, ctr_hi = (uint32_t)(ctr >> 32) & 0x00FFFFFFu;
 #pragma unroll
   for (int j = 0; j < QPT; ++j) {
     const int64_t q = base + j * kQuadStride;
-    uint32_t cellv[4] = {pos4[j].x & 0xFFFFu, pos4[j].x >> 16, pos4[j].y & 0xFFFFu, pos4[j].y >> 16};
-    uint32_t goalv[4] = {goal4[j].x & 0xFFFFu, goal4[j].x >> 16, goal4[j].y & 0xFFFFu, goal4[j].y >> 16};
-    int32_t ev[4] = {e4[j].x, e4[j].y, e4[j].z, e4[j].w};
+    uint32_t (&cellv)[4] = cellq[j];
+    uint32_t (&goalv)[4] = goalq[j];
+    int32_t (&ev)[4] = evq[j];
     float rv[4];
     uint32_t tw = 0, trw = 0;
     uint32_t o32[4] = {0, 0, 0, 0};  // scalar obs, or packed bytes of the vector obs (lo)
@@ -344,7 +384,7 @@ __global__ void __launch_bounds__(RoomsShape<OBS, GRID_N>::kThreads, STATS ? 1 :
     uint4 slip = make_uint4(0, 0, 0, 0);
     if (!REPLAY) {  // one Philox block feeds the slip draws of the 4 envs of this quad
       const uint64_t gq = (uint64_t)(P.env_offset + q) >> 2;
-      slip = philox4x32_10(make_uint4((uint32_t)gq, (uint32_t)(gq >> 32), P.rng.step_lo, P.rng.step_hi), P.rng);
+      slip = philox4x32_10(make_uint4((uint32_t)gq, (uint32_t)(gq >> 32), ctr_lo, ctr_hi), P.rng);
     }
     const uint32_t slipv[4] = {slip.x, slip.y, slip.z, slip.w};
 
@@ -410,7 +450,7 @@ __global__ void __launch_bounds__(RoomsShape<OBS, GRID_N>::kThreads, STATS ? 1 :
         uint32_t g = 0;
 #pragma unroll
         for (int i = 0; i < 4; ++i) g = i == k ? goalv[i] : g;
-        const uint32_t fresh = rooms_respawn<RGOAL, REPLAY>(P, T.valid, q + k, g);
+        const uint32_t fresh = rooms_respawn<RGOAL, REPLAY>(P, T.valid, q + k, g, (uint32_t)t);
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           if (i == k) {
@@ -443,14 +483,22 @@ __global__ void __launch_bounds__(RoomsShape<OBS, GRID_N>::kThreads, STATS ? 1 :
       window_quad<GRID_N>(T, OC, cellv, goalv, stage + (uint32_t)(lane * kQuad) * (uint32_t)(GRID_N * GRID_N));
 
     // ---- stores ------------------------------------------------------------------------------
+    st_stream(reinterpret_cast<float4*>(P.reward + orow + q), make_float4(rv[0], rv[1], rv[2], rv[3]));
+    st_stream(reinterpret_cast<uint32_t*>(P.terminated + orow + q), tw);
+    st_stream(reinterpret_cast<uint32_t*>(P.truncated + orow + q), trw);
+    store_obs<OBS>((uint8_t*)P.obs + (size_t)orow * obs_row, q, wbase + j * kQuadStride, P.hansen_n, gn, lane, stage, o32, o32b);
+    if constexpr (STATS) st_stream(reinterpret_cast<float4*>(P.ep_return + q), ret4[j]);
+    a4[j] = a_next[j];
+  }
+  }  // steps of a fused launch
+#pragma unroll
+  for (int j = 0; j < QPT; ++j) {
+    const int64_t q = base + j * kQuadStride;
+    const uint32_t (&cellv)[4] = cellq[j];
+    const uint32_t (&goalv)[4] = goalq[j];
     st_stream(reinterpret_cast<uint2*>(P.pos + q), make_uint2(cellv[0] | (cellv[1] << 16), cellv[2] | (cellv[3] << 16)));
     if (RGOAL) st_stream(reinterpret_cast<uint2*>(P.goal + q), make_uint2(goalv[0] | (goalv[1] << 16), goalv[2] | (goalv[3] << 16)));
-    st_stream(reinterpret_cast<int4*>(P.elapsed + q), make_int4(ev[0], ev[1], ev[2], ev[3]));
-    st_stream(reinterpret_cast<float4*>(P.reward + q), make_float4(rv[0], rv[1], rv[2], rv[3]));
-    st_stream(reinterpret_cast<uint32_t*>(P.terminated + q), tw);
-    st_stream(reinterpret_cast<uint32_t*>(P.truncated + q), trw);
-    store_obs<OBS>(P.obs, q, wbase + j * kQuadStride, P.hansen_n, gn, lane, stage, o32, o32b);
-    if constexpr (STATS) st_stream(reinterpret_cast<float4*>(P.ep_return + q), ret4[j]);
+    st_stream(reinterpret_cast<int4*>(P.elapsed + q), make_int4(evq[j][0], evq[j][1], evq[j][2], evq[j][3]));
   }
   if constexpr (STATS) acc.flush(P.stats);
 }
@@ -462,17 +510,22 @@ static void* pick_rr2(bool rgoal, bool replay) {
               : (replay ? (K)rooms_step_kernel<OBS, false, true, GRID_N, STATS> : (K)rooms_step_kernel<OBS, false, false, GRID_N, STATS>);
   return (void*)k;
 }
+// variant: 0 = plain single step, 1 = single step with in-kernel statistics, 2 = fused multi-step (Philox mode)
 template <int OBS, int GRID_N>
-static void* pick_rr(bool rgoal, bool replay, bool stats) {
-  return stats ? pick_rr2<OBS, GRID_N, true>(rgoal, replay) : pick_rr2<OBS, GRID_N, false>(rgoal, replay);
+static void* pick_rr(bool rgoal, bool replay, int variant) {
+  using K = void (*)(const RoomsParams);
+  if (variant == 2)
+    return replay ? nullptr
+                  : (void*)(rgoal ? (K)rooms_step_kernel<OBS, true, false, GRID_N, false, true> : (K)rooms_step_kernel<OBS, false, false, GRID_N, false, true>);
+  return variant == 1 ? pick_rr2<OBS, GRID_N, true>(rgoal, replay) : pick_rr2<OBS, GRID_N, false>(rgoal, replay);
 }
 
 // kernel instantiations live in gpt_rooms_k*.cu so that they compile in parallel
-void* rooms_pick_table(int obs, bool rgoal, bool replay, bool stats);   // ROOM, ROOM_GOAL, MDP, MDP_GOAL
-void* rooms_pick_vec(int obs, bool rgoal, bool replay, bool stats);     // VEC_MDP, VEC_MDP_GOAL, HANSEN
-void* rooms_pick_vhansen(int obs, bool rgoal, bool replay, bool stats); // VEC_HANSEN, VEC_HANSEN_GOAL
-void* rooms_pick_grid_small(int n, bool rgoal, bool replay, bool stats);  // 3, 5
-void* rooms_pick_grid_large(int n, bool rgoal, bool replay, bool stats);  // 7, 9
-void* rooms_pick_grid_any(bool rgoal, bool replay, bool stats);           // run-time n <= 15
+void* rooms_pick_table(int obs, bool rgoal, bool replay, int variant);   // ROOM, ROOM_GOAL, MDP, MDP_GOAL
+void* rooms_pick_vec(int obs, bool rgoal, bool replay, int variant);     // VEC_MDP, VEC_MDP_GOAL, HANSEN
+void* rooms_pick_vhansen(int obs, bool rgoal, bool replay, int variant); // VEC_HANSEN, VEC_HANSEN_GOAL
+void* rooms_pick_grid_small(int n, bool rgoal, bool replay, int variant);  // 3, 5
+void* rooms_pick_grid_large(int n, bool rgoal, bool replay, int variant);  // 7, 9
+void* rooms_pick_grid_any(bool rgoal, bool replay, int variant);           // run-time n <= 15
 
 }  // namespace gpt

@@ -232,3 +232,32 @@ def test_episode_statistics_match_returned_rewards(obs_type, goal_xy):
     with pytest.raises(ValueError):
         from gym_po.envs import CRoomsEnv
         CRoomsEnv(64, device=DEV, track_stats=True)
+
+
+@pytest.mark.parametrize("obs_type,goal_xy,layout", [("hansen8", (0, 0), "4"), ("grid", None, "8"), ("vector_goal_hansen8", None, "10b"),
+                                                     ("grid", (0, 0), "32"), ("mdp_goal", None, "2"), ("vector_mdp", (0, 0), "16")])
+def test_fused_multi_step_launch_equals_single_steps(obs_type, goal_xy, layout):
+    """gpt_step_many on ROOMS runs T steps in ONE launch (pos / goal / elapsed in registers); every step's outputs and the
+    final state must be bit-identical to T single-step launches (Philox counters = (global env / quad id, step))."""
+    from gym_po.envs import RoomsEnv
+    b, T = 3000, 29
+    kw = dict(layout=layout, obs_type=obs_type, obs_n=5, goal_xy=goal_xy, time_limit=11, step_reward=-0.1, wall_reward=-0.5)
+    a = RoomsEnv(b, device=DEV, seed=9, **kw)
+    c = RoomsEnv(b, device=DEV, seed=9, **kw)
+    a.reset(seed=9); c.reset(seed=9)
+    gen = torch.Generator(device=DEV).manual_seed(4)
+    for rep in range(3):
+        acts = torch.randint(0, 8, (T, a.capacity), dtype=torch.int8, device=DEV, generator=gen)
+        out = {n: torch.zeros((T,) + tuple(a._arrays[n].shape), dtype=a._arrays[n].dtype, device=DEV)
+               for n in ("obs", "reward", "terminated", "truncated")}
+        l0 = a.launch_count
+        a.step_many(acts, out)
+        assert a.launch_count == l0 + 1      # one fused launch
+        for t in range(T):
+            o = c.step(acts[t])
+            for n, x in zip(("obs", "reward", "terminated", "truncated"), o[:4]):
+                assert torch.equal(out[n][t][:b].reshape(x.shape).view(x.dtype), x), (n, rep, t)
+        sa, sc = a.get_state(), c.get_state()
+        for k in sa:
+            assert torch.equal(sa[k], sc[k]), k
+        assert a.rng_counter == c.rng_counter
