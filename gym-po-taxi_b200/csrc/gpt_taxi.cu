@@ -264,7 +264,7 @@ __device__ __noinline__ uint32_t taxi_fix(const TaxiParams& P, const uint2* alia
 }
 
 #ifndef GPT_TAXI_MINB_MULTI
-#define GPT_TAXI_MINB_MULTI 6   // measured on B200 (2^22 envs, 8 steps per launch): 5 -> 380 G, 6 -> 405 G, 7 -> 389 G, 8 -> 304 G
+#define GPT_TAXI_MINB_MULTI 6   // 72 registers; measured on B200 (2^22 envs, 8 steps per launch): 4 -> 412 G, 6 -> 417 G, 7 -> 418 G
 #endif
 template <bool STATS, int QPT, int THREADS>
 __global__ void __launch_bounds__(THREADS, STATS ? 1 : GPT_TAXI_MINB_MULTI) taxi_table_multi_kernel(const __grid_constant__ TaxiMultiParams M) {
@@ -322,6 +322,7 @@ __global__ void __launch_bounds__(THREADS, STATS ? 1 : GPT_TAXI_MINB_MULTI) taxi
       if (more) a_next[j] = ld_stream(reinterpret_cast<const uint32_t*>(P.actions + (int64_t)(t + 1) * M.act_stride + base + j * kQuadStride));
     }
     const int64_t orow = (int64_t)t * M.out_stride;
+    uint32_t fix_done = 0, fix_goal = 0;   // bit 8k + j: env k of quad j finished its episode / delivered a passenger
 #pragma unroll
     for (int j = 0; j < QPT; ++j) {
       const int64_t q = base + j * kQuadStride;
@@ -352,33 +353,37 @@ __global__ void __launch_bounds__(THREADS, STATS ? 1 : GPT_TAXI_MINB_MULTI) taxi
           ret[j][k] = (term | trunc) ? 0.f : ret[j][k];
         }
       }
-      if (tw | trw | gw) {  // rare: full reset of finished envs, passenger respawn after a delivery (:283-286)
-        const uint32_t donew = tw | trw;
-#pragma unroll 1
-        for (uint32_t m = donew | gw; m; m &= m - 1) {
-          const int k = (__ffs(m) - 1) >> 3;
-          const bool full = (donew >> (8 * k)) & 1u;
-          uint32_t cur = 0;
-#pragma unroll
-          for (int i = 0; i < 4; ++i) cur = i == k ? off[j][i] : cur;
-          const uint32_t fresh = taxi_fix<REPLAY>(P, alias, q + k, (uint32_t)t, cur >> kRowShift, full);
-          const int32_t fobs = (int32_t)hobs[fresh];
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            if (i == k) {
-              off[j][i] = fresh << kRowShift;
-              ov[i] = fobs;
-              ev[j][i] = full ? 0 : ev[j][i];
-              ndv[j][i] = full ? 0u : ndv[j][i];
-            }
-          }
-        }
-      }
+      // the vector stores go out now; the rare envs are fixed below, ONCE per step for all of the thread's envs (their
+      // observation is patched with a scalar store: same thread, same address, program order)
+      fix_done |= ((tw | trw) & 0x01010101u) << j;
+      fix_goal |= (gw & 0x01010101u) << j;
       st_stream(reinterpret_cast<int4*>(P.obs + orow + q), make_int4(ov[0], ov[1], ov[2], ov[3]));
       st_stream(reinterpret_cast<float4*>(P.reward + orow + q), make_float4(rv[0], rv[1], rv[2], rv[3]));
       st_stream(reinterpret_cast<uint32_t*>(P.terminated + orow + q), tw);
       st_stream(reinterpret_cast<uint32_t*>(P.truncated + orow + q), trw);
       a4[j] = a_next[j];
+    }
+    if (fix_done | fix_goal) {  // rare: full reset of finished envs, passenger respawn after a delivery (:283-286)
+#pragma unroll 1
+      for (uint32_t m = fix_done | fix_goal; m; m &= m - 1) {
+        const int bit = __ffs(m) - 1, k = bit >> 3, j = bit & 7;   // bit 8k + j <-> quad j, env k
+        const bool full = (fix_done >> bit) & 1u;
+        const int idx = j * 4 + k;
+        uint32_t cur = 0;
+#pragma unroll
+        for (int i = 0; i < 4 * QPT; ++i) cur = i == idx ? off[i >> 2][i & 3] : cur;
+        const int64_t env = base + j * kQuadStride + k;
+        const uint32_t fresh = taxi_fix<REPLAY>(P, alias, env, (uint32_t)t, cur >> kRowShift, full);
+        P.obs[orow + env] = (int32_t)hobs[fresh];
+#pragma unroll
+        for (int i = 0; i < 4 * QPT; ++i) {
+          if (i == idx) {
+            off[i >> 2][i & 3] = fresh << kRowShift;
+            ev[i >> 2][i & 3] = full ? 0 : ev[i >> 2][i & 3];
+            ndv[i >> 2][i & 3] = full ? 0u : ndv[i >> 2][i & 3];
+          }
+        }
+      }
     }
   }
 #pragma unroll
@@ -725,8 +730,11 @@ int taxi_launch(gpt_env* env, const LaunchArgs& a) {
     M.out_stride = a.out_stride_rows;
     using KM = void (*)(const TaxiMultiParams);
     KM km = c.track_stats ? (KM)taxi_table_multi_kernel<true, 2, 128> : (KM)taxi_table_multi_kernel<false, 2, 128>;
+    int qpt = 2;
+    if (env->taxi_shape == 4128 && !c.track_stats) { km = (KM)taxi_table_multi_kernel<false, 4, 128>; qpt = 4; }
+    if (env->taxi_shape == 1128 && !c.track_stats) { km = (KM)taxi_table_multi_kernel<false, 1, 128>; qpt = 1; }
     threads = 128;
-    const int64_t envs_per_cta = (int64_t)threads * kQuad * 2;
+    const int64_t envs_per_cta = (int64_t)threads * kQuad * qpt;
     grid = (int)(((int64_t)a.n_tiles * kTileEnvs + envs_per_cta - 1) / envs_per_cta);
     kernel = (const void*)km;
     args[0] = (void*)&M;
