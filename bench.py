@@ -46,7 +46,7 @@ WORKLOADS = {
                     desc="point-mass Tag (float64 parity mode), yx float32 actions"),
     "car": dict(alg_bytes=44, n_act=0, act_cols=1, dtype="f32", cpu_family="car",
                 desc="car-flag (heaven/hell with priest), float32 forces; obs is the live float32 state row"),
-    "msrooms": dict(alg_bytes=23, n_act=4, dtype="int32", cpu_family="msrooms",
+    "msrooms": dict(alg_bytes=23, state_bytes=12, n_act=4, dtype="int32", cpu_family="msrooms",
                     desc="multistory FourRooms (3 floors, stairs), mdp obs, 1/3 action-slip, cardinal actions, fixed goal, Philox RNG"),
     "rooms_grid9": dict(alg_bytes=19 + 81, state_bytes=12, n_act=8, dtype="u8", cpu_family="rooms_grid9",
                         desc="FourRooms '4', 9x9 egocentric window obs, 0.2 action-slip, fixed goal"),

@@ -329,7 +329,8 @@ int gpt_step_many(gpt_env* env, const void* actions, int32_t n_steps, int64_t ou
   }
   static const bool no_fuse = getenv("GPT_NO_FUSED_STEPS") != nullptr;
   const bool fuse = !no_fuse && !env->no_fused_steps && n_steps > 1 &&
-                    ((env->cfg.family == GPT_FAMILY_TAXI && taxi_can_fuse(env)) || (env->cfg.family == GPT_FAMILY_ROOMS && rooms_can_fuse(env)));
+                    ((env->cfg.family == GPT_FAMILY_TAXI && taxi_can_fuse(env)) || (env->cfg.family == GPT_FAMILY_ROOMS && rooms_can_fuse(env)) ||
+                     (env->cfg.family == GPT_FAMILY_MSROOMS && msrooms_can_fuse(env)));
   if (fuse) {  // one launch for all n_steps: state stays in registers, only actions are read and outputs written per step
     LaunchArgs a;
     a.mode = kModeStep;

@@ -103,6 +103,7 @@ struct LaunchArgs {
 };
 bool taxi_can_fuse(const gpt_env* env);
 bool rooms_can_fuse(const gpt_env* env);
+bool msrooms_can_fuse(const gpt_env* env);
 int taxi_launch(gpt_env* env, const LaunchArgs& a);
 int rooms_launch(gpt_env* env, const LaunchArgs& a);
 int crooms_launch(gpt_env* env, const LaunchArgs& a);

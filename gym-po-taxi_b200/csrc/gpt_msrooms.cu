@@ -98,6 +98,9 @@ struct MsParams {
   int32_t n_actions, n_agent, n_goal, time_limit, goal_cell;
   MsObsCfg oc;
   float r_step, r_wall, r_goal;
+  int32_t n_steps;      // fused multi-step launch (MULTI kernels): steps per launch
+  int64_t act_stride;   // bytes between consecutive steps' action rows (= capacity)
+  int64_t out_stride;   // rows between consecutive steps' outputs (0 = overwrite in place)
   RngKey rng;
 };
 
@@ -105,13 +108,16 @@ constexpr int kMsThreads = 128, kMsQpt = 2;
 
 // _reset_some (msrooms.py:385-390): goal first (random-goal envs), then agent.  Rare, out of line.
 template <bool RGOAL, bool REPLAY>
-__device__ __noinline__ uint32_t ms_respawn(const MsParams& P, const uint16_t* avalid, const uint16_t* gvalid, int64_t env, uint32_t gcell) {
+__device__ __noinline__ uint32_t ms_respawn(const MsParams& P, const uint16_t* avalid, const uint16_t* gvalid, int64_t env, uint32_t gcell, uint32_t t) {
   uint32_t cell;
   if (REPLAY) {
     if (RGOAL) gcell = (uint32_t)P.rp_reset_goal[env];
     cell = (uint32_t)P.rp_reset_agent[env];
   } else {
-    const uint4 r = env_random(P.rng, (uint64_t)(P.env_offset + env), 1u);
+    const uint64_t ctr = (((uint64_t)P.rng.step_hi << 32) | P.rng.step_lo) + t;   // step index inside a fused launch
+    const uint64_t ge = (uint64_t)(P.env_offset + env);
+    const uint4 r = philox4x32_10(make_uint4((uint32_t)ge, (uint32_t)(ge >> 32), (uint32_t)ctr,
+                                             ((uint32_t)(ctr >> 32) & 0x00FFFFFFu) ^ (1u << 24)), P.rng);
     if (RGOAL) gcell = gvalid[bounded(r.y, (uint32_t)P.n_goal)];
     cell = avalid[bounded(r.x, (uint32_t)P.n_agent)];
   }
@@ -133,8 +139,10 @@ __device__ __forceinline__ uint32_t quad_obs_word(const uint64_t (&e)[4], int w)
 // OB = observation bytes per env (4: int32 scalar or 4 Hansen bytes, 3: z,y,x, 6: z,y,x,gz,gy,gx, 8: 8 Hansen bytes)
 // RGOAL = random goal (observation computed from the per-cell tables), otherwise tabulated per cell;
 // MERGED = fixed goal and a 16-bit observation riding in the move-table entry.
-template <int OB, bool RGOAL, bool MERGED, bool REPLAY>
-__global__ void __launch_bounds__(kMsThreads, 8) msrooms_step_kernel(const __grid_constant__ MsParams P) {
+// MULTI: gpt_step_many as ONE launch (state in registers for P.n_steps steps), bit-identical to single-step launches.
+template <int OB, bool RGOAL, bool MERGED, bool REPLAY, bool MULTI = false>
+__global__ void __launch_bounds__(kMsThreads, MULTI ? 6 : 8) msrooms_step_kernel(const __grid_constant__ MsParams P) {
+  static_assert(!MULTI || !REPLAY, "fused launches need Philox mode");
   constexpr int kEnvsPerWarp = kWarp * kQuad * kMsQpt;
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ uint64_t bar;
@@ -179,12 +187,33 @@ __global__ void __launch_bounds__(kMsThreads, 8) msrooms_step_kernel(const __gri
   T.vh = reinterpret_cast<const uint32_t*>(smem + P.vh_off);
   const uint32_t col_shift = 32u - P.log2n;
 
+  uint32_t cellq[kMsQpt][4], goalq[kMsQpt][4];   // state in registers (across the steps of a fused launch)
+  int32_t evq[kMsQpt][4];
+#pragma unroll
+  for (int j = 0; j < kMsQpt; ++j) {
+    cellq[j][0] = pos4[j].x & 0xFFFFu; cellq[j][1] = pos4[j].x >> 16; cellq[j][2] = pos4[j].y & 0xFFFFu; cellq[j][3] = pos4[j].y >> 16;
+    goalq[j][0] = goal4[j].x & 0xFFFFu; goalq[j][1] = goal4[j].x >> 16; goalq[j][2] = goal4[j].y & 0xFFFFu; goalq[j][3] = goal4[j].y >> 16;
+    evq[j][0] = e4[j].x; evq[j][1] = e4[j].y; evq[j][2] = e4[j].z; evq[j][3] = e4[j].w;
+  }
+  const int32_t n_steps = MULTI ? P.n_steps : 1;
+#pragma unroll 1
+  for (int32_t t = 0; t < n_steps; ++t) {
+  uint32_t a_next[kMsQpt];
+  const bool more = MULTI && t + 1 < n_steps;
+#pragma unroll
+  for (int j = 0; j < kMsQpt; ++j) {   // prefetch the next step's action bytes (the only per-step read)
+    a_next[j] = 0u;
+    if (more) a_next[j] = ld_stream(reinterpret_cast<const uint32_t*>(P.actions + (int64_t)(t + 1) * P.act_stride + base + j * kQuadStride));
+  }
+  const int64_t orow = MULTI ? (int64_t)t * P.out_stride : 0;
+  const uint64_t ctr = (((uint64_t)P.rng.step_hi << 32) | P.rng.step_lo) + (uint32_t)t;
+  const uint32_t ctr_lo = (uint32_t)ctr, ctr_hi = (uint32_t)(ctr >> 32) & 0x00FFFFFFu;
 #pragma unroll
   for (int j = 0; j < kMsQpt; ++j) {
     const int64_t q = base + j * kQuadStride;
-    uint32_t cellv[4] = {pos4[j].x & 0xFFFFu, pos4[j].x >> 16, pos4[j].y & 0xFFFFu, pos4[j].y >> 16};
-    uint32_t goalv[4] = {goal4[j].x & 0xFFFFu, goal4[j].x >> 16, goal4[j].y & 0xFFFFu, goal4[j].y >> 16};
-    int32_t ev[4] = {e4[j].x, e4[j].y, e4[j].z, e4[j].w};
+    uint32_t (&cellv)[4] = cellq[j];
+    uint32_t (&goalv)[4] = goalq[j];
+    int32_t (&ev)[4] = evq[j];
     float rv[4];
     uint32_t tw = 0, trw = 0, again = 0;
     uint32_t lo[4] = {0, 0, 0, 0}, hi[4] = {0, 0, 0, 0};
@@ -192,7 +221,7 @@ __global__ void __launch_bounds__(kMsThreads, 8) msrooms_step_kernel(const __gri
     uint4 slip = make_uint4(0, 0, 0, 0);
     if (!REPLAY) {  // one Philox block feeds the slip draws of the 4 envs of this quad
       const uint64_t gq = (uint64_t)(P.env_offset + q) >> 2;
-      slip = philox4x32_10(make_uint4((uint32_t)gq, (uint32_t)(gq >> 32), P.rng.step_lo, P.rng.step_hi), P.rng);
+      slip = philox4x32_10(make_uint4((uint32_t)gq, (uint32_t)(gq >> 32), ctr_lo, ctr_hi), P.rng);
     }
     const uint32_t slipv[4] = {slip.x, slip.y, slip.z, slip.w};
 
@@ -240,7 +269,7 @@ __global__ void __launch_bounds__(kMsThreads, 8) msrooms_step_kernel(const __gri
         uint32_t g = 0;
 #pragma unroll
         for (int i = 0; i < 4; ++i) g = i == k ? goalv[i] : g;
-        const uint32_t fresh = ms_respawn<RGOAL, REPLAY>(P, avalid, gvalid, q + k, g);
+        const uint32_t fresh = ms_respawn<RGOAL, REPLAY>(P, avalid, gvalid, q + k, g, (uint32_t)t);
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           if (i == k) {
@@ -271,13 +300,10 @@ __global__ void __launch_bounds__(kMsThreads, 8) msrooms_step_kernel(const __gri
       ob[k] = (uint64_t)lo[k] | ((uint64_t)hi[k] << 32);
     }
 
-    st_stream(reinterpret_cast<uint2*>(P.pos + q), make_uint2(cellv[0] | (cellv[1] << 16), cellv[2] | (cellv[3] << 16)));
-    if (RGOAL) st_stream(reinterpret_cast<uint2*>(P.goal + q), make_uint2(goalv[0] | (goalv[1] << 16), goalv[2] | (goalv[3] << 16)));
-    st_stream(reinterpret_cast<int4*>(P.elapsed + q), make_int4(ev[0], ev[1], ev[2], ev[3]));
-    st_stream(reinterpret_cast<float4*>(P.reward + q), make_float4(rv[0], rv[1], rv[2], rv[3]));
-    st_stream(reinterpret_cast<uint32_t*>(P.terminated + q), tw);
-    st_stream(reinterpret_cast<uint32_t*>(P.truncated + q), trw);
-    uint8_t* o = P.obs + q * OB;   // the quad's 4*OB observation bytes are contiguous
+    st_stream(reinterpret_cast<float4*>(P.reward + orow + q), make_float4(rv[0], rv[1], rv[2], rv[3]));
+    st_stream(reinterpret_cast<uint32_t*>(P.terminated + orow + q), tw);
+    st_stream(reinterpret_cast<uint32_t*>(P.truncated + orow + q), trw);
+    uint8_t* o = P.obs + (orow + q) * OB;   // the quad's 4*OB observation bytes are contiguous
     if constexpr (OB == 4) {
       st_stream(reinterpret_cast<int4*>(o), make_int4((int)lo[0], (int)lo[1], (int)lo[2], (int)lo[3]));
     } else if constexpr (OB == 8) {
@@ -291,6 +317,17 @@ __global__ void __launch_bounds__(kMsThreads, 8) msrooms_step_kernel(const __gri
 #pragma unroll
       for (int w = 0; w < 3; ++w) st_stream(reinterpret_cast<uint32_t*>(o) + w, quad_obs_word<3>(ob, w));
     }
+    a4[j] = a_next[j];
+  }
+  }  // steps of a fused launch
+#pragma unroll
+  for (int j = 0; j < kMsQpt; ++j) {
+    const int64_t q = base + j * kQuadStride;
+    const uint32_t (&cellv)[4] = cellq[j];
+    const uint32_t (&goalv)[4] = goalq[j];
+    st_stream(reinterpret_cast<uint2*>(P.pos + q), make_uint2(cellv[0] | (cellv[1] << 16), cellv[2] | (cellv[3] << 16)));
+    if (RGOAL) st_stream(reinterpret_cast<uint2*>(P.goal + q), make_uint2(goalv[0] | (goalv[1] << 16), goalv[2] | (goalv[3] << 16)));
+    st_stream(reinterpret_cast<int4*>(P.elapsed + q), make_int4(evq[j][0], evq[j][1], evq[j][2], evq[j][3]));
   }
 }
 
@@ -453,14 +490,22 @@ int msrooms_create(gpt_env* env, const gpt_config* c) {
 }
 
 template <int OB>
-static void* ms_pick(bool rgoal, bool merged, bool replay) {
+static void* ms_pick(bool rgoal, bool merged, bool replay, bool multi) {
   using K = void (*)(const MsParams);
   K k;
+  if (multi) {  // Philox mode only
+    if (rgoal) k = (K)msrooms_step_kernel<OB, true, false, false, true>;
+    else if (merged && OB == 4) k = (K)msrooms_step_kernel<4, false, true, false, true>;
+    else k = (K)msrooms_step_kernel<OB, false, false, false, true>;
+    return (void*)k;
+  }
   if (rgoal) k = replay ? (K)msrooms_step_kernel<OB, true, false, true> : (K)msrooms_step_kernel<OB, true, false, false>;
   else if (merged && OB == 4) k = replay ? (K)msrooms_step_kernel<4, false, true, true> : (K)msrooms_step_kernel<4, false, true, false>;
   else k = replay ? (K)msrooms_step_kernel<OB, false, false, true> : (K)msrooms_step_kernel<OB, false, false, false>;
   return (void*)k;
 }
+
+bool msrooms_can_fuse(const gpt_env* env) { return env->cfg.rng_mode == GPT_RNG_PHILOX; }
 
 int msrooms_launch(gpt_env* env, const LaunchArgs& a) {
   const gpt_config& c = env->cfg;
@@ -519,12 +564,17 @@ int msrooms_launch(gpt_env* env, const LaunchArgs& a) {
   const int64_t envs_per_cta = (int64_t)kMsThreads * kQuad * kMsQpt;
   const int nblocks = (int)(((int64_t)a.n_tiles * kTileEnvs + envs_per_cta - 1) / envs_per_cta);
   if (nblocks <= 0) return GPT_OK;
+  const bool multi = a.n_steps > 1;
+  if (multi && replay) return fail(GPT_E_ARG, "msrooms: fused multi-step launches need Philox mode");
+  P.n_steps = a.n_steps;
+  P.act_stride = env->capacity;
+  P.out_stride = a.out_stride_rows;
   void* k = nullptr;
   switch (L.obs_bytes) {
-    case 3: k = ms_pick<3>(rgoal, false, replay); break;
-    case 4: k = ms_pick<4>(rgoal, L.merged, replay); break;
-    case 6: k = ms_pick<6>(rgoal, false, replay); break;
-    case 8: k = ms_pick<8>(rgoal, false, replay); break;
+    case 3: k = ms_pick<3>(rgoal, false, replay, multi); break;
+    case 4: k = ms_pick<4>(rgoal, L.merged, replay, multi); break;
+    case 6: k = ms_pick<6>(rgoal, false, replay, multi); break;
+    case 8: k = ms_pick<8>(rgoal, false, replay, multi); break;
   }
   if (!k) return fail(GPT_E_ARG, "msrooms: no kernel for this observation layout");
   const size_t smem = env->blob_bytes;

@@ -192,3 +192,31 @@ def test_constructor_errors_like_the_reference():
         MultistoryFourRoomsEnv(8, agent_xyz=(1, 1, 0), device=DEV)
     with pytest.raises(NotImplementedError):
         MultistoryFourRoomsEnv(8, obs_type="grid", device=DEV)
+
+
+@pytest.mark.parametrize("obs_type,goal_xyz,floors", [("mdp", (9, 7, -1), 3), ("hansen8", None, 2), ("vector_mdp_goal", None, 4),
+                                                      ("vector_goal_hansen8", (9, 7, -1), 2), ("vector_mdp", (9, 7, -1), 1)])
+def test_fused_multi_step_launch_equals_single_steps(obs_type, goal_xyz, floors):
+    """gpt_step_many runs T steps in ONE launch; outputs of every step and the final state must be bit-identical to T
+    single-step launches."""
+    from gym_po.envs import MultistoryFourRoomsEnv
+    b, T = 3000, 31
+    kw = dict(grid_z=floors, obs_type=obs_type, goal_xyz=goal_xyz, time_limit=19, step_reward=-0.1, wall_reward=-0.5)
+    a = MultistoryFourRoomsEnv(b, device=DEV, seed=9, **kw)
+    c = MultistoryFourRoomsEnv(b, device=DEV, seed=9, **kw)
+    a.reset(seed=9); c.reset(seed=9)
+    gen = torch.Generator(device=DEV).manual_seed(4)
+    for rep in range(3):
+        acts = torch.randint(0, 4, (T, a.capacity), dtype=torch.int8, device=DEV, generator=gen)
+        out = {n: torch.zeros((T,) + tuple(a._arrays[n].shape), dtype=a._arrays[n].dtype, device=DEV)
+               for n in ("obs", "reward", "terminated", "truncated")}
+        l0 = a.launch_count
+        a.step_many(acts, out)
+        assert a.launch_count == l0 + 1
+        for t in range(T):
+            o = c.step(acts[t])
+            for n, x in zip(("obs", "reward", "terminated", "truncated"), o[:4]):
+                assert torch.equal(out[n][t][:b].reshape(x.shape).view(x.dtype), x), (n, rep, t)
+        sa, sc = a.get_state(), c.get_state()
+        for k in sa:
+            assert torch.equal(sa[k], sc[k]), k
