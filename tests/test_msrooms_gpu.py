@@ -220,3 +220,27 @@ def test_fused_multi_step_launch_equals_single_steps(obs_type, goal_xyz, floors)
         sa, sc = a.get_state(), c.get_state()
         for k in sa:
             assert torch.equal(sa[k], sc[k]), k
+
+
+def test_custom_floor_map_lockstep():
+    """A caller-supplied floor map (the kwarg the reference takes): open hall with pillars, 3 floors, random goal."""
+    from gym_po.envs import MultistoryFourRoomsEnv
+    fm = np.zeros((13, 15), dtype=np.int64)
+    fm[1:12, 1:14] = 1
+    fm[3:10:3, 3:12:4] = 0                      # pillars
+    fm[6, 1:6] = 0                              # a partial wall
+    b = 2000
+    kw = dict(grid_z=3, floor_map=fm, obs_type="vector_goal_hansen8", action_type="ordinal", goal_xyz=None, time_limit=120)
+    orc = oracle.MSRoomsOracle(b, draws=oracle.GeneratorDraws(seed=8), **kw)
+    env = MultistoryFourRoomsEnv(b, device=DEV, rng_mode="replay", **kw)
+    o, _ = orc.reset()
+    env.set_replay(**orc.draws)
+    np.testing.assert_array_equal(env.reset()[0].cpu().numpy(), o)
+    rng = np.random.default_rng(3)
+    for t in range(200):
+        a = rng.integers(8, size=b)
+        o = orc.step(a)
+        env.set_replay(**orc.draws)
+        _cmp(env.step(torch.as_tensor(a, dtype=torch.int8, device=DEV))[:4], o[:4], t)
+    np.testing.assert_array_equal(env.agent_zyx.cpu().numpy(), orc.agent)
+    assert len(np.unique(orc.agent[:, 0])) >= 2          # the stairs were used

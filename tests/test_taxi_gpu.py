@@ -349,3 +349,30 @@ def test_fused_multi_step_launch_equals_single_steps(kw):
         o = c.step(acts[t])
     for n, x in zip(("obs", "reward"), o[:2]):
         assert torch.equal(a._arrays[n][:b], x)
+
+
+@pytest.mark.parametrize("b", [1, 513, 4096])
+def test_fused_launch_ragged_sizes_and_stats(b):
+    """Fused launches at ragged batch sizes, with in-kernel statistics: equal to single steps, padding rows excluded."""
+    from gym_po.envs import TaxiVecEnv
+    T = 23
+    a = TaxiVecEnv(b, time_limit=7, device=DEV, seed=3, track_stats=True)
+    c = TaxiVecEnv(b, time_limit=7, device=DEV, seed=3, track_stats=True)
+    a.reset(seed=3); c.reset(seed=3)
+    gen = torch.Generator(device=DEV).manual_seed(4)
+    acts = torch.randint(0, 5, (T, a.capacity), dtype=torch.int8, device=DEV, generator=gen)
+    out = {n: torch.zeros((T,) + tuple(a._arrays[n].shape), dtype=a._arrays[n].dtype, device=DEV)
+           for n in ("obs", "reward", "terminated", "truncated")}
+    a.step_many(acts, out)
+    for t in range(T):
+        o = c.step(acts[t])
+        for n, x in zip(("obs", "reward", "terminated", "truncated"), o[:4]):
+            assert torch.equal(out[n][t][:b].view(x.dtype), x), (n, t)
+    sa, sc = a.stats_tensor().cpu().numpy(), c.stats_tensor().cpu().numpy()
+    assert sa[0] == sc[0] > 0 and sa[2] == sc[2] and sa[4] == sc[4] == b * T
+    np.testing.assert_allclose(sa[[1, 3]], sc[[1, 3]], rtol=1e-6)
+    # the switch: one launch per step on request
+    a.set_fused_steps(False)
+    l0 = a.launch_count
+    a.step_many(acts[:5])
+    assert a.launch_count == l0 + 5
