@@ -101,7 +101,8 @@ def test_tag_move_target_matches_reference_vectors():
 
 
 @pytest.mark.skipif(not reference_available(), reason="/root/reference not present (GPU box)")
-@pytest.mark.parametrize("name", ["taxi", "taxi_multi", "rooms_hansen8", "rooms32_grid9_rgoal", "crooms_vel_rg"])
+@pytest.mark.parametrize("name", ["taxi", "taxi_multi", "rooms_hansen8", "rooms32_grid9_rgoal", "crooms_vel_rg",
+                                  "msrooms_hansen8_3floors", "msrooms_vghansen_rg"])
 def test_oracle_lockstep_with_live_reference(name):
     from oracle.draws import make_generator
     from oracle.ref_loader import load_reference
