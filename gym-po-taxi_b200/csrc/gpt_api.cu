@@ -4,6 +4,8 @@
 #include <cstring>
 #include <new>
 
+#include <nvtx3/nvToolsExt.h>
+
 #include "gpt_internal.h"
 
 // Minimal DLPack (v0.x ABI) definitions — only what gpt_bind_dlpack / gpt_step_dlpack read.
@@ -35,6 +37,22 @@ typedef struct GptDLManagedTensor {
 enum { kDLCUDA = 2, kDLCUDAManaged = 13, kDLInt = 0, kDLUInt = 1, kDLFloat = 2, kDLBool = 6 };
 
 namespace gpt {
+
+// Optional NVTX ranges around the entry points (GPT_NVTX=1): shows the host-side cost of a step next to the kernels
+// in an Nsight Systems timeline.  Header-only NVTX3: a no-op unless a profiler is attached.
+struct NvtxRange {
+  static bool enabled() {
+    static const bool on = getenv("GPT_NVTX") != nullptr;
+    return on;
+  }
+  explicit NvtxRange(const char* name) : active(enabled()) {
+    if (active) nvtxRangePushA(name);
+  }
+  ~NvtxRange() {
+    if (active) nvtxRangePop();
+  }
+  bool active;
+};
 
 static thread_local std::string g_error;
 void set_error(const std::string& msg) { g_error = msg; }
@@ -283,6 +301,7 @@ int gpt_bind_dlpack(gpt_env* env, int index, void* managed) {
 
 int gpt_reset(gpt_env* env, int has_seed, uint64_t seed, void* stream) {
   if (!env) return fail(GPT_E_ARG, "gpt_reset: NULL env");
+  NvtxRange range("gpt_reset");
   if (has_seed) {
     env->cfg.seed = seed;
     env->counter = 0;
@@ -298,6 +317,7 @@ int gpt_reset(gpt_env* env, int has_seed, uint64_t seed, void* stream) {
 
 int gpt_step(gpt_env* env, const void* actions, void* stream) {
   if (!env) return fail(GPT_E_ARG, "gpt_step: NULL env");
+  NvtxRange range("gpt_step");
   LaunchArgs a;
   a.mode = kModeStep;
   a.actions = actions;
@@ -319,6 +339,7 @@ int gpt_step_dlpack(gpt_env* env, void* managed_actions, void* stream) {
 
 int gpt_step_many(gpt_env* env, const void* actions, int32_t n_steps, int64_t out_stride_rows, void* stream) {
   if (!env) return fail(GPT_E_ARG, "gpt_step_many: NULL env");
+  NvtxRange range("gpt_step_many");
   if (n_steps < 0 || out_stride_rows < 0) return fail(GPT_E_ARG, "gpt_step_many: negative argument");
   if (out_stride_rows != 0 && out_stride_rows < env->capacity) return fail(GPT_E_ARG, "gpt_step_many: out_stride_rows < capacity");
   const size_t arow = (size_t)env->action_cols * elem_size(env->action_dtype);
@@ -372,6 +393,7 @@ int gpt_set_fused_steps(gpt_env* env, int enable) {
 int gpt_step_host(gpt_env* env, const gpt_host_io* io) {
   if (!env || !io || !io->actions || !io->obs || !io->reward || !io->terminated || !io->truncated)
     return fail(GPT_E_ARG, "gpt_step_host: NULL argument");
+  NvtxRange range("gpt_step_host");
   cudaError_t e = cudaSetDevice(env->cfg.device);
   if (e != cudaSuccess) return cuda_fail(e, "cudaSetDevice");
   if (int rc = host_path_init(env)) return rc;
