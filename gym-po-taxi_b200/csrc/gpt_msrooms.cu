@@ -140,8 +140,14 @@ __device__ __forceinline__ uint32_t quad_obs_word(const uint64_t (&e)[4], int w)
 // RGOAL = random goal (observation computed from the per-cell tables), otherwise tabulated per cell;
 // MERGED = fixed goal and a 16-bit observation riding in the move-table entry.
 // MULTI: gpt_step_many as ONE launch (state in registers for P.n_steps steps), bit-identical to single-step launches.
+#ifndef GPT_MS_MINB_MULTI
+#define GPT_MS_MINB_MULTI 6
+#endif
+#ifndef GPT_MS_MINB_SINGLE
+#define GPT_MS_MINB_SINGLE 8
+#endif
 template <int OB, bool RGOAL, bool MERGED, bool REPLAY, bool MULTI = false>
-__global__ void __launch_bounds__(kMsThreads, MULTI ? 6 : 8) msrooms_step_kernel(const __grid_constant__ MsParams P) {
+__global__ void __launch_bounds__(kMsThreads, MULTI ? GPT_MS_MINB_MULTI : GPT_MS_MINB_SINGLE) msrooms_step_kernel(const __grid_constant__ MsParams P) {
   static_assert(!MULTI || !REPLAY, "fused launches need Philox mode");
   constexpr int kEnvsPerWarp = kWarp * kQuad * kMsQpt;
   extern __shared__ __align__(128) uint8_t smem[];

@@ -272,8 +272,10 @@ __device__ __noinline__ uint32_t rooms_respawn(const RoomsParams& P, const uint1
   return cell | (gcell << 16);   // values, not references: no local-memory round trip at the call site
 }
 
+// resident CTAs per SM of the fused kernels; measured on B200 (2^22 envs, 8 steps per launch): hansen8 6 -> 331 G,
+// 7 -> 346 G, 8 -> 340 G env-steps/s; window 5x5 6 -> 178 G, 7 -> 174 G, 8 -> 169 G
 #ifndef GPT_ROOMS_MINB_MULTI
-#define GPT_ROOMS_MINB_MULTI 6
+#define GPT_ROOMS_MINB_MULTI (OBS == GPT_OBS_GRID ? 6 : 7)
 #endif
 // MULTI: gpt_step_many as ONE launch — pos / goal / elapsed are read once, live in registers for P.n_steps steps and
 // are written once; per step only the action byte is read and the outputs are written.  Bit-identical to n_steps
