@@ -25,6 +25,10 @@ _NUMPY_DTYPES = {
 }
 
 
+# raw cudaStream_t of torch's current stream without building a Stream object (about 1 us cheaper per step)
+_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+
+
 class _CudaBuffer:
     """Zero-copy view of a device pointer the library owns (``__cuda_array_interface__``)."""
 
@@ -50,6 +54,7 @@ class DeviceVecEnv:
         if dev.index is None:
             dev = torch.device("cuda", torch.cuda.current_device())
         self.device = dev
+        self._dev_index = dev.index
         self.rng_mode = rng_mode
         if seed is None:  # the reference seeds its generator from OS entropy
             seed = int(np.random.SeedSequence().generate_state(1, np.uint64)[0])
@@ -85,6 +90,7 @@ class DeviceVecEnv:
             self._arrays[name] = t
         ashape = (self.capacity,) if self._action_cols == 1 else (self.capacity, self._action_cols)
         self._action_pad = torch.zeros(ashape, dtype=self._action_dtype, device=dev)
+        self._action_shape_cap = torch.Size(ashape)
         b = self.num_envs
         self._obs = self._shape_obs(self._arrays["obs"][:b])
         self._reward = self._arrays["reward"][:b]
@@ -109,7 +115,9 @@ class DeviceVecEnv:
 
     # ------------------------------------------------------------------ helpers
     def _stream(self):
-        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+        if _raw_stream is not None:
+            return _raw_stream(self._dev_index)
+        return torch.cuda.current_stream(self.device).cuda_stream
 
     def _on_device(self):
         return torch.cuda.device(self.device)
@@ -147,10 +155,19 @@ class DeviceVecEnv:
         ``(obs, reward, terminated, truncated, {})`` as views of the env's output tensors, which are
         overwritten by the next ``step`` — ``clone()`` to keep them.
         """
-        a = self._device_actions(actions)
-        with self._on_device():
-            N.check(N.lib.gpt_step(self._h, C.c_void_p(a.data_ptr()), self._stream()))
-        return self._results()
+        a = actions
+        # fast path: a contiguous device tensor of the action dtype with `capacity` rows goes straight to the library
+        if not (type(a) is torch.Tensor and a.dtype is self._action_dtype and a.shape == self._action_shape_cap
+                and a.device == self.device and a.is_contiguous()):
+            a = self._device_actions(actions)
+        if torch.cuda.current_device() == self._dev_index:
+            rc = N.lib.gpt_step(self._h, a.data_ptr(), self._stream())
+        else:
+            with self._on_device():
+                rc = N.lib.gpt_step(self._h, a.data_ptr(), self._stream())
+        if rc:
+            N.check(rc)
+        return self._obs, self._reward, self._terminated, self._truncated, {}
 
     def step_dlpack(self, actions):
         """Like :meth:`step` for any ``__dlpack__`` producer; the C library validates device, dtype,
