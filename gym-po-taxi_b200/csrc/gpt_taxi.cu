@@ -266,7 +266,11 @@ __device__ __noinline__ uint32_t taxi_fix(const TaxiParams& P, const uint2* alia
 #ifndef GPT_TAXI_MINB_MULTI
 #define GPT_TAXI_MINB_MULTI 6   // 72 registers; measured on B200 (2^22 envs, 8 steps per launch): 4 -> 412 G, 6 -> 417 G, 7 -> 418 G
 #endif
-template <bool STATS, int QPT, int THREADS>
+// ONE: num_passengers == 1 (the default).  A delivery then always terminates the episode, so `terminated` is the
+// delivered bit of the table entry, there is no passenger respawn and the dropoff counter is 0 at every step
+// boundary: the kernel neither loads nor tracks it and stores 0 (a counter injected with set_state is ignored here;
+// the single-step kernel keeps the reference's arithmetic).
+template <bool STATS, int QPT, int THREADS, bool ONE>
 __global__ void __launch_bounds__(THREADS, STATS ? 1 : GPT_TAXI_MINB_MULTI) taxi_table_multi_kernel(const __grid_constant__ TaxiMultiParams M) {
   constexpr bool REPLAY = false;   // replayed draws are per step: replay mode uses the single-step kernel
   const TaxiParams& P = M.p;
@@ -297,7 +301,7 @@ __global__ void __launch_bounds__(THREADS, STATS ? 1 : GPT_TAXI_MINB_MULTI) taxi
     const int64_t q = base + j * kQuadStride;
     const int4 s4 = ld_stream(reinterpret_cast<const int4*>(P.s + q));
     const int4 e4 = ld_stream(reinterpret_cast<const int4*>(P.elapsed + q));
-    const uint32_t nd4 = ld_stream(reinterpret_cast<const uint32_t*>(P.ndrop + q));
+    const uint32_t nd4 = ONE ? 0u : ld_stream(reinterpret_cast<const uint32_t*>(P.ndrop + q));
     a4[j] = ld_stream(reinterpret_cast<const uint32_t*>(P.actions + q));
     off[j][0] = (uint32_t)s4.x << kRowShift; off[j][1] = (uint32_t)s4.y << kRowShift;
     off[j][2] = (uint32_t)s4.z << kRowShift; off[j][3] = (uint32_t)s4.w << kRowShift;
@@ -334,16 +338,16 @@ __global__ void __launch_bounds__(THREADS, STATS ? 1 : GPT_TAXI_MINB_MULTI) taxi
         const uint32_t aoff = (k == 0 ? (a4[j] << 2) : (a4[j] >> (8 * k - 2))) & 0x1Cu;   // 4 * (action & 7)
         const uint32_t ent = *reinterpret_cast<const uint32_t*>(trans + off[j][k] + aoff);
         const uint32_t goal = ent & kTransGoal;
-        ndv[j][k] += goal;
+        if constexpr (!ONE) ndv[j][k] += goal;
         off[j][k] = ent & kTransRow;
         ov[k] = (int32_t)(ent >> 16);
         ev[j][k] += 1;
         rv[k] = goal ? P.r_goal : ((ent & kTransBad) ? P.r_bad : P.r_any);
-        const uint32_t term = ndv[j][k] == (uint32_t)P.n_dropoffs;      // (:276-279)
+        const uint32_t term = ONE ? goal : (uint32_t)(ndv[j][k] == (uint32_t)P.n_dropoffs);      // (:276-279)
         const uint32_t trunc = ev[j][k] > P.time_limit;
         tw |= term << (8 * k);
         trw |= trunc << (8 * k);
-        gw |= goal << (8 * k);
+        if constexpr (!ONE) gw |= goal << (8 * k);
         if constexpr (STATS) {
           ret[j][k] += rv[k];
           if (q + k < P.num_envs) {
@@ -380,7 +384,7 @@ __global__ void __launch_bounds__(THREADS, STATS ? 1 : GPT_TAXI_MINB_MULTI) taxi
           if (i == idx) {
             off[i >> 2][i & 3] = fresh << kRowShift;
             ev[i >> 2][i & 3] = full ? 0 : ev[i >> 2][i & 3];
-            ndv[i >> 2][i & 3] = full ? 0u : ndv[i >> 2][i & 3];
+            if constexpr (!ONE) ndv[i >> 2][i & 3] = full ? 0u : ndv[i >> 2][i & 3];
           }
         }
       }
@@ -393,7 +397,7 @@ __global__ void __launch_bounds__(THREADS, STATS ? 1 : GPT_TAXI_MINB_MULTI) taxi
                                                           (int)(off[j][2] >> kRowShift), (int)(off[j][3] >> kRowShift)));
     st_stream(reinterpret_cast<int4*>(P.elapsed + q), make_int4(ev[j][0], ev[j][1], ev[j][2], ev[j][3]));
     st_stream(reinterpret_cast<uint32_t*>(P.ndrop + q),
-              (ndv[j][0] & 0xFFu) | ((ndv[j][1] & 0xFFu) << 8) | ((ndv[j][2] & 0xFFu) << 16) | ((ndv[j][3] & 0xFFu) << 24));
+              ONE ? 0u : ((ndv[j][0] & 0xFFu) | ((ndv[j][1] & 0xFFu) << 8) | ((ndv[j][2] & 0xFFu) << 16) | ((ndv[j][3] & 0xFFu) << 24)));
     if constexpr (STATS) st_stream(reinterpret_cast<float4*>(P.ep_return + q), make_float4(ret[j][0], ret[j][1], ret[j][2], ret[j][3]));
   }
   if constexpr (STATS) acc.flush(P.stats);
@@ -729,10 +733,10 @@ int taxi_launch(gpt_env* env, const LaunchArgs& a) {
     M.act_stride = env->capacity;
     M.out_stride = a.out_stride_rows;
     using KM = void (*)(const TaxiMultiParams);
-    KM km = c.track_stats ? (KM)taxi_table_multi_kernel<true, 2, 128> : (KM)taxi_table_multi_kernel<false, 2, 128>;
-    int qpt = 2;
-    if (env->taxi_shape == 4128 && !c.track_stats) { km = (KM)taxi_table_multi_kernel<false, 4, 128>; qpt = 4; }
-    if (env->taxi_shape == 1128 && !c.track_stats) { km = (KM)taxi_table_multi_kernel<false, 1, 128>; qpt = 1; }
+    const bool one = c.taxi_n_dropoffs == 1;
+    KM km = c.track_stats ? (one ? (KM)taxi_table_multi_kernel<true, 2, 128, true> : (KM)taxi_table_multi_kernel<true, 2, 128, false>)
+                          : (one ? (KM)taxi_table_multi_kernel<false, 2, 128, true> : (KM)taxi_table_multi_kernel<false, 2, 128, false>);
+    const int qpt = 2;
     threads = 128;
     const int64_t envs_per_cta = (int64_t)threads * kQuad * qpt;
     grid = (int)(((int64_t)a.n_tiles * kTileEnvs + envs_per_cta - 1) / envs_per_cta);
