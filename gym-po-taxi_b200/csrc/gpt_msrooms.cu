@@ -108,7 +108,7 @@ constexpr int kMsThreads = 128, kMsQpt = 2;
 
 // _reset_some (msrooms.py:385-390): goal first (random-goal envs), then agent.  Rare, out of line.
 template <bool RGOAL, bool REPLAY>
-__device__ __noinline__ uint32_t ms_respawn(const MsParams& P, const uint16_t* avalid, const uint16_t* gvalid, int64_t env, uint32_t gcell, uint32_t t) {
+__device__ __forceinline__ uint32_t ms_respawn_inline(const MsParams& P, const uint16_t* avalid, const uint16_t* gvalid, int64_t env, uint32_t gcell, uint32_t t) {
   uint32_t cell;
   if (REPLAY) {
     if (RGOAL) gcell = (uint32_t)P.rp_reset_goal[env];
@@ -122,6 +122,11 @@ __device__ __noinline__ uint32_t ms_respawn(const MsParams& P, const uint16_t* a
     cell = avalid[bounded(r.x, (uint32_t)P.n_agent)];
   }
   return cell | (gcell << 16);
+}
+// out-of-line copy for the single-step kernels
+template <bool RGOAL, bool REPLAY>
+__device__ __noinline__ uint32_t ms_respawn(const MsParams& P, const uint16_t* avalid, const uint16_t* gvalid, int64_t env, uint32_t gcell, uint32_t t) {
+  return ms_respawn_inline<RGOAL, REPLAY>(P, avalid, gvalid, env, gcell, t);
 }
 
 // word W of the 4*OB contiguous observation bytes of a quad (env k contributes bytes e[k] >> 8*o, o < OB)
@@ -275,7 +280,8 @@ __global__ void __launch_bounds__(kMsThreads, MULTI ? GPT_MS_MINB_MULTI : GPT_MS
         uint32_t g = 0;
 #pragma unroll
         for (int i = 0; i < 4; ++i) g = i == k ? goalv[i] : g;
-        const uint32_t fresh = ms_respawn<RGOAL, REPLAY>(P, avalid, gvalid, q + k, g, (uint32_t)t);
+        // fused launches inline it: a CALL would wait for the in-flight action prefetch
+        const uint32_t fresh = MULTI ? ms_respawn_inline<RGOAL, REPLAY>(P, avalid, gvalid, q + k, g, (uint32_t)t) : ms_respawn<RGOAL, REPLAY>(P, avalid, gvalid, q + k, g, (uint32_t)t);
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           if (i == k) {

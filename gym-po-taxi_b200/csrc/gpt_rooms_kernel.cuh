@@ -256,7 +256,7 @@ template <int GRID_N> struct RoomsShape<GPT_OBS_GRID, GRID_N> {
 // Rare path, deliberately out of line (one copy per kernel instead of one per unrolled env):
 // _reset_some (rooms.py:191-196) — new goal first (random-goal envs), then new agent cell.
 template <bool RGOAL, bool REPLAY>
-__device__ __noinline__ uint32_t rooms_respawn(const RoomsParams& P, const uint16_t* valid, int64_t env, uint32_t gcell, uint32_t t) {
+__device__ __forceinline__ uint32_t rooms_respawn_inline(const RoomsParams& P, const uint16_t* valid, int64_t env, uint32_t gcell, uint32_t t) {
   uint32_t cell;
   if (REPLAY) {
     if (RGOAL) gcell = (uint32_t)P.rp_reset_goal[env];
@@ -270,6 +270,11 @@ __device__ __noinline__ uint32_t rooms_respawn(const RoomsParams& P, const uint1
     cell = valid[bounded(r.x, (uint32_t)P.n_valid)];
   }
   return cell | (gcell << 16);   // values, not references: no local-memory round trip at the call site
+}
+// out-of-line copy for the single-step kernels
+template <bool RGOAL, bool REPLAY>
+__device__ __noinline__ uint32_t rooms_respawn(const RoomsParams& P, const uint16_t* valid, int64_t env, uint32_t gcell, uint32_t t) {
+  return rooms_respawn_inline<RGOAL, REPLAY>(P, valid, env, gcell, t);
 }
 
 // resident CTAs per SM of the fused kernels; measured on B200 (2^22 envs, 8 steps per launch): hansen8 6 -> 331 G,
@@ -452,7 +457,8 @@ rooms_step_kernel(const __grid_constant__ RoomsParams P) {
         uint32_t g = 0;
 #pragma unroll
         for (int i = 0; i < 4; ++i) g = i == k ? goalv[i] : g;
-        const uint32_t fresh = rooms_respawn<RGOAL, REPLAY>(P, T.valid, q + k, g, (uint32_t)t);
+        // fused launches inline it: a CALL would wait for the in-flight action prefetch
+        const uint32_t fresh = MULTI ? rooms_respawn_inline<RGOAL, REPLAY>(P, T.valid, q + k, g, (uint32_t)t) : rooms_respawn<RGOAL, REPLAY>(P, T.valid, q + k, g, (uint32_t)t);
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           if (i == k) {

@@ -242,7 +242,7 @@ struct TaxiMultiParams {
 // Rare branch, out of line (one copy per kernel): full reset (extended_taxi.py:344-352) or passenger respawn
 // (:354-364) -> new state id.  `t` = step index inside a fused launch.
 template <bool REPLAY>
-__device__ __noinline__ uint32_t taxi_fix(const TaxiParams& P, const uint2* alias, int64_t env, uint32_t t, uint32_t cur, bool full) {
+__device__ __forceinline__ uint32_t taxi_fix_inline(const TaxiParams& P, const uint2* alias, int64_t env, uint32_t t, uint32_t cur, bool full) {
   if (REPLAY) {
     if (full) return (uint32_t)P.rp_reset_state[env];
     const uint32_t cell = fdiv(cur, P.div_pd);
@@ -261,6 +261,11 @@ __device__ __noinline__ uint32_t taxi_fix(const TaxiParams& P, const uint2* alia
   uint32_t d = bounded(rnd.z, (uint32_t)P.nlocs - 1);
   d += d >= p ? 1u : 0u;
   return (cell * (uint32_t)(P.nlocs + 1) + p) * (uint32_t)P.nlocs + d;
+}
+// out-of-line copy for the single-step kernel (its registers are dead at the call site)
+template <bool REPLAY>
+__device__ __noinline__ uint32_t taxi_fix(const TaxiParams& P, const uint2* alias, int64_t env, uint32_t t, uint32_t cur, bool full) {
+  return taxi_fix_inline<REPLAY>(P, alias, env, t, cur, full);
 }
 
 #ifndef GPT_TAXI_MINB_MULTI
@@ -313,17 +318,24 @@ __global__ void __launch_bounds__(THREADS, STATS ? 1 : GPT_TAXI_MINB_MULTI) taxi
       ret[j][0] = r4.x; ret[j][1] = r4.y; ret[j][2] = r4.z; ret[j][3] = r4.w;
     }
   }
+  uint32_t a_next[QPT];
+#pragma unroll
+  for (int j = 0; j < QPT; ++j) {
+    a_next[j] = 0u;
+    if (n_steps > 1) a_next[j] = ld_stream(reinterpret_cast<const uint32_t*>(P.actions + M.act_stride + base + j * kQuadStride));
+  }
   stage_tables_wait(&bar);
 
 #pragma unroll 1
   for (int32_t t = 0; t < n_steps; ++t) {
-    // prefetch the next step's action bytes (the only per-step read) ahead of this step's dependent table lookups
-    uint32_t a_next[QPT];
-    const bool more = t + 1 < n_steps;
+    // prefetch the action bytes (the only per-step read) TWO steps ahead: under the write-dominated traffic of this
+    // kernel a load takes longer than one loop iteration to come back
+    uint32_t a_next2[QPT];
+    const bool more = t + 2 < n_steps;
 #pragma unroll
     for (int j = 0; j < QPT; ++j) {
-      a_next[j] = 0u;
-      if (more) a_next[j] = ld_stream(reinterpret_cast<const uint32_t*>(P.actions + (int64_t)(t + 1) * M.act_stride + base + j * kQuadStride));
+      a_next2[j] = 0u;
+      if (more) a_next2[j] = ld_stream(reinterpret_cast<const uint32_t*>(P.actions + (int64_t)(t + 2) * M.act_stride + base + j * kQuadStride));
     }
     const int64_t orow = (int64_t)t * M.out_stride;
     uint32_t fix_done = 0, fix_goal = 0;   // bit 8k + j: env k of quad j finished its episode / delivered a passenger
@@ -366,6 +378,7 @@ __global__ void __launch_bounds__(THREADS, STATS ? 1 : GPT_TAXI_MINB_MULTI) taxi
       st_stream(reinterpret_cast<uint32_t*>(P.terminated + orow + q), tw);
       st_stream(reinterpret_cast<uint32_t*>(P.truncated + orow + q), trw);
       a4[j] = a_next[j];
+      a_next[j] = a_next2[j];
     }
     if (fix_done | fix_goal) {  // rare: full reset of finished envs, passenger respawn after a delivery (:283-286)
 #pragma unroll 1
@@ -377,7 +390,8 @@ __global__ void __launch_bounds__(THREADS, STATS ? 1 : GPT_TAXI_MINB_MULTI) taxi
 #pragma unroll
         for (int i = 0; i < 4 * QPT; ++i) cur = i == idx ? off[i >> 2][i & 3] : cur;
         const int64_t env = base + j * kQuadStride + k;
-        const uint32_t fresh = taxi_fix<REPLAY>(P, alias, env, (uint32_t)t, cur >> kRowShift, full);
+        // inlined: a CALL here would wait for the in-flight action prefetch (ncu: 20 % of all stall samples)
+        const uint32_t fresh = taxi_fix_inline<REPLAY>(P, alias, env, (uint32_t)t, cur >> kRowShift, full);
         P.obs[orow + env] = (int32_t)hobs[fresh];
 #pragma unroll
         for (int i = 0; i < 4 * QPT; ++i) {
