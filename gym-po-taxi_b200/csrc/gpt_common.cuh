@@ -8,6 +8,10 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#ifndef GPT_RESPAWN_INLINE_SINGLE
+#define GPT_RESPAWN_INLINE_SINGLE 1   // single-step ROOMS / MSRooms kernels inline the respawn too (measured: hansen8 259 -> 277 G, MSRooms 257 -> 281 G; 0 = out of line)
+#endif
+
 namespace gpt {
 
 constexpr int kWarp = 32;

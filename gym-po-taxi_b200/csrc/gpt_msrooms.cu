@@ -281,7 +281,7 @@ __global__ void __launch_bounds__(kMsThreads, MULTI ? GPT_MS_MINB_MULTI : GPT_MS
 #pragma unroll
         for (int i = 0; i < 4; ++i) g = i == k ? goalv[i] : g;
         // fused launches inline it: a CALL would wait for the in-flight action prefetch
-        const uint32_t fresh = MULTI ? ms_respawn_inline<RGOAL, REPLAY>(P, avalid, gvalid, q + k, g, (uint32_t)t) : ms_respawn<RGOAL, REPLAY>(P, avalid, gvalid, q + k, g, (uint32_t)t);
+        const uint32_t fresh = (MULTI || GPT_RESPAWN_INLINE_SINGLE) ? ms_respawn_inline<RGOAL, REPLAY>(P, avalid, gvalid, q + k, g, (uint32_t)t) : ms_respawn<RGOAL, REPLAY>(P, avalid, gvalid, q + k, g, (uint32_t)t);
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           if (i == k) {

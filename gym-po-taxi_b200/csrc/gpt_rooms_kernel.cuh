@@ -458,7 +458,7 @@ rooms_step_kernel(const __grid_constant__ RoomsParams P) {
 #pragma unroll
         for (int i = 0; i < 4; ++i) g = i == k ? goalv[i] : g;
         // fused launches inline it: a CALL would wait for the in-flight action prefetch
-        const uint32_t fresh = MULTI ? rooms_respawn_inline<RGOAL, REPLAY>(P, T.valid, q + k, g, (uint32_t)t) : rooms_respawn<RGOAL, REPLAY>(P, T.valid, q + k, g, (uint32_t)t);
+        const uint32_t fresh = (MULTI || GPT_RESPAWN_INLINE_SINGLE) ? rooms_respawn_inline<RGOAL, REPLAY>(P, T.valid, q + k, g, (uint32_t)t) : rooms_respawn<RGOAL, REPLAY>(P, T.valid, q + k, g, (uint32_t)t);
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           if (i == k) {

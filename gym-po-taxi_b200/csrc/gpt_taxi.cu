@@ -268,6 +268,9 @@ __device__ __noinline__ uint32_t taxi_fix(const TaxiParams& P, const uint2* alia
   return taxi_fix_inline<REPLAY>(P, alias, env, t, cur, full);
 }
 
+#ifndef GPT_TAXI_FIX_INLINE_SINGLE
+#define GPT_TAXI_FIX_INLINE_SINGLE 0
+#endif
 #ifndef GPT_TAXI_MINB_MULTI
 #define GPT_TAXI_MINB_MULTI 6   // 72 registers; measured on B200 (2^22 envs, 8 steps per launch): 4 -> 412 G, 6 -> 417 G, 7 -> 418 G
 #endif
@@ -525,7 +528,11 @@ __global__ void __launch_bounds__(THREADS, (STATS || QPT > 2) ? 1 : 1280 / THREA
     int32_t cur = 0;
 #pragma unroll
     for (int i = 0; i < 4 * QPT; ++i) cur = i == b ? keep_s[i] : cur;
+#if GPT_TAXI_FIX_INLINE_SINGLE
+    const uint32_t fresh = taxi_fix_inline<REPLAY>(P, alias, env, 0u, (uint32_t)cur, full);   // same sampler as the fused kernel
+#else
     const uint32_t fresh = taxi_fix<REPLAY>(P, alias, env, 0u, (uint32_t)cur, full);   // same sampler as the fused kernel
+#endif
     if (full) {
       P.elapsed[env] = 0;
       P.ndrop[env] = 0;
