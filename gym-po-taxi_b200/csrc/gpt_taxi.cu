@@ -269,7 +269,7 @@ __device__ __noinline__ uint32_t taxi_fix(const TaxiParams& P, const uint2* alia
 }
 
 #ifndef GPT_TAXI_FIX_INLINE_SINGLE
-#define GPT_TAXI_FIX_INLINE_SINGLE 0
+#define GPT_TAXI_FIX_INLINE_SINGLE 1   // measured: 253.9 -> 256.4 G (0 = out-of-line call)
 #endif
 #ifndef GPT_TAXI_MINB_MULTI
 #define GPT_TAXI_MINB_MULTI 6   // 72 registers; measured on B200 (2^22 envs, 8 steps per launch): 4 -> 412 G, 6 -> 417 G, 7 -> 418 G
