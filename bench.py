@@ -217,6 +217,10 @@ def run_b200(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    from gym_po.sharding import bind_to_gpu_numa_node
+    # multi-GPU runs: pin each rank next to its GPU before any pinned host buffer is allocated (single-GPU runs keep
+    # the whole cpuset: the CPU baseline of the same run uses every host core)
+    numa = bind_to_gpu_numa_node(local_rank) if world > 1 else "not bound (single process)"
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     wl = WORKLOADS[args.workload]
@@ -353,7 +357,8 @@ def run_b200(args):
                          "traffic": None, "peak_source": peak_src, "alg_bytes_per_env_step": alg_bytes,
                          "steps_per_launch": steps_per_launch, "kernel_us": per_launch_s * 1e6, "frac_of_nominal_8TBs": achieved / 8000.0},
             "e2e": {"value": total_envs * e2e_steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d * world,
-                    "d2h_bytes_per_step": d2h * world, "steps": e2e_steps, "api": "env.step_host(numpy) -> gpt_step_host"},
+                    "d2h_bytes_per_step": d2h * world, "steps": e2e_steps, "api": "env.step_host(numpy) -> gpt_step_host",
+                    "host_numa": numa},
             "gpu_launches": launches * world,
             "clocks": sampler.summary(),
         }

@@ -38,6 +38,38 @@ def shard_envs(total_envs: int, rank: int, world: int, align: int = ENV_ALIGN):
     return n, offset
 
 
+def bind_to_gpu_numa_node(device_index: int) -> str:
+    """Pin the calling process to the CPUs of the NUMA node the GPU hangs off (one process per GPU: the host path's
+    pinned buffers are then allocated next to the GPU's PCIe root and the ranks stop sharing one socket's memory
+    controllers).  Best effort: returns a short description, or the reason nothing was done."""
+    if os.environ.get("GPT_NO_NUMA_BIND"):
+        return "disabled (GPT_NO_NUMA_BIND)"
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        bus = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(device_index)).busId
+        bus = (bus.decode() if isinstance(bus, bytes) else bus).lower()
+        if len(bus.split(":")[0]) == 8:          # NVML prints an 8-digit PCI domain, sysfs a 4-digit one
+            bus = bus[4:]
+        with open(f"/sys/bus/pci/devices/{bus}/numa_node") as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return "no NUMA information for the GPU"
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+            spec = f.read().strip()
+        cpus = set()
+        for part in spec.split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return f"NUMA node {node} has no CPU in this process's cpuset"
+        os.sched_setaffinity(0, cpus)
+        return f"bound to NUMA node {node} ({len(cpus)} CPUs)"
+    except Exception as e:  # pragma: no cover - depends on the box
+        return f"not bound ({type(e).__name__}: {e})"
+
+
 def allreduce_stats(stats: torch.Tensor) -> dict:
     """Sum the per-rank statistics vector over all ranks (in place) and return it as a dict with the
     derived means.  A no-op reduction when torch.distributed is not initialised (single GPU)."""
