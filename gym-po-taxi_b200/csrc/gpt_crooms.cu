@@ -106,7 +106,6 @@ int crooms_launch(gpt_env* env, const LaunchArgs& a) {
   P.room_off = env->rl.room_off;
   P.sid_off = env->rl.sid_off;
   P.valid_off = env->rl.valid_off;
-  P.thr32_off = env->rl.thr32_off;
   P.thr64_off = env->rl.thr64_off;
   P.rows_off = env->rl.rows_off;
   P.grid_off = env->rl.grid_off;

@@ -88,7 +88,7 @@ struct CRoomsParams {
   const int32_t* rp_reset_agent;
   const int32_t* rp_reset_goal;
   const uint8_t* blob;
-  uint32_t blob_bytes, nb8_off, room_off, sid_off, valid_off, thr32_off, thr64_off, rows_off, stage_off, grid_off, alias_off;
+  uint32_t blob_bytes, nb8_off, room_off, sid_off, valid_off, thr64_off, rows_off, stage_off, grid_off, alias_off;
   uint32_t log2n;
   int64_t env_offset;
   int32_t first_tile, n_tiles, mode;
@@ -202,7 +202,6 @@ __global__ void __launch_bounds__(128, GPT_CROOMS_MINB) crooms_step_kernel(const
   T.room = smem + P.room_off;
   T.sid = reinterpret_cast<const uint16_t*>(smem + P.sid_off);
   T.valid = reinterpret_cast<const uint16_t*>(smem + P.valid_off);
-  T.thr32 = reinterpret_cast<const uint32_t*>(smem + P.thr32_off);
   T.thr64 = reinterpret_cast<const double*>(smem + P.thr64_off);
   T.rows = reinterpret_cast<const uint64_t*>(smem + P.rows_off);
   const int8_t* grid = reinterpret_cast<const int8_t*>(smem + P.grid_off);

@@ -52,7 +52,7 @@ struct gpt_env {
   int taxi_shape = 0;  // launch-shape tuning knob (GPT_TAXI_SHAPE), 0 = default
   // ---- rooms / crooms ----
   struct RoomsLayout {
-    uint32_t nb8_off = 0, yx_off = 0, room_off = 0, sid_off = 0, valid_off = 0, thr32_off = 0, thr64_off = 0,
+    uint32_t nb8_off = 0, yx_off = 0, room_off = 0, sid_off = 0, valid_off = 0, thr64_off = 0,
              rows_off = 0, grid_off = 0, move_off = 0, obstab_off = 0, alias_off = 0, moveobs_off = 0;
     int32_t n_valid = 0, n_rooms = 0, n_cells = 0;
   } rl;

@@ -76,24 +76,12 @@ int rooms_build_tables(gpt_env* env, const gpt_config* c, bool discrete_actions)
   env->rl.n_rooms = n_rooms;
   env->rl.n_cells = nc;
 
-  std::vector<uint32_t> thr32;
   std::vector<double> thr64;
   if (discrete_actions) {
     const int n = c->rooms_n_actions;
     if (n != 4 && n != 8) return fail(GPT_E_ARG, "rooms: n_actions must be 4 (cardinal) or 8 (ordinal)");
     if (!c->rooms_slip_cumsum) return fail(GPT_E_ARG, "rooms: slip_cumsum missing");
-    thr64.assign(c->rooms_slip_cumsum, c->rooms_slip_cumsum + n * n);
-    // Philox-mode thresholds: rows of 8 in ordinal-direction units.  a' = min(#{T_j < u}, n-1) means the
-    // last threshold never counts, i.e. it is +inf (0xFFFFFFFF); a cardinal env stores every threshold
-    // twice so that the count comes out as the ordinal direction 2a'.
-    thr32.assign(n * 8, 0xFFFFFFFFu);
-    const int rep = 8 / n;
-    for (int a = 0; a < n; ++a)
-      for (int j = 0; j + 1 < n; ++j) {
-        const double t = thr64[a * n + j] * 4294967296.0;
-        const uint32_t q32 = t >= 4294967295.0 ? 0xFFFFFFFFu : (t <= 0 ? 0u : (uint32_t)t);  // floor
-        for (int r = 0; r < rep; ++r) thr32[a * 8 + j * rep + r] = q32;
-      }
+    thr64.assign(c->rooms_slip_cumsum, c->rooms_slip_cumsum + n * n);   // replay mode compares the recorded u with these
   }
   // walkable-bit rows padded by the window radius (grid obs)
   std::vector<uint64_t> rows;
@@ -190,7 +178,6 @@ int rooms_build_tables(gpt_env* env, const gpt_config* c, bool discrete_actions)
   env->rl.room_off = blob_append(blob, room);
   env->rl.sid_off = blob_append(blob, sid);
   env->rl.valid_off = blob_append(blob, valid);
-  env->rl.thr32_off = blob_append(blob, thr32);
   env->rl.thr64_off = blob_append(blob, thr64);
   env->rl.rows_off = blob_append(blob, rows);
   if (!discrete_actions || c->family == GPT_FAMILY_CROOMS) {  // continuous env: wall test on floor(pos / cell)
@@ -311,7 +298,6 @@ int rooms_launch(gpt_env* env, const LaunchArgs& a) {
   P.room_off = env->rl.room_off;
   P.sid_off = env->rl.sid_off;
   P.valid_off = env->rl.valid_off;
-  P.thr32_off = env->rl.thr32_off;
   P.thr64_off = env->rl.thr64_off;
   P.rows_off = env->rl.rows_off;
   P.move_off = env->rl.move_off;

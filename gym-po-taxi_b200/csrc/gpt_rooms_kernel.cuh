@@ -14,7 +14,7 @@
 //   nb8   uint8 [cells]  bit i = neighbour i (N,NE,E,SE,S,SW,W,NW) is walkable.  Drives BOTH the wall
 //                        collision (blocked = bit of the slipped direction clear) and the Hansen obs.
 //   room  uint8 [cells], sid uint16[cells] (dense cell id), valid uint16[n_valid] (spawn cells)
-//   thr32 uint32[n*n]    floor(cumsum(P[a]) * 2^32)  Philox-mode slip thresholds
+//   alias uint2[n*8]     Walker alias table per intended action (Philox-mode slip): {threshold, dir | alias dir << 8}
 //   thr64 double[n*n]    cumsum(P[a]) exactly as numpy computes it (replay mode compares the recorded u)
 //   rows  uint64[H+2*off] walkable-bit rows, padded by the window radius (grid obs only)
 #pragma once
@@ -39,7 +39,7 @@ struct RoomsParams {
   const int32_t* rp_reset_agent;
   const int32_t* rp_reset_goal;
   const uint8_t* blob;
-  uint32_t blob_bytes, nb8_off, room_off, sid_off, valid_off, thr32_off, thr64_off, rows_off, stage_off, move_off, obstab_off, alias_off, moveobs_off;
+  uint32_t blob_bytes, nb8_off, room_off, sid_off, valid_off, thr64_off, rows_off, stage_off, move_off, obstab_off, alias_off, moveobs_off;
   uint32_t log2n;   // log2(n_actions)
   int64_t env_offset;
   int32_t first_tile, n_tiles, mode;
@@ -59,7 +59,6 @@ struct RoomsTables {
   const uint8_t* room;
   const uint16_t* sid;
   const uint16_t* valid;
-  const uint32_t* thr32;
   const double* thr64;
   const uint64_t* rows;
 };
@@ -337,7 +336,6 @@ rooms_step_kernel(const __grid_constant__ RoomsParams P) {
   T.room = smem + P.room_off;
   T.sid = reinterpret_cast<const uint16_t*>(smem + P.sid_off);
   T.valid = reinterpret_cast<const uint16_t*>(smem + P.valid_off);
-  T.thr32 = reinterpret_cast<const uint32_t*>(smem + P.thr32_off);
   T.thr64 = reinterpret_cast<const double*>(smem + P.thr64_off);
   T.rows = reinterpret_cast<const uint64_t*>(smem + P.rows_off);
   const uint16_t* move = reinterpret_cast<const uint16_t*>(smem + P.move_off);     // [cell*8 + dir] next cell | blocked << 15

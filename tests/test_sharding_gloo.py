@@ -59,3 +59,14 @@ def test_shard_envs_properties():
             assert pos == total
     with pytest.raises(ValueError):
         shard_envs(10, 2, 2)
+
+
+def test_numa_binding_is_best_effort():
+    """bind_to_gpu_numa_node never raises: without NVML / sysfs information it reports why nothing was done."""
+    import os
+    from gym_po.sharding import bind_to_gpu_numa_node
+    before = os.sched_getaffinity(0)
+    msg = bind_to_gpu_numa_node(0)
+    assert isinstance(msg, str) and msg
+    assert os.sched_getaffinity(0) <= before
+    os.sched_setaffinity(0, before)
