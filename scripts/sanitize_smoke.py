@@ -4,7 +4,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "gym-po-taxi_b200"))
 import numpy as np, torch
 import oracle
-from gym_po.envs import TaxiVecEnv, RoomsEnv, CRoomsEnv, TagVecEnv
+from gym_po.envs import TaxiVecEnv, RoomsEnv, CRoomsEnv, TagVecEnv, MultistoryFourRoomsEnv, CarVecEnv
+from gym_po.wrappers import NormalizeReward, RecordEpisodeStatistics
 dev = "cuda:0"
 for b in (1, 700, 5000):
     for hansen in (False, True):
@@ -28,6 +29,25 @@ for b in (1, 700, 5000):
         e.reset()
         for _ in range(20):
             e.step(torch.rand((b, 2), device=dev) * 2 - 1)
+    # multistory rooms (all observation byte widths), car-flag, wrapper layer, fused multi-step launches
+    for obs, goal in (("mdp", (9, 7, -1)), ("vector_mdp", (9, 7, -1)), ("vector_mdp_goal", None), ("vector_goal_hansen8", None), ("hansen", None)):
+        e = MultistoryFourRoomsEnv(b, grid_z=3, obs_type=obs, goal_xyz=goal, time_limit=6, device=dev, seed=5)
+        e.reset()
+        for _ in range(20):
+            e.step(torch.randint(0, 4, (b,), dtype=torch.int8, device=dev))
+        e.step_many(torch.randint(0, 4, (9, e.capacity), dtype=torch.int8, device=dev))
+    e = CarVecEnv(b, time_limit=6, device=dev, seed=6)
+    e.reset()
+    for _ in range(20):
+        e.step(torch.rand((b, 1), device=dev) * 2 - 1)
+    w = NormalizeReward(RecordEpisodeStatistics(TaxiVecEnv(b, time_limit=7, device=dev, seed=7)), gamma=0.9)
+    w.reset()
+    for _ in range(20):
+        w.step(torch.randint(0, 5, (b,), dtype=torch.int8, device=dev))
+    for env, n_act in ((TaxiVecEnv(b, time_limit=7, num_passengers=2, device=dev, seed=8), 5),
+                       (RoomsEnv(b, "8", obs_type="grid", obs_n=7, goal_xy=None, time_limit=6, device=dev, seed=9), 8)):
+        env.reset()
+        env.step_many(torch.randint(0, n_act, (11, env.capacity), dtype=torch.int8, device=dev))
 # replay mode, arith kernel
 big = ("A" + " " * 13 + "B",) + (" " * 6 + "|" + " " * 8,) * 6 + ("C" + " " * 13 + "D",) + (" " * 15,) * 6 + ("E" + " " * 13 + "F",)
 orc = oracle.TaxiOracle(600, map=big, time_limit=5, draws=oracle.GeneratorDraws(seed=1))
