@@ -100,6 +100,23 @@ int upload_blob(gpt_env* env, const std::vector<uint8_t>& blob) {
   return GPT_OK;
 }
 
+// graph mode: advances the device-resident Philox step counter after a step (one thread; captured into the graph)
+__global__ void tick_kernel(uint64_t* counter, uint64_t n) { *counter += n; }
+
+static bool graph_mode_family(const gpt_env* env) {
+  const gpt_config& c = env->cfg;
+  if (c.rng_mode != GPT_RNG_PHILOX || c.track_stats) return false;
+  return (c.family == GPT_FAMILY_TAXI && env->taxi_use_table) || c.family == GPT_FAMILY_ROOMS;
+}
+
+static int tick(gpt_env* env, uint64_t n, cudaStream_t stream) {
+  if (!env->graph_mode) return GPT_OK;
+  tick_kernel<<<1, 1, 0, stream>>>(env->d_counter, n);
+  env->launches += 1;
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? GPT_OK : cuda_fail(e, "tick_kernel launch");
+}
+
 static int launch(gpt_env* env, const LaunchArgs& a) {
   switch (env->cfg.family) {
     case GPT_FAMILY_TAXI: return taxi_launch(env, a);
@@ -252,6 +269,7 @@ int gpt_destroy(gpt_env* env) {
   cudaSetDevice(env->cfg.device);
   if (env->d_blob) cudaFree(env->d_blob);
   if (env->d_stats) cudaFree(env->d_stats);
+  if (env->d_counter) cudaFree(env->d_counter);
   if (env->host.ready) {
     for (int i = 0; i < HostPath::kStreams; ++i) {
       if (env->host.done[i]) cudaEventDestroy(env->host.done[i]);
@@ -310,8 +328,14 @@ int gpt_reset(gpt_env* env, int has_seed, uint64_t seed, void* stream) {
   a.mode = kModeReset;
   a.n_tiles = env->n_tiles;
   a.stream = (cudaStream_t)stream;
+  if (env->graph_mode && has_seed) {  // the seed restarts the counter: mirror it to the device (not capturable, like reset itself)
+    cudaError_t e = cudaMemcpyAsync(env->d_counter, &env->counter, sizeof(uint64_t), cudaMemcpyHostToDevice, a.stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(a.stream);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMemcpyAsync(step counter)");
+  }
   int rc = launch(env, a);
   env->counter += 1;
+  if (rc == GPT_OK) rc = tick(env, 1, a.stream);
   return rc;
 }
 
@@ -325,6 +349,7 @@ int gpt_step(gpt_env* env, const void* actions, void* stream) {
   a.stream = (cudaStream_t)stream;
   int rc = launch(env, a);
   env->counter += 1;
+  if (rc == GPT_OK) rc = tick(env, 1, a.stream);
   return rc;
 }
 
@@ -349,7 +374,7 @@ int gpt_step_many(gpt_env* env, const void* actions, int32_t n_steps, int64_t ou
         return fail(GPT_E_ARG, "gpt_step_many: bound output arrays are too small for n_steps*out_stride_rows");
   }
   static const bool no_fuse = getenv("GPT_NO_FUSED_STEPS") != nullptr;
-  const bool fuse = !no_fuse && !env->no_fused_steps && n_steps > 1 &&
+  const bool fuse = !no_fuse && !env->no_fused_steps && !env->graph_mode && n_steps > 1 &&
                     ((env->cfg.family == GPT_FAMILY_TAXI && taxi_can_fuse(env)) || (env->cfg.family == GPT_FAMILY_ROOMS && rooms_can_fuse(env)) ||
                      (env->cfg.family == GPT_FAMILY_MSROOMS && msrooms_can_fuse(env)));
   if (fuse) {  // one launch for all n_steps: state stays in registers, only actions are read and outputs written per step
@@ -379,6 +404,7 @@ int gpt_step_many(gpt_env* env, const void* actions, int32_t n_steps, int64_t ou
     }
     int rc = launch(env, a);
     env->counter += 1;
+    if (rc == GPT_OK) rc = tick(env, 1, a.stream);
     if (rc) return rc;
   }
   return GPT_OK;
@@ -390,9 +416,34 @@ int gpt_set_fused_steps(gpt_env* env, int enable) {
   return GPT_OK;
 }
 
+int gpt_set_graph_mode(gpt_env* env, int enable, void* stream) {
+  if (!env) return fail(GPT_E_ARG, "gpt_set_graph_mode: NULL env");
+  cudaError_t e = cudaSetDevice(env->cfg.device);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaSetDevice");
+  if (enable) {
+    if (!graph_mode_family(env))
+      return fail(GPT_E_ARG, "gpt_set_graph_mode: supported for Taxi (table kernel) and ROOMS in Philox mode without track_stats");
+    if (!env->d_counter) {
+      e = cudaMalloc((void**)&env->d_counter, sizeof(uint64_t));
+      if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc(step counter)");
+    }
+    e = cudaMemcpyAsync(env->d_counter, &env->counter, sizeof(uint64_t), cudaMemcpyHostToDevice, (cudaStream_t)stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize((cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMemcpyAsync(step counter)");
+    env->graph_mode = true;
+  } else if (env->graph_mode) {  // back to launch-parameter counters: fetch the device value (graph replays advanced it)
+    e = cudaStreamSynchronize((cudaStream_t)stream);
+    if (e == cudaSuccess) e = cudaMemcpy(&env->counter, env->d_counter, sizeof(uint64_t), cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMemcpy(step counter)");
+    env->graph_mode = false;
+  }
+  return GPT_OK;
+}
+
 int gpt_step_host(gpt_env* env, const gpt_host_io* io) {
   if (!env || !io || !io->actions || !io->obs || !io->reward || !io->terminated || !io->truncated)
     return fail(GPT_E_ARG, "gpt_step_host: NULL argument");
+  if (env->graph_mode) return fail(GPT_E_ARG, "gpt_step_host: not available in graph mode");
   NvtxRange range("gpt_step_host");
   cudaError_t e = cudaSetDevice(env->cfg.device);
   if (e != cudaSuccess) return cuda_fail(e, "cudaSetDevice");
@@ -454,11 +505,23 @@ int gpt_step_host(gpt_env* env, const gpt_host_io* io) {
 int gpt_get_counter(const gpt_env* env, uint64_t* counter) {
   if (!env || !counter) return fail(GPT_E_ARG, "gpt_get_counter: NULL argument");
   *counter = env->counter;
+  if (env->graph_mode) {  // the device value is the truth (graph replays advance it); synchronises the device
+    cudaError_t e = cudaSetDevice(env->cfg.device);
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    if (e == cudaSuccess) e = cudaMemcpy(counter, env->d_counter, sizeof(uint64_t), cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMemcpy(step counter)");
+  }
   return GPT_OK;
 }
 int gpt_set_counter(gpt_env* env, uint64_t counter) {
   if (!env) return fail(GPT_E_ARG, "gpt_set_counter: NULL env");
   env->counter = counter;
+  if (env->graph_mode) {
+    cudaError_t e = cudaSetDevice(env->cfg.device);
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    if (e == cudaSuccess) e = cudaMemcpy(env->d_counter, &env->counter, sizeof(uint64_t), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMemcpy(step counter)");
+  }
   return GPT_OK;
 }
 int gpt_set_env_offset(gpt_env* env, int64_t env_offset) {

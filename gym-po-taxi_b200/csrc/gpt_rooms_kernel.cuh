@@ -52,6 +52,7 @@ struct RoomsParams {
   int64_t act_stride;   // bytes between consecutive steps' action rows (= capacity)
   int64_t out_stride;   // rows between consecutive steps' outputs (0 = overwrite in place)
   RngKey rng;
+  const uint64_t* ctr_ptr;   // graph mode (DEVCTR kernels): device-resident Philox step counter, else unused
 };
 
 struct RoomsTables {
@@ -255,13 +256,12 @@ template <int GRID_N> struct RoomsShape<GPT_OBS_GRID, GRID_N> {
 // Rare path, deliberately out of line (one copy per kernel instead of one per unrolled env):
 // _reset_some (rooms.py:191-196) — new goal first (random-goal envs), then new agent cell.
 template <bool RGOAL, bool REPLAY>
-__device__ __forceinline__ uint32_t rooms_respawn_inline(const RoomsParams& P, const uint16_t* valid, int64_t env, uint32_t gcell, uint32_t t) {
+__device__ __forceinline__ uint32_t rooms_respawn_inline(const RoomsParams& P, const uint16_t* valid, int64_t env, uint32_t gcell, uint64_t ctr) {
   uint32_t cell;
   if (REPLAY) {
     if (RGOAL) gcell = (uint32_t)P.rp_reset_goal[env];
     cell = (uint32_t)P.rp_reset_agent[env];
   } else {
-    const uint64_t ctr = (((uint64_t)P.rng.step_hi << 32) | P.rng.step_lo) + t;   // step index inside a fused launch
     const uint64_t ge = (uint64_t)(P.env_offset + env);
     const uint4 r = philox4x32_10(make_uint4((uint32_t)ge, (uint32_t)(ge >> 32), (uint32_t)ctr,
                                              ((uint32_t)(ctr >> 32) & 0x00FFFFFFu) ^ (1u << 24)), P.rng);
@@ -272,8 +272,8 @@ __device__ __forceinline__ uint32_t rooms_respawn_inline(const RoomsParams& P, c
 }
 // out-of-line copy for the single-step kernels
 template <bool RGOAL, bool REPLAY>
-__device__ __noinline__ uint32_t rooms_respawn(const RoomsParams& P, const uint16_t* valid, int64_t env, uint32_t gcell, uint32_t t) {
-  return rooms_respawn_inline<RGOAL, REPLAY>(P, valid, env, gcell, t);
+__device__ __noinline__ uint32_t rooms_respawn(const RoomsParams& P, const uint16_t* valid, int64_t env, uint32_t gcell, uint64_t ctr) {
+  return rooms_respawn_inline<RGOAL, REPLAY>(P, valid, env, gcell, ctr);
 }
 
 // resident CTAs per SM of the fused kernels; measured on B200 (2^22 envs, 8 steps per launch): hansen8 6 -> 331 G,
@@ -284,7 +284,7 @@ __device__ __noinline__ uint32_t rooms_respawn(const RoomsParams& P, const uint1
 // MULTI: gpt_step_many as ONE launch — pos / goal / elapsed are read once, live in registers for P.n_steps steps and
 // are written once; per step only the action byte is read and the outputs are written.  Bit-identical to n_steps
 // single-step launches (Philox counters = (global env / quad id, first step + t)).
-template <int OBS, bool RGOAL, bool REPLAY, int GRID_N, bool STATS, bool MULTI = false>
+template <int OBS, bool RGOAL, bool REPLAY, int GRID_N, bool STATS, bool MULTI = false, bool DEVCTR = false>
 __global__ void __launch_bounds__(RoomsShape<OBS, GRID_N>::kThreads,
                                   STATS ? 1 : (MULTI ? (RoomsShape<OBS, GRID_N>::kMinBlocks > 1 ? GPT_ROOMS_MINB_MULTI : 1) : RoomsShape<OBS, GRID_N>::kMinBlocks))
 rooms_step_kernel(const __grid_constant__ RoomsParams P) {
@@ -361,6 +361,9 @@ rooms_step_kernel(const __grid_constant__ RoomsParams P) {
     evq[j][0] = e4[j].x; evq[j][1] = e4[j].y; evq[j][2] = e4[j].z; evq[j][3] = e4[j].w;
   }
   const int32_t n_steps = MULTI ? P.n_steps : 1;
+  // DEVCTR (graph mode): the step counter comes from device memory, so that a captured CUDA graph can be replayed
+  uint64_t ctr0 = ((uint64_t)P.rng.step_hi << 32) | P.rng.step_lo;
+  if constexpr (DEVCTR) ctr0 = *P.ctr_ptr;
   const size_t obs_row = OBS == GPT_OBS_GRID ? (size_t)(gn * gn)
                          : (OBS == GPT_OBS_VEC_MDP ? 2 : ((OBS == GPT_OBS_VEC_HANSEN || OBS == GPT_OBS_VEC_HANSEN_GOAL) ? (size_t)P.hansen_n : 4));
 #pragma unroll 1
@@ -373,7 +376,7 @@ rooms_step_kernel(const __grid_constant__ RoomsParams P) {
     if (more) a_next[j] = ld_stream(reinterpret_cast<const uint32_t*>(P.actions + (int64_t)(t + 1) * P.act_stride + base + j * kQuadStride));
   }
   const int64_t orow = MULTI ? (int64_t)t * P.out_stride : 0;
-  const uint64_t ctr = (((uint64_t)P.rng.step_hi << 32) | P.rng.step_lo) + (uint32_t)t;
+  const uint64_t ctr = ctr0 + (uint32_t)t;   // Philox step counter of this step
   const uint32_t ctr_lo = (uint32_t)ctr, ctr_hi = (uint32_t)(ctr >> 32) & 0x00FFFFFFu;
 #pragma unroll
   for (int j = 0; j < QPT; ++j) {
@@ -456,7 +459,7 @@ rooms_step_kernel(const __grid_constant__ RoomsParams P) {
 #pragma unroll
         for (int i = 0; i < 4; ++i) g = i == k ? goalv[i] : g;
         // fused launches inline it: a CALL would wait for the in-flight action prefetch
-        const uint32_t fresh = (MULTI || GPT_RESPAWN_INLINE_SINGLE) ? rooms_respawn_inline<RGOAL, REPLAY>(P, T.valid, q + k, g, (uint32_t)t) : rooms_respawn<RGOAL, REPLAY>(P, T.valid, q + k, g, (uint32_t)t);
+        const uint32_t fresh = (MULTI || GPT_RESPAWN_INLINE_SINGLE) ? rooms_respawn_inline<RGOAL, REPLAY>(P, T.valid, q + k, g, ctr) : rooms_respawn<RGOAL, REPLAY>(P, T.valid, q + k, g, ctr);
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           if (i == k) {
@@ -516,10 +519,14 @@ static void* pick_rr2(bool rgoal, bool replay) {
               : (replay ? (K)rooms_step_kernel<OBS, false, true, GRID_N, STATS> : (K)rooms_step_kernel<OBS, false, false, GRID_N, STATS>);
   return (void*)k;
 }
-// variant: 0 = plain single step, 1 = single step with in-kernel statistics, 2 = fused multi-step (Philox mode)
+// variant: 0 = plain single step, 1 = single step with in-kernel statistics, 2 = fused multi-step (Philox mode),
+// 3 = single step with the device-resident step counter (graph mode, Philox)
 template <int OBS, int GRID_N>
 static void* pick_rr(bool rgoal, bool replay, int variant) {
   using K = void (*)(const RoomsParams);
+  if (variant == 3)
+    return replay ? nullptr
+                  : (void*)(rgoal ? (K)rooms_step_kernel<OBS, true, false, GRID_N, false, false, true> : (K)rooms_step_kernel<OBS, false, false, GRID_N, false, false, true>);
   if (variant == 2)
     return replay ? nullptr
                   : (void*)(rgoal ? (K)rooms_step_kernel<OBS, true, false, GRID_N, false, true> : (K)rooms_step_kernel<OBS, false, false, GRID_N, false, true>);

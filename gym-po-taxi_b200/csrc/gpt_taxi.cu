@@ -59,6 +59,7 @@ struct TaxiParams {
   FastDiv div_nlocs, div_nlocs1;
   float r_goal, r_bad, r_any;
   RngKey rng;
+  const uint64_t* ctr_ptr;   // graph mode (DEVCTR kernels): device-resident Philox step counter, else unused
 };
 
 struct TaxiTables {
@@ -242,13 +243,13 @@ struct TaxiMultiParams {
 // Rare branch, out of line (one copy per kernel): full reset (extended_taxi.py:344-352) or passenger respawn
 // (:354-364) -> new state id.  `t` = step index inside a fused launch.
 template <bool REPLAY>
-__device__ __forceinline__ uint32_t taxi_fix_inline(const TaxiParams& P, const uint2* alias, int64_t env, uint32_t t, uint32_t cur, bool full) {
+__device__ __forceinline__ uint32_t taxi_fix_inline(const TaxiParams& P, const uint2* alias, int64_t env, uint64_t ctr0, uint32_t t, uint32_t cur, bool full) {
   if (REPLAY) {
     if (full) return (uint32_t)P.rp_reset_state[env];
     const uint32_t cell = fdiv(cur, P.div_pd);
     return (cell * (uint32_t)(P.nlocs + 1) + (uint32_t)P.rp_new_p[env]) * (uint32_t)P.nlocs + (uint32_t)P.rp_new_d[env];
   }
-  const uint64_t ctr = (((uint64_t)P.rng.step_hi << 32) | P.rng.step_lo) + t;
+  const uint64_t ctr = ctr0 + t;   // Philox step counter of this step
   const uint64_t ge = (uint64_t)(P.env_offset + env);
   const uint4 rnd = philox4x32_10(make_uint4((uint32_t)ge, (uint32_t)(ge >> 32), (uint32_t)ctr, (uint32_t)(ctr >> 32) & 0x00FFFFFFu), P.rng);
   if (full) {  // the law of argmax(multinomial(ns, uniform over valid states)), sampled through its alias table
@@ -264,8 +265,8 @@ __device__ __forceinline__ uint32_t taxi_fix_inline(const TaxiParams& P, const u
 }
 // out-of-line copy for the single-step kernel (its registers are dead at the call site)
 template <bool REPLAY>
-__device__ __noinline__ uint32_t taxi_fix(const TaxiParams& P, const uint2* alias, int64_t env, uint32_t t, uint32_t cur, bool full) {
-  return taxi_fix_inline<REPLAY>(P, alias, env, t, cur, full);
+__device__ __noinline__ uint32_t taxi_fix(const TaxiParams& P, const uint2* alias, int64_t env, uint64_t ctr0, uint32_t t, uint32_t cur, bool full) {
+  return taxi_fix_inline<REPLAY>(P, alias, env, ctr0, t, cur, full);
 }
 
 #ifndef GPT_TAXI_FIX_INLINE_SINGLE
@@ -301,6 +302,7 @@ __global__ void __launch_bounds__(THREADS, STATS ? 1 : GPT_TAXI_MINB_MULTI) taxi
   const int64_t base = first + wtile * kEnvsPerWarp + lane * kQuad;
   if (base >= last) return;
   pdl_wait();   // the previous launch's writes are complete and visible from here on
+  const uint64_t ctr0 = ((uint64_t)P.rng.step_hi << 32) | P.rng.step_lo;
   uint32_t off[QPT][4], ndv[QPT][4], a4[QPT];   // off = state id << kRowShift
   int32_t ev[QPT][4];
   float ret[STATS ? QPT : 1][4];
@@ -394,7 +396,7 @@ __global__ void __launch_bounds__(THREADS, STATS ? 1 : GPT_TAXI_MINB_MULTI) taxi
         for (int i = 0; i < 4 * QPT; ++i) cur = i == idx ? off[i >> 2][i & 3] : cur;
         const int64_t env = base + j * kQuadStride + k;
         // inlined: a CALL here would wait for the in-flight action prefetch (ncu: 20 % of all stall samples)
-        const uint32_t fresh = taxi_fix_inline<REPLAY>(P, alias, env, (uint32_t)t, cur >> kRowShift, full);
+        const uint32_t fresh = taxi_fix_inline<REPLAY>(P, alias, env, ctr0, (uint32_t)t, cur >> kRowShift, full);
         P.obs[orow + env] = (int32_t)hobs[fresh];
 #pragma unroll
         for (int i = 0; i < 4 * QPT; ++i) {
@@ -425,7 +427,9 @@ __global__ void __launch_bounds__(THREADS, STATS ? 1 : GPT_TAXI_MINB_MULTI) taxi
 constexpr uint32_t kT16State = 0x1FFFu, kT16Goal = 1u << 13, kT16Bad = 1u << 14;
 constexpr int kT16Cols = 6;  // actions 0..4 + "no-op" column for out-of-range action bytes
 
-template <bool HANSEN, bool REPLAY, bool STATS, int QPT, int THREADS>
+// DEVCTR (graph mode): the Philox step counter is read from device memory instead of the launch parameters, so that
+// a captured CUDA graph can be replayed (a one-thread tick kernel advances the counter after every step).
+template <bool HANSEN, bool REPLAY, bool STATS, int QPT, int THREADS, bool DEVCTR = false>
 __global__ void __launch_bounds__(THREADS, (STATS || QPT > 2) ? 1 : 1280 / THREADS) taxi_table_kernel(const __grid_constant__ TaxiParams P) {
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ uint64_t bar;
@@ -442,6 +446,8 @@ __global__ void __launch_bounds__(THREADS, (STATS || QPT > 2) ? 1 : 1280 / THREA
   // launches this same kernel (taxi_launch), which keeps the hot loop free of mode branches.
 
   pdl_wait();   // the previous step's writes are complete and visible from here on
+  uint64_t ctr0 = ((uint64_t)P.rng.step_hi << 32) | P.rng.step_lo;
+  if constexpr (DEVCTR) ctr0 = *P.ctr_ptr;
   int4 s4[QPT], e4[QPT];
   uint32_t nd4[QPT], a4[QPT];
   float4 ret4[QPT];
@@ -529,9 +535,9 @@ __global__ void __launch_bounds__(THREADS, (STATS || QPT > 2) ? 1 : 1280 / THREA
 #pragma unroll
     for (int i = 0; i < 4 * QPT; ++i) cur = i == b ? keep_s[i] : cur;
 #if GPT_TAXI_FIX_INLINE_SINGLE
-    const uint32_t fresh = taxi_fix_inline<REPLAY>(P, alias, env, 0u, (uint32_t)cur, full);   // same sampler as the fused kernel
+    const uint32_t fresh = taxi_fix_inline<REPLAY>(P, alias, env, ctr0, 0u, (uint32_t)cur, full);   // same sampler as the fused kernel
 #else
-    const uint32_t fresh = taxi_fix<REPLAY>(P, alias, env, 0u, (uint32_t)cur, full);   // same sampler as the fused kernel
+    const uint32_t fresh = taxi_fix<REPLAY>(P, alias, env, ctr0, 0u, (uint32_t)cur, full);   // same sampler as the fused kernel
 #endif
     if (full) {
       P.elapsed[env] = 0;
@@ -772,6 +778,11 @@ int taxi_launch(gpt_env* env, const LaunchArgs& a) {
 #define GPT_TAXI_PICK(Q, T) (c.track_stats ? GPT_TAXI_PICK2(true, Q, T) : GPT_TAXI_PICK2(false, Q, T))
     K k;
     int qpt;
+    P.ctr_ptr = env->d_counter;
+    if (env->graph_mode && !replay && !c.track_stats) {  // graph mode: step counter in device memory
+      k = hansen ? (K)taxi_table_kernel<true, false, false, 2, 128, true> : (K)taxi_table_kernel<false, false, false, 2, 128, true>;
+      qpt = 2; threads = 128;
+    } else
     switch (env->taxi_shape) {  // measured on B200 at 2^22 envs: 2x128 18.9 us, 4x128 19.3 us, 1x256 20.3 us per step
       case 4128: k = GPT_TAXI_PICK(4, 128); qpt = 4; threads = 128; break;
       default: k = GPT_TAXI_PICK(2, 128); qpt = 2; threads = 128; break;
@@ -793,7 +804,7 @@ int taxi_launch(gpt_env* env, const LaunchArgs& a) {
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(taxi)");
   }
-  cudaError_t e = launch_pdl(kernel, dim3(grid), dim3(threads), smem, a.stream, args);
+  cudaError_t e = launch_pdl(kernel, dim3(grid), dim3(threads), smem, a.stream, args, !env->graph_mode);
   env->launches += 1;
   if (e != cudaSuccess) return cuda_fail(e, "taxi step kernel launch");
   if (table_reset) {

@@ -298,6 +298,13 @@ class DeviceVecEnv:
         """``step_many`` as one fused multi-step launch where the family supports it (Taxi) — on by default."""
         N.check(N.lib.gpt_set_fused_steps(self._h, int(bool(enable))))
 
+    def set_graph_mode(self, enable: bool = True):
+        """Make ``step()`` capturable into a CUDA graph (Taxi / ROOMS, Philox mode): the Philox step counter moves into
+        device memory and a one-thread tick kernel advances it after every step, so every replay of a captured graph
+        draws fresh random numbers.  Call it outside of stream capture; ``step_host`` is unavailable while it is on."""
+        with self._on_device():
+            N.check(N.lib.gpt_set_graph_mode(self._h, int(bool(enable)), self._stream()))
+
     @property
     def launch_count(self) -> int:
         return int(N.lib.gpt_launch_count(self._h))

@@ -84,6 +84,7 @@ SIGNATURES = {
     "gpt_step_dlpack": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "gpt_step_many": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_void_p]),
     "gpt_set_fused_steps": (C.c_int, [C.c_void_p, C.c_int]),
+    "gpt_set_graph_mode": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
     "gpt_step_host": (C.c_int, [C.c_void_p, C.POINTER(GptHostIO)]),
     "gpt_get_counter": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64)]),
     "gpt_set_counter": (C.c_int, [C.c_void_p, C.c_uint64]),

@@ -376,3 +376,46 @@ def test_fused_launch_ragged_sizes_and_stats(b):
     l0 = a.launch_count
     a.step_many(acts[:5])
     assert a.launch_count == l0 + 5
+
+
+@pytest.mark.parametrize("family", ["taxi", "rooms"])
+def test_cuda_graph_capture_and_replay(family):
+    """Graph mode: step() calls captured into a CUDA graph draw fresh random numbers on every replay (the Philox step
+    counter lives in device memory) — the replayed trajectory equals an eagerly stepped twin env, bit for bit."""
+    from gym_po.envs import RoomsEnv, TaxiVecEnv
+    b, K, n_act = 3000, 4, (5 if family == "taxi" else 8)
+    mk = (lambda: TaxiVecEnv(b, time_limit=9, hansen_obs=True, device=DEV, seed=3)) if family == "taxi" else \
+         (lambda: RoomsEnv(b, "8", obs_type="grid", obs_n=5, goal_xy=None, time_limit=9, device=DEV, seed=3))
+    env, twin = mk(), mk()
+    env.reset(seed=3); twin.reset(seed=3)
+    env.set_graph_mode(True)
+    static_a = torch.zeros((K, env.capacity), dtype=torch.int8, device=DEV)
+    first = env.step(static_a[0])                                      # one eager step in graph mode
+    rec = [[torch.zeros_like(x) for x in first[:4]] for _ in range(K)]
+    twin.step(static_a[0])
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        for i in range(K):
+            out = env.step(static_a[i])
+            for dst, src in zip(rec[i], out[:4]):
+                dst.copy_(src)
+    gen = torch.Generator(device=DEV).manual_seed(5)
+    for rep in range(6):
+        static_a.copy_(torch.randint(0, n_act, static_a.shape, dtype=torch.int8, device=DEV, generator=gen))
+        g.replay()
+        torch.cuda.synchronize()
+        for i in range(K):
+            o = twin.step(static_a[i])
+            for name, x, y in zip(("obs", "reward", "terminated", "truncated"), rec[i], o[:4]):
+                assert torch.equal(x, y), (name, rep, i)
+    sa, sb = env.get_state(), twin.get_state()
+    for k in sa:
+        assert torch.equal(sa[k], sb[k]), k
+    assert env.rng_counter == twin.rng_counter          # read back from the device
+    env.set_graph_mode(False)                            # and back to launch-parameter counters
+    a = torch.randint(0, n_act, (env.capacity,), dtype=torch.int8, device=DEV, generator=gen)
+    for x, y in zip(env.step(a)[:4], twin.step(a)[:4]):
+        assert torch.equal(x, y)
+    with pytest.raises(ValueError):
+        TaxiVecEnv(64, device=DEV, rng_mode="replay").set_graph_mode(True)
