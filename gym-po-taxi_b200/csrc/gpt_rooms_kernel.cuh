@@ -255,13 +255,14 @@ template <int GRID_N> struct RoomsShape<GPT_OBS_GRID, GRID_N> {
 
 // Rare path, deliberately out of line (one copy per kernel instead of one per unrolled env):
 // _reset_some (rooms.py:191-196) — new goal first (random-goal envs), then new agent cell.
-template <bool RGOAL, bool REPLAY>
-__device__ __forceinline__ uint32_t rooms_respawn_inline(const RoomsParams& P, const uint16_t* valid, int64_t env, uint32_t gcell, uint64_t ctr) {
+template <bool RGOAL, bool REPLAY, bool DEVCTR = false>
+__device__ __forceinline__ uint32_t rooms_respawn_inline(const RoomsParams& P, const uint16_t* valid, int64_t env, uint32_t gcell, uint32_t t, uint64_t ctr_dev = 0) {
   uint32_t cell;
   if (REPLAY) {
     if (RGOAL) gcell = (uint32_t)P.rp_reset_goal[env];
     cell = (uint32_t)P.rp_reset_agent[env];
   } else {
+    const uint64_t ctr = (DEVCTR ? ctr_dev : (((uint64_t)P.rng.step_hi << 32) | P.rng.step_lo)) + t;   // step index inside a fused launch
     const uint64_t ge = (uint64_t)(P.env_offset + env);
     const uint4 r = philox4x32_10(make_uint4((uint32_t)ge, (uint32_t)(ge >> 32), (uint32_t)ctr,
                                              ((uint32_t)(ctr >> 32) & 0x00FFFFFFu) ^ (1u << 24)), P.rng);
@@ -272,8 +273,8 @@ __device__ __forceinline__ uint32_t rooms_respawn_inline(const RoomsParams& P, c
 }
 // out-of-line copy for the single-step kernels
 template <bool RGOAL, bool REPLAY>
-__device__ __noinline__ uint32_t rooms_respawn(const RoomsParams& P, const uint16_t* valid, int64_t env, uint32_t gcell, uint64_t ctr) {
-  return rooms_respawn_inline<RGOAL, REPLAY>(P, valid, env, gcell, ctr);
+__device__ __noinline__ uint32_t rooms_respawn(const RoomsParams& P, const uint16_t* valid, int64_t env, uint32_t gcell, uint32_t t) {
+  return rooms_respawn_inline<RGOAL, REPLAY>(P, valid, env, gcell, t);
 }
 
 // resident CTAs per SM of the fused kernels; measured on B200 (2^22 envs, 8 steps per launch): hansen8 6 -> 331 G,
@@ -362,8 +363,8 @@ rooms_step_kernel(const __grid_constant__ RoomsParams P) {
   }
   const int32_t n_steps = MULTI ? P.n_steps : 1;
   // DEVCTR (graph mode): the step counter comes from device memory, so that a captured CUDA graph can be replayed
-  uint64_t ctr0 = ((uint64_t)P.rng.step_hi << 32) | P.rng.step_lo;
-  if constexpr (DEVCTR) ctr0 = *P.ctr_ptr;
+  uint64_t ctr_dev = 0;
+  if constexpr (DEVCTR) ctr_dev = *P.ctr_ptr;
   const size_t obs_row = OBS == GPT_OBS_GRID ? (size_t)(gn * gn)
                          : (OBS == GPT_OBS_VEC_MDP ? 2 : ((OBS == GPT_OBS_VEC_HANSEN || OBS == GPT_OBS_VEC_HANSEN_GOAL) ? (size_t)P.hansen_n : 4));
 #pragma unroll 1
@@ -376,7 +377,7 @@ rooms_step_kernel(const __grid_constant__ RoomsParams P) {
     if (more) a_next[j] = ld_stream(reinterpret_cast<const uint32_t*>(P.actions + (int64_t)(t + 1) * P.act_stride + base + j * kQuadStride));
   }
   const int64_t orow = MULTI ? (int64_t)t * P.out_stride : 0;
-  const uint64_t ctr = ctr0 + (uint32_t)t;   // Philox step counter of this step
+  const uint64_t ctr = (DEVCTR ? ctr_dev : (((uint64_t)P.rng.step_hi << 32) | P.rng.step_lo)) + (uint32_t)t;   // Philox step counter of this step
   const uint32_t ctr_lo = (uint32_t)ctr, ctr_hi = (uint32_t)(ctr >> 32) & 0x00FFFFFFu;
 #pragma unroll
   for (int j = 0; j < QPT; ++j) {
@@ -459,7 +460,7 @@ rooms_step_kernel(const __grid_constant__ RoomsParams P) {
 #pragma unroll
         for (int i = 0; i < 4; ++i) g = i == k ? goalv[i] : g;
         // fused launches inline it: a CALL would wait for the in-flight action prefetch
-        const uint32_t fresh = (MULTI || GPT_RESPAWN_INLINE_SINGLE) ? rooms_respawn_inline<RGOAL, REPLAY>(P, T.valid, q + k, g, ctr) : rooms_respawn<RGOAL, REPLAY>(P, T.valid, q + k, g, ctr);
+        const uint32_t fresh = (MULTI || DEVCTR || GPT_RESPAWN_INLINE_SINGLE) ? rooms_respawn_inline<RGOAL, REPLAY, DEVCTR>(P, T.valid, q + k, g, (uint32_t)t, ctr_dev) : rooms_respawn<RGOAL, REPLAY>(P, T.valid, q + k, g, (uint32_t)t);
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           if (i == k) {

@@ -242,14 +242,14 @@ struct TaxiMultiParams {
 
 // Rare branch, out of line (one copy per kernel): full reset (extended_taxi.py:344-352) or passenger respawn
 // (:354-364) -> new state id.  `t` = step index inside a fused launch.
-template <bool REPLAY>
-__device__ __forceinline__ uint32_t taxi_fix_inline(const TaxiParams& P, const uint2* alias, int64_t env, uint64_t ctr0, uint32_t t, uint32_t cur, bool full) {
+template <bool REPLAY, bool DEVCTR = false>
+__device__ __forceinline__ uint32_t taxi_fix_inline(const TaxiParams& P, const uint2* alias, int64_t env, uint32_t t, uint32_t cur, bool full, uint64_t ctr_dev = 0) {
   if (REPLAY) {
     if (full) return (uint32_t)P.rp_reset_state[env];
     const uint32_t cell = fdiv(cur, P.div_pd);
     return (cell * (uint32_t)(P.nlocs + 1) + (uint32_t)P.rp_new_p[env]) * (uint32_t)P.nlocs + (uint32_t)P.rp_new_d[env];
   }
-  const uint64_t ctr = ctr0 + t;   // Philox step counter of this step
+  const uint64_t ctr = (DEVCTR ? ctr_dev : (((uint64_t)P.rng.step_hi << 32) | P.rng.step_lo)) + t;   // Philox step counter of this step
   const uint64_t ge = (uint64_t)(P.env_offset + env);
   const uint4 rnd = philox4x32_10(make_uint4((uint32_t)ge, (uint32_t)(ge >> 32), (uint32_t)ctr, (uint32_t)(ctr >> 32) & 0x00FFFFFFu), P.rng);
   if (full) {  // the law of argmax(multinomial(ns, uniform over valid states)), sampled through its alias table
@@ -265,8 +265,8 @@ __device__ __forceinline__ uint32_t taxi_fix_inline(const TaxiParams& P, const u
 }
 // out-of-line copy for the single-step kernel (its registers are dead at the call site)
 template <bool REPLAY>
-__device__ __noinline__ uint32_t taxi_fix(const TaxiParams& P, const uint2* alias, int64_t env, uint64_t ctr0, uint32_t t, uint32_t cur, bool full) {
-  return taxi_fix_inline<REPLAY>(P, alias, env, ctr0, t, cur, full);
+__device__ __noinline__ uint32_t taxi_fix(const TaxiParams& P, const uint2* alias, int64_t env, uint32_t t, uint32_t cur, bool full) {
+  return taxi_fix_inline<REPLAY>(P, alias, env, t, cur, full);
 }
 
 #ifndef GPT_TAXI_FIX_INLINE_SINGLE
@@ -302,7 +302,6 @@ __global__ void __launch_bounds__(THREADS, STATS ? 1 : GPT_TAXI_MINB_MULTI) taxi
   const int64_t base = first + wtile * kEnvsPerWarp + lane * kQuad;
   if (base >= last) return;
   pdl_wait();   // the previous launch's writes are complete and visible from here on
-  const uint64_t ctr0 = ((uint64_t)P.rng.step_hi << 32) | P.rng.step_lo;
   uint32_t off[QPT][4], ndv[QPT][4], a4[QPT];   // off = state id << kRowShift
   int32_t ev[QPT][4];
   float ret[STATS ? QPT : 1][4];
@@ -396,7 +395,7 @@ __global__ void __launch_bounds__(THREADS, STATS ? 1 : GPT_TAXI_MINB_MULTI) taxi
         for (int i = 0; i < 4 * QPT; ++i) cur = i == idx ? off[i >> 2][i & 3] : cur;
         const int64_t env = base + j * kQuadStride + k;
         // inlined: a CALL here would wait for the in-flight action prefetch (ncu: 20 % of all stall samples)
-        const uint32_t fresh = taxi_fix_inline<REPLAY>(P, alias, env, ctr0, (uint32_t)t, cur >> kRowShift, full);
+        const uint32_t fresh = taxi_fix_inline<REPLAY>(P, alias, env, (uint32_t)t, cur >> kRowShift, full);
         P.obs[orow + env] = (int32_t)hobs[fresh];
 #pragma unroll
         for (int i = 0; i < 4 * QPT; ++i) {
@@ -446,8 +445,8 @@ __global__ void __launch_bounds__(THREADS, (STATS || QPT > 2) ? 1 : 1280 / THREA
   // launches this same kernel (taxi_launch), which keeps the hot loop free of mode branches.
 
   pdl_wait();   // the previous step's writes are complete and visible from here on
-  uint64_t ctr0 = ((uint64_t)P.rng.step_hi << 32) | P.rng.step_lo;
-  if constexpr (DEVCTR) ctr0 = *P.ctr_ptr;
+  uint64_t ctr_dev = 0;
+  if constexpr (DEVCTR) ctr_dev = *P.ctr_ptr;
   int4 s4[QPT], e4[QPT];
   uint32_t nd4[QPT], a4[QPT];
   float4 ret4[QPT];
@@ -535,9 +534,9 @@ __global__ void __launch_bounds__(THREADS, (STATS || QPT > 2) ? 1 : 1280 / THREA
 #pragma unroll
     for (int i = 0; i < 4 * QPT; ++i) cur = i == b ? keep_s[i] : cur;
 #if GPT_TAXI_FIX_INLINE_SINGLE
-    const uint32_t fresh = taxi_fix_inline<REPLAY>(P, alias, env, ctr0, 0u, (uint32_t)cur, full);   // same sampler as the fused kernel
+    const uint32_t fresh = taxi_fix_inline<REPLAY, DEVCTR>(P, alias, env, 0u, (uint32_t)cur, full, ctr_dev);   // same sampler as the fused kernel
 #else
-    const uint32_t fresh = taxi_fix<REPLAY>(P, alias, env, ctr0, 0u, (uint32_t)cur, full);   // same sampler as the fused kernel
+    const uint32_t fresh = taxi_fix<REPLAY>(P, alias, env, 0u, (uint32_t)cur, full);   // same sampler as the fused kernel
 #endif
     if (full) {
       P.elapsed[env] = 0;
