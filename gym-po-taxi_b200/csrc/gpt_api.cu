@@ -106,7 +106,7 @@ __global__ void tick_kernel(uint64_t* counter, uint64_t n) { *counter += n; }
 static bool graph_mode_family(const gpt_env* env) {
   const gpt_config& c = env->cfg;
   if (c.rng_mode != GPT_RNG_PHILOX || c.track_stats) return false;
-  return (c.family == GPT_FAMILY_TAXI && env->taxi_use_table) || c.family == GPT_FAMILY_ROOMS;
+  return c.family != GPT_FAMILY_TAXI || env->taxi_use_table;   // every family; Taxi only with the table kernel
 }
 
 static int tick(gpt_env* env, uint64_t n, cudaStream_t stream) {
@@ -422,7 +422,7 @@ int gpt_set_graph_mode(gpt_env* env, int enable, void* stream) {
   if (e != cudaSuccess) return cuda_fail(e, "cudaSetDevice");
   if (enable) {
     if (!graph_mode_family(env))
-      return fail(GPT_E_ARG, "gpt_set_graph_mode: supported for Taxi (table kernel) and ROOMS in Philox mode without track_stats");
+      return fail(GPT_E_ARG, "gpt_set_graph_mode: needs Philox mode without track_stats (Taxi: a map small enough for the table kernel)");
     if (!env->d_counter) {
       e = cudaMalloc((void**)&env->d_counter, sizeof(uint64_t));
       if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc(step counter)");

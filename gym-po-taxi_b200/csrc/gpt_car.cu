@@ -33,11 +33,12 @@ struct CarParams {
   int32_t first_tile, n_tiles, time_limit, n_actions;
   double priest_lo[2], priest_hi[2];   // [priest at -0.5, priest at +0.5]: priests -/+ PRIEST_THRESHOLD in float64
   RngKey rng;
+  const uint64_t* ctr_ptr;   // graph mode (DEVCTR kernels): device-resident Philox step counter, else unused
 };
 
 template <typename A> __device__ __forceinline__ A car_clip(A v, A lo, A hi) { return fmin(fmax(v, lo), hi); }
 
-template <typename A, int KIND, bool REPLAY>
+template <typename A, int KIND, bool REPLAY, bool DEVCTR = false>
 __global__ void __launch_bounds__(128) car_step_kernel(const __grid_constant__ CarParams P) {
   pdl_launch_dependents();
   const int64_t first = (int64_t)P.first_tile * kTileEnvs, last = first + (int64_t)P.n_tiles * kTileEnvs;
@@ -95,7 +96,9 @@ __global__ void __launch_bounds__(128) car_step_kernel(const __grid_constant__ C
         hv = P.rp_heaven[env] > 0;
         pr = P.rp_priest[env] > 0;
       } else {
-        const uint4 r = env_random(P.rng, (uint64_t)(P.env_offset + env), 0u);
+        uint64_t ctr_dev = 0;   // graph mode: step counter from device memory (rare path only)
+        if constexpr (DEVCTR) ctr_dev = *P.ctr_ptr;
+        const uint4 r = rnd_block<DEVCTR>(P.rng, ctr_dev, (uint64_t)(P.env_offset + env), 0u);
         const double u = (double)(((uint64_t)r.x << 21) ^ (uint64_t)(r.y >> 11)) * (1.0 / 9007199254740992.0);
         p0 = -0.2 + 0.4 * u;          // numpy uniform: low + (high - low) * random()
         hv = r.z >> 31;
@@ -203,8 +206,12 @@ int car_launch(gpt_env* env, const LaunchArgs& a) {
   if (kind == kCarF32) k = replay ? (K)car_step_kernel<float, kCarF32, true> : (K)car_step_kernel<float, kCarF32, false>;
   else if (kind == kCarF64) k = replay ? (K)car_step_kernel<double, kCarF64, true> : (K)car_step_kernel<double, kCarF64, false>;
   else k = replay ? (K)car_step_kernel<double, kCarDiscrete, true> : (K)car_step_kernel<double, kCarDiscrete, false>;
+  P.ctr_ptr = env->d_counter;
+  if (env->graph_mode && !replay)   // graph mode: step counter in device memory
+    k = kind == kCarF32 ? (K)car_step_kernel<float, kCarF32, false, true>
+                        : (kind == kCarF64 ? (K)car_step_kernel<double, kCarF64, false, true> : (K)car_step_kernel<double, kCarDiscrete, false, true>);
   void* args[] = {(void*)&P};
-  cudaError_t e = launch_pdl((const void*)k, dim3(nblocks), dim3(threads), 0, a.stream, args);
+  cudaError_t e = launch_pdl((const void*)k, dim3(nblocks), dim3(threads), 0, a.stream, args, !env->graph_mode);
   env->launches += 1;
   if (e != cudaSuccess) return cuda_fail(e, "car_step_kernel launch");
   if (reset) {

@@ -69,6 +69,15 @@ __device__ __forceinline__ uint4 env_random(const RngKey& k, uint64_t env, uint3
   return philox4x32_10(make_uint4((uint32_t)env, (uint32_t)(env >> 32), k.step_lo, k.step_hi ^ (stream << 24)), k);
 }
 
+// Graph mode (DEVCTR kernel instantiations): the step counter comes from device memory instead of the launch parameters.
+template <bool DEVCTR>
+__device__ __forceinline__ uint4 rnd_block(const RngKey& k, uint64_t ctr_dev, uint64_t id, uint32_t stream) {
+  if constexpr (DEVCTR)
+    return philox4x32_10(make_uint4((uint32_t)id, (uint32_t)(id >> 32), (uint32_t)ctr_dev, ((uint32_t)(ctr_dev >> 32) & 0x00FFFFFFu) ^ (stream << 24)), k);
+  else
+    return env_random(k, id, stream);
+}
+
 // unbiased-enough bounded integer: floor(u * n / 2^32); bias <= n * 2^-32
 __device__ __forceinline__ uint32_t bounded(uint32_t u, uint32_t n) { return __umulhi(u, n); }
 

@@ -152,14 +152,16 @@ int crooms_launch(gpt_env* env, const LaunchArgs& a) {
   if (nblocks <= 0) return GPT_OK;
   size_t smem = env->blob_bytes;
   if (grid) smem = P.stage_off + (size_t)warps * kQuadStride * P.grid_n * P.grid_n;
-  void* k = c.c_state_f32 ? crooms_pick_f32(c.rooms_obs_kind, replay) : crooms_pick_obs<double>(c.rooms_obs_kind, replay);
+  const bool devctr = env->graph_mode && !replay;   // graph mode: step counter in device memory
+  P.ctr_ptr = env->d_counter;
+  void* k = c.c_state_f32 ? crooms_pick_f32(c.rooms_obs_kind, replay, devctr) : crooms_pick_obs<double>(c.rooms_obs_kind, replay, devctr);
   if (!k) return fail(GPT_E_ARG, "crooms: no kernel for this obs kind");
   if (smem > 40 * 1024) {  // static + dynamic shared memory above 48 KB needs the opt-in
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(crooms)");
   }
   void* args[] = {(void*)&P};
-  cudaError_t e = launch_pdl(k, dim3(nblocks), dim3(threads), smem, a.stream, args);
+  cudaError_t e = launch_pdl(k, dim3(nblocks), dim3(threads), smem, a.stream, args, !env->graph_mode);
   env->launches += 1;
   if (e != cudaSuccess) return cuda_fail(e, "crooms_step_kernel launch");
   return GPT_OK;
@@ -226,9 +228,11 @@ int tag_launch(gpt_env* env, const LaunchArgs& a) {
   const int64_t quads = (int64_t)a.n_tiles * (kTileEnvs / kQuad);
   const int nblocks = (int)((quads + threads - 1) / threads);
   if (nblocks <= 0) return GPT_OK;
-  void* k = c.c_state_f32 ? tag_pick_f32(replay) : tag_pick_rr<double>(replay);
+  const bool devctr = env->graph_mode && !replay;
+  P.ctr_ptr = env->d_counter;
+  void* k = c.c_state_f32 ? tag_pick_f32(replay, devctr) : tag_pick_rr<double>(replay, devctr);
   void* args[] = {(void*)&P};
-  cudaError_t e = launch_pdl(k, dim3(nblocks), dim3(threads), 0, a.stream, args);
+  cudaError_t e = launch_pdl(k, dim3(nblocks), dim3(threads), 0, a.stream, args, !env->graph_mode);
   env->launches += 1;
   if (e != cudaSuccess) return cuda_fail(e, "tag_step_kernel launch");
   return GPT_OK;

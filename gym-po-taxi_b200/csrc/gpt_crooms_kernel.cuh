@@ -102,6 +102,7 @@ struct CRoomsParams {
   float r_step, r_wall, r_goal;
   float f_cell, f_inv_cell, f_half, f_std, f_pow, f_max_y, f_max_x, f_thr2, f_goal_y, f_goal_x;   // float32 fast mode
   RngKey rng;
+  const uint64_t* ctr_ptr;   // graph mode (DEVCTR kernels): device-resident Philox step counter, else unused
 };
 
 // two standard normals from 4 x 32 random bits (Box-Muller on 53-bit uniforms)
@@ -136,14 +137,14 @@ __device__ __forceinline__ float2 normal_pair_f(uint32_t a, uint32_t b) {
 template <typename R> __device__ __forceinline__ R clipd(R v, R lo, R hi) { return fmin(fmax(v, lo), hi); }
 
 // _reset_some (crooms.py:268-274): goal cell first (random-goal envs), then agent cell.  Rare, out of line.
-template <bool REPLAY>
-__device__ GPT_CONT_RESPAWN_ATTR uint32_t crooms_respawn(const CRoomsParams& P, const uint16_t* valid, int64_t env) {
+template <bool REPLAY, bool DEVCTR = false>
+__device__ GPT_CONT_RESPAWN_ATTR uint32_t crooms_respawn(const CRoomsParams& P, const uint16_t* valid, int64_t env, uint64_t ctr_dev = 0) {
   uint32_t ac, gc = 0;
   if (REPLAY) {
     if (P.rgoal) gc = (uint32_t)P.rp_reset_goal[env];
     ac = (uint32_t)P.rp_reset_agent[env];
   } else {
-    const uint4 r = env_random(P.rng, (uint64_t)(P.env_offset + env), 1u);
+    const uint4 r = rnd_block<DEVCTR>(P.rng, ctr_dev, (uint64_t)(P.env_offset + env), 1u);
     if (P.rgoal) gc = valid[bounded(r.y, (uint32_t)P.n_valid)];
     ac = valid[bounded(r.x, (uint32_t)P.n_valid)];
   }
@@ -153,7 +154,7 @@ __device__ GPT_CONT_RESPAWN_ATTR uint32_t crooms_respawn(const CRoomsParams& P, 
 #ifndef GPT_CROOMS_MINB
 #define GPT_CROOMS_MINB 7   // measured on B200 (2^22 envs, f32): 1 -> 83 G, 6 -> 106 G, 7 -> 113.5 G, 8 -> 110.6 G env-steps/s
 #endif
-template <typename R, int OBS, bool REPLAY>
+template <typename R, int OBS, bool REPLAY, bool DEVCTR = false>
 __global__ void __launch_bounds__(128, GPT_CROOMS_MINB) crooms_step_kernel(const __grid_constant__ CRoomsParams P) {
   using V2 = typename RealTraits<R>::V2;
   constexpr bool kFast = sizeof(R) == 4;   // float32 fast mode: reciprocal multiply, squared distances, MUFU noise
@@ -179,6 +180,8 @@ __global__ void __launch_bounds__(128, GPT_CROOMS_MINB) crooms_step_kernel(const
   auto cell_of = [&](R v) -> int { return kFast ? (int)floor(v * inv_cell) : (int)floor(v / cell_size); };
 
   pdl_wait();
+  uint64_t ctr_dev = 0;   // graph mode: step counter from device memory
+  if constexpr (DEVCTR) ctr_dev = *P.ctr_ptr;
   V2 pos[4], gpos[4], vel[4], push[4];
   int32_t ev[4] = {0, 0, 0, 0};
   uint32_t abytes = 0;
@@ -223,7 +226,8 @@ __global__ void __launch_bounds__(128, GPT_CROOMS_MINB) crooms_step_kernel(const
     uint4 slipq = make_uint4(0, 0, 0, 0);
     if (!REPLAY && P.act_kind == kActI8) {  // one Philox block feeds the slip draws of the quad
       const uint64_t gq = (uint64_t)(P.env_offset + q) >> 2;
-      slipq = philox4x32_10(make_uint4((uint32_t)gq, (uint32_t)(gq >> 32), P.rng.step_lo, P.rng.step_hi ^ (3u << 24)), P.rng);
+      if constexpr (DEVCTR) slipq = rnd_block<true>(P.rng, ctr_dev, gq, 3u);
+      else slipq = philox4x32_10(make_uint4((uint32_t)gq, (uint32_t)(gq >> 32), P.rng.step_lo, P.rng.step_hi ^ (3u << 24)), P.rng);
     }
     const uint32_t slipv[4] = {slipq.x, slipq.y, slipq.z, slipq.w};
     // float32 fast mode: 3 Philox blocks per quad = 3 words per env: 24 + 24 bits for the action-noise pair, 16 + 16
@@ -233,7 +237,9 @@ __global__ void __launch_bounds__(128, GPT_CROOMS_MINB) crooms_step_kernel(const
       const uint64_t gq = (uint64_t)(P.env_offset + q) >> 2;
 #pragma unroll
       for (int j = 0; j < 3; ++j) {
-        const uint4 b = philox4x32_10(make_uint4((uint32_t)gq, (uint32_t)(gq >> 32), P.rng.step_lo, P.rng.step_hi ^ ((uint32_t)(4 + j) << 24)), P.rng);
+        uint4 b;
+        if constexpr (DEVCTR) b = rnd_block<true>(P.rng, ctr_dev, gq, (uint32_t)(4 + j));
+        else b = philox4x32_10(make_uint4((uint32_t)gq, (uint32_t)(gq >> 32), P.rng.step_lo, P.rng.step_hi ^ ((uint32_t)(4 + j) << 24)), P.rng);
         qw[4 * j] = b.x; qw[4 * j + 1] = b.y; qw[4 * j + 2] = b.z; qw[4 * j + 3] = b.w;
       }
     }
@@ -244,7 +250,7 @@ __global__ void __launch_bounds__(128, GPT_CROOMS_MINB) crooms_step_kernel(const
       // ---- noisy action (crooms.py:175-178 / :188-196) ----
       uint4 r0 = make_uint4(0, 0, 0, 0);
       if constexpr (kFast && !REPLAY) r0 = make_uint4(qw[3 * k], qw[3 * k + 1], qw[3 * k + 2] & 0xFFFF0000u, qw[3 * k + 2] << 16);
-      else if (!REPLAY) r0 = env_random(P.rng, (uint64_t)(P.env_offset + env), 0u);
+      else if (!REPLAY) r0 = rnd_block<DEVCTR>(P.rng, ctr_dev, (uint64_t)(P.env_offset + env), 0u);
       if (P.act_kind == kActI8) {
         uint32_t a = (abytes >> (8 * k)) & 0xFFu;
         a = a < n ? a : n - 1;
@@ -314,7 +320,7 @@ __global__ void __launch_bounds__(128, GPT_CROOMS_MINB) crooms_step_kernel(const
             const double2 zz = P.rp_resample[env];   // normal(scale=0.5)
             z = RealTraits<R>::make((R)zz.x, (R)zz.y);
           } else {
-            const double2 zz = normal_pair(env_random(P.rng, (uint64_t)(P.env_offset + env), 2u));
+            const double2 zz = normal_pair(rnd_block<DEVCTR>(P.rng, ctr_dev, (uint64_t)(P.env_offset + env), 2u));
             z = RealTraits<R>::make((R)zz.x * (R)0.5, (R)zz.y * (R)0.5);
           }
           pos[k].x = clipd<R>(cy + z.x, cy - half, cy + half - (R)1e-8);
@@ -336,7 +342,7 @@ __global__ void __launch_bounds__(128, GPT_CROOMS_MINB) crooms_step_kernel(const
 #pragma unroll 1
     for (uint32_t m = again; m; m &= m - 1) {
       const int k = __ffs(m) - 1;
-      const uint32_t fresh = crooms_respawn<REPLAY>(P, T.valid, q + k);
+      const uint32_t fresh = crooms_respawn<REPLAY, DEVCTR>(P, T.valid, q + k, ctr_dev);
       const uint32_t ac = fresh & 0xFFFFu, gc = fresh >> 16;
       const uint32_t ay = fdiv(ac, P.div_w), gy = fdiv(gc, P.div_w);
       const V2 np = RealTraits<R>::make((R)ay + (R)0.5, (R)(ac - ay * P.w) + (R)0.5);
@@ -403,13 +409,14 @@ struct TagParams {
   int32_t first_tile, n_tiles, mode, time_limit, act_kind;
   double action_std, action_power;
   RngKey rng;
+  const uint64_t* ctr_ptr;   // graph mode (DEVCTR kernels): device-resident Philox step counter, else unused
 };
 
 
 // reset_model (ant_tag.py:88-103): agent uniform in the cage, target redrawn while within the minimum distance.
 // Rare, out of line; returns (agent, target) through registers.
-template <typename R, bool REPLAY>
-__device__ GPT_CONT_RESPAWN_ATTR void tag_respawn(const TagParams& P, int64_t env, typename RealTraits<R>::V2* pos_out, typename RealTraits<R>::V2* tgt_out) {
+template <typename R, bool REPLAY, bool DEVCTR = false>
+__device__ GPT_CONT_RESPAWN_ATTR void tag_respawn(const TagParams& P, int64_t env, typename RealTraits<R>::V2* pos_out, typename RealTraits<R>::V2* tgt_out, uint64_t ctr_dev = 0) {
   using V2 = typename RealTraits<R>::V2;
   constexpr R kMinSpawn = (R)5.0;
   V2 pos, tgt;
@@ -418,13 +425,13 @@ __device__ GPT_CONT_RESPAWN_ATTR void tag_respawn(const TagParams& P, int64_t en
     pos = RealTraits<R>::make((R)sa.x, (R)sa.y);
     tgt = RealTraits<R>::make((R)st.x, (R)st.y);
   } else {
-    const uint4 r = env_random(P.rng, (uint64_t)(P.env_offset + env), 1u);
+    const uint4 r = rnd_block<DEVCTR>(P.rng, ctr_dev, (uint64_t)(P.env_offset + env), 1u);
     const double s = 2.0 * 4.5 / 4294967296.0;
     pos = RealTraits<R>::make((R)((double)r.x * s - 4.5), (R)((double)r.y * s - 4.5));
     tgt = pos;
     uint32_t attempt = 0;
     do {
-      const uint4 t = env_random(P.rng, (uint64_t)(P.env_offset + env), 16u + (attempt >> 1));
+      const uint4 t = rnd_block<DEVCTR>(P.rng, ctr_dev, (uint64_t)(P.env_offset + env), 16u + (attempt >> 1));
       tgt = (attempt & 1u) ? RealTraits<R>::make((R)((double)t.z * s - 4.5), (R)((double)t.w * s - 4.5))
                            : RealTraits<R>::make((R)((double)t.x * s - 4.5), (R)((double)t.y * s - 4.5));
       ++attempt;
@@ -439,7 +446,7 @@ __device__ GPT_CONT_RESPAWN_ATTR void tag_respawn(const TagParams& P, int64_t en
 #ifndef GPT_TAG_MINB
 #define GPT_TAG_MINB 1
 #endif
-template <typename R, bool REPLAY>
+template <typename R, bool REPLAY, bool DEVCTR = false>
 __global__ void __launch_bounds__(128, GPT_TAG_MINB) tag_step_kernel(const __grid_constant__ TagParams P) {
   using V2 = typename RealTraits<R>::V2;
   constexpr bool kFast = sizeof(R) == 4;
@@ -451,6 +458,8 @@ __global__ void __launch_bounds__(128, GPT_TAG_MINB) tag_step_kernel(const __gri
   if (q >= last) return;
   const bool reset_all = P.mode == kModeReset;
   pdl_wait();
+  uint64_t ctr_dev = 0;   // graph mode: step counter from device memory
+  if constexpr (DEVCTR) ctr_dev = *P.ctr_ptr;
   float rv[4] = {0.f, 0.f, 0.f, 0.f};
   uint32_t tw = 0, trw = 0, again = reset_all ? 0xFu : 0u;
   int32_t ev[4] = {0, 0, 0, 0};
@@ -470,7 +479,9 @@ __global__ void __launch_bounds__(128, GPT_TAG_MINB) tag_step_kernel(const __gri
       const uint64_t gq = (uint64_t)(P.env_offset + q) >> 2;
 #pragma unroll
       for (int j = 0; j < 2; ++j) {
-        const uint4 b = philox4x32_10(make_uint4((uint32_t)gq, (uint32_t)(gq >> 32), P.rng.step_lo, P.rng.step_hi ^ ((uint32_t)(4 + j) << 24)), P.rng);
+        uint4 b;
+        if constexpr (DEVCTR) b = rnd_block<true>(P.rng, ctr_dev, gq, (uint32_t)(4 + j));
+        else b = philox4x32_10(make_uint4((uint32_t)gq, (uint32_t)(gq >> 32), P.rng.step_lo, P.rng.step_hi ^ ((uint32_t)(4 + j) << 24)), P.rng);
         qw[4 * j] = b.x; qw[4 * j + 1] = b.y; qw[4 * j + 2] = b.z; qw[4 * j + 3] = b.w;
       }
     }
@@ -480,7 +491,7 @@ __global__ void __launch_bounds__(128, GPT_TAG_MINB) tag_step_kernel(const __gri
       ev[k] += 1;
       uint4 r0 = make_uint4(0, 0, 0, 0);
       if constexpr (kFast && !REPLAY) r0 = make_uint4(qw[2 * k], qw[2 * k + 1], qw[2 * k] << 30, 0u);
-      else if (!REPLAY) r0 = env_random(P.rng, (uint64_t)(P.env_offset + env), 0u);
+      else if (!REPLAY) r0 = rnd_block<DEVCTR>(P.rng, ctr_dev, (uint64_t)(P.env_offset + env), 0u);
       V2 z;
       uint32_t choice;
       if constexpr (REPLAY) {
@@ -494,7 +505,7 @@ __global__ void __launch_bounds__(128, GPT_TAG_MINB) tag_step_kernel(const __gri
       } else {
         const double2 zz = normal_pair(r0);
         z = RealTraits<R>::make((R)zz.x * a_std, (R)zz.y * a_std);
-        choice = env_random(P.rng, (uint64_t)(P.env_offset + env), 3u).x >> 30;
+        choice = rnd_block<DEVCTR>(P.rng, ctr_dev, (uint64_t)(P.env_offset + env), 3u).x >> 30;
       }
       push[k].x = (push[k].x + z.x) * a_pow;
       push[k].y = (push[k].y + z.y) * a_pow;
@@ -532,7 +543,7 @@ __global__ void __launch_bounds__(128, GPT_TAG_MINB) tag_step_kernel(const __gri
     for (uint32_t m = again; m; m &= m - 1) {
       const int k = __ffs(m) - 1;
       V2 np, nt;
-      tag_respawn<R, REPLAY>(P, q + k, &np, &nt);
+      tag_respawn<R, REPLAY, DEVCTR>(P, q + k, &np, &nt, ctr_dev);
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         if (i == k) {
@@ -563,32 +574,34 @@ __global__ void __launch_bounds__(128, GPT_TAG_MINB) tag_step_kernel(const __gri
 // Instantiations: the float64 kernels (bit-exact parity with numpy) live in gpt_crooms.cu, compiled with -fmad=false;
 // the float32 fast-mode kernels live in gpt_crooms_f32.cu, compiled with FMA contraction enabled.
 template <typename R, int OBS>
-static void* crooms_pick_rr(bool replay) {
+static void* crooms_pick_rr(bool replay, bool devctr) {
   using K = void (*)(const CRoomsParams);
+  if (devctr) return replay ? nullptr : (void*)(K)crooms_step_kernel<R, OBS, false, true>;   // graph mode (Philox)
   return replay ? (void*)(K)crooms_step_kernel<R, OBS, true> : (void*)(K)crooms_step_kernel<R, OBS, false>;
 }
 template <typename R>
-static void* crooms_pick_obs(int obs, bool replay) {
+static void* crooms_pick_obs(int obs, bool replay, bool devctr = false) {
   switch (obs) {
-    case GPT_OBS_ROOM: return crooms_pick_rr<R, GPT_OBS_ROOM>(replay);
-    case GPT_OBS_ROOM_GOAL: return crooms_pick_rr<R, GPT_OBS_ROOM_GOAL>(replay);
-    case GPT_OBS_MDP: return crooms_pick_rr<R, GPT_OBS_MDP>(replay);
-    case GPT_OBS_MDP_GOAL: return crooms_pick_rr<R, GPT_OBS_MDP_GOAL>(replay);
-    case GPT_OBS_VEC_MDP: return crooms_pick_rr<R, GPT_OBS_VEC_MDP>(replay);
-    case GPT_OBS_VEC_MDP_GOAL: return crooms_pick_rr<R, GPT_OBS_VEC_MDP_GOAL>(replay);
-    case GPT_OBS_HANSEN: return crooms_pick_rr<R, GPT_OBS_HANSEN>(replay);
-    case GPT_OBS_VEC_HANSEN: return crooms_pick_rr<R, GPT_OBS_VEC_HANSEN>(replay);
-    case GPT_OBS_VEC_HANSEN_GOAL: return crooms_pick_rr<R, GPT_OBS_VEC_HANSEN_GOAL>(replay);
-    case GPT_OBS_GRID: return crooms_pick_rr<R, GPT_OBS_GRID>(replay);
+    case GPT_OBS_ROOM: return crooms_pick_rr<R, GPT_OBS_ROOM>(replay, devctr);
+    case GPT_OBS_ROOM_GOAL: return crooms_pick_rr<R, GPT_OBS_ROOM_GOAL>(replay, devctr);
+    case GPT_OBS_MDP: return crooms_pick_rr<R, GPT_OBS_MDP>(replay, devctr);
+    case GPT_OBS_MDP_GOAL: return crooms_pick_rr<R, GPT_OBS_MDP_GOAL>(replay, devctr);
+    case GPT_OBS_VEC_MDP: return crooms_pick_rr<R, GPT_OBS_VEC_MDP>(replay, devctr);
+    case GPT_OBS_VEC_MDP_GOAL: return crooms_pick_rr<R, GPT_OBS_VEC_MDP_GOAL>(replay, devctr);
+    case GPT_OBS_HANSEN: return crooms_pick_rr<R, GPT_OBS_HANSEN>(replay, devctr);
+    case GPT_OBS_VEC_HANSEN: return crooms_pick_rr<R, GPT_OBS_VEC_HANSEN>(replay, devctr);
+    case GPT_OBS_VEC_HANSEN_GOAL: return crooms_pick_rr<R, GPT_OBS_VEC_HANSEN_GOAL>(replay, devctr);
+    case GPT_OBS_GRID: return crooms_pick_rr<R, GPT_OBS_GRID>(replay, devctr);
   }
   return nullptr;
 }
 template <typename R>
-static void* tag_pick_rr(bool replay) {
+static void* tag_pick_rr(bool replay, bool devctr = false) {
   using K = void (*)(const TagParams);
+  if (devctr) return replay ? nullptr : (void*)(K)tag_step_kernel<R, false, true>;   // graph mode (Philox)
   return replay ? (void*)(K)tag_step_kernel<R, true> : (void*)(K)tag_step_kernel<R, false>;
 }
-void* crooms_pick_f32(int obs, bool replay);   // gpt_crooms_f32.cu
-void* tag_pick_f32(bool replay);
+void* crooms_pick_f32(int obs, bool replay, bool devctr);   // gpt_crooms_f32.cu
+void* tag_pick_f32(bool replay, bool devctr);
 
 }  // namespace gpt

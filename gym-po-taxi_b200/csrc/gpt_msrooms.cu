@@ -102,19 +102,20 @@ struct MsParams {
   int64_t act_stride;   // bytes between consecutive steps' action rows (= capacity)
   int64_t out_stride;   // rows between consecutive steps' outputs (0 = overwrite in place)
   RngKey rng;
+  const uint64_t* ctr_ptr;   // graph mode (DEVCTR kernels): device-resident Philox step counter, else unused
 };
 
 constexpr int kMsThreads = 128, kMsQpt = 2;
 
 // _reset_some (msrooms.py:385-390): goal first (random-goal envs), then agent.  Rare, out of line.
-template <bool RGOAL, bool REPLAY>
-__device__ __forceinline__ uint32_t ms_respawn_inline(const MsParams& P, const uint16_t* avalid, const uint16_t* gvalid, int64_t env, uint32_t gcell, uint32_t t) {
+template <bool RGOAL, bool REPLAY, bool DEVCTR = false>
+__device__ __forceinline__ uint32_t ms_respawn_inline(const MsParams& P, const uint16_t* avalid, const uint16_t* gvalid, int64_t env, uint32_t gcell, uint32_t t, uint64_t ctr_dev = 0) {
   uint32_t cell;
   if (REPLAY) {
     if (RGOAL) gcell = (uint32_t)P.rp_reset_goal[env];
     cell = (uint32_t)P.rp_reset_agent[env];
   } else {
-    const uint64_t ctr = (((uint64_t)P.rng.step_hi << 32) | P.rng.step_lo) + t;   // step index inside a fused launch
+    const uint64_t ctr = (DEVCTR ? ctr_dev : (((uint64_t)P.rng.step_hi << 32) | P.rng.step_lo)) + t;   // step index inside a fused launch
     const uint64_t ge = (uint64_t)(P.env_offset + env);
     const uint4 r = philox4x32_10(make_uint4((uint32_t)ge, (uint32_t)(ge >> 32), (uint32_t)ctr,
                                              ((uint32_t)(ctr >> 32) & 0x00FFFFFFu) ^ (1u << 24)), P.rng);
@@ -151,7 +152,7 @@ __device__ __forceinline__ uint32_t quad_obs_word(const uint64_t (&e)[4], int w)
 #ifndef GPT_MS_MINB_SINGLE
 #define GPT_MS_MINB_SINGLE 7
 #endif
-template <int OB, bool RGOAL, bool MERGED, bool REPLAY, bool MULTI = false>
+template <int OB, bool RGOAL, bool MERGED, bool REPLAY, bool MULTI = false, bool DEVCTR = false>
 __global__ void __launch_bounds__(kMsThreads, MULTI ? GPT_MS_MINB_MULTI : GPT_MS_MINB_SINGLE) msrooms_step_kernel(const __grid_constant__ MsParams P) {
   static_assert(!MULTI || !REPLAY, "fused launches need Philox mode");
   constexpr int kEnvsPerWarp = kWarp * kQuad * kMsQpt;
@@ -207,6 +208,8 @@ __global__ void __launch_bounds__(kMsThreads, MULTI ? GPT_MS_MINB_MULTI : GPT_MS
     evq[j][0] = e4[j].x; evq[j][1] = e4[j].y; evq[j][2] = e4[j].z; evq[j][3] = e4[j].w;
   }
   const int32_t n_steps = MULTI ? P.n_steps : 1;
+  uint64_t ctr_dev = 0;   // graph mode: step counter from device memory
+  if constexpr (DEVCTR) ctr_dev = *P.ctr_ptr;
 #pragma unroll 1
   for (int32_t t = 0; t < n_steps; ++t) {
   uint32_t a_next[kMsQpt];
@@ -217,7 +220,7 @@ __global__ void __launch_bounds__(kMsThreads, MULTI ? GPT_MS_MINB_MULTI : GPT_MS
     if (more) a_next[j] = ld_stream(reinterpret_cast<const uint32_t*>(P.actions + (int64_t)(t + 1) * P.act_stride + base + j * kQuadStride));
   }
   const int64_t orow = MULTI ? (int64_t)t * P.out_stride : 0;
-  const uint64_t ctr = (((uint64_t)P.rng.step_hi << 32) | P.rng.step_lo) + (uint32_t)t;
+  const uint64_t ctr = (DEVCTR ? ctr_dev : (((uint64_t)P.rng.step_hi << 32) | P.rng.step_lo)) + (uint32_t)t;
   const uint32_t ctr_lo = (uint32_t)ctr, ctr_hi = (uint32_t)(ctr >> 32) & 0x00FFFFFFu;
 #pragma unroll
   for (int j = 0; j < kMsQpt; ++j) {
@@ -281,7 +284,7 @@ __global__ void __launch_bounds__(kMsThreads, MULTI ? GPT_MS_MINB_MULTI : GPT_MS
 #pragma unroll
         for (int i = 0; i < 4; ++i) g = i == k ? goalv[i] : g;
         // fused launches inline it: a CALL would wait for the in-flight action prefetch
-        const uint32_t fresh = (MULTI || GPT_RESPAWN_INLINE_SINGLE) ? ms_respawn_inline<RGOAL, REPLAY>(P, avalid, gvalid, q + k, g, (uint32_t)t) : ms_respawn<RGOAL, REPLAY>(P, avalid, gvalid, q + k, g, (uint32_t)t);
+        const uint32_t fresh = (MULTI || DEVCTR || GPT_RESPAWN_INLINE_SINGLE) ? ms_respawn_inline<RGOAL, REPLAY, DEVCTR>(P, avalid, gvalid, q + k, g, (uint32_t)t, ctr_dev) : ms_respawn<RGOAL, REPLAY>(P, avalid, gvalid, q + k, g, (uint32_t)t);
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           if (i == k) {
@@ -502,9 +505,15 @@ int msrooms_create(gpt_env* env, const gpt_config* c) {
 }
 
 template <int OB>
-static void* ms_pick(bool rgoal, bool merged, bool replay, bool multi) {
+static void* ms_pick(bool rgoal, bool merged, bool replay, bool multi, bool devctr) {
   using K = void (*)(const MsParams);
   K k;
+  if (devctr) {  // graph mode: single step, Philox, step counter in device memory
+    if (rgoal) k = (K)msrooms_step_kernel<OB, true, false, false, false, true>;
+    else if (merged && OB == 4) k = (K)msrooms_step_kernel<4, false, true, false, false, true>;
+    else k = (K)msrooms_step_kernel<OB, false, false, false, false, true>;
+    return (void*)k;
+  }
   if (multi) {  // Philox mode only
     if (rgoal) k = (K)msrooms_step_kernel<OB, true, false, false, true>;
     else if (merged && OB == 4) k = (K)msrooms_step_kernel<4, false, true, false, true>;
@@ -581,12 +590,14 @@ int msrooms_launch(gpt_env* env, const LaunchArgs& a) {
   P.n_steps = a.n_steps;
   P.act_stride = env->capacity;
   P.out_stride = a.out_stride_rows;
+  const bool devctr = env->graph_mode && !multi && !replay;
+  P.ctr_ptr = env->d_counter;
   void* k = nullptr;
   switch (L.obs_bytes) {
-    case 3: k = ms_pick<3>(rgoal, false, replay, multi); break;
-    case 4: k = ms_pick<4>(rgoal, L.merged, replay, multi); break;
-    case 6: k = ms_pick<6>(rgoal, false, replay, multi); break;
-    case 8: k = ms_pick<8>(rgoal, false, replay, multi); break;
+    case 3: k = ms_pick<3>(rgoal, false, replay, multi, devctr); break;
+    case 4: k = ms_pick<4>(rgoal, L.merged, replay, multi, devctr); break;
+    case 6: k = ms_pick<6>(rgoal, false, replay, multi, devctr); break;
+    case 8: k = ms_pick<8>(rgoal, false, replay, multi, devctr); break;
   }
   if (!k) return fail(GPT_E_ARG, "msrooms: no kernel for this observation layout");
   const size_t smem = env->blob_bytes;
@@ -595,7 +606,7 @@ int msrooms_launch(gpt_env* env, const LaunchArgs& a) {
     if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(msrooms)");
   }
   void* args[] = {(void*)&P};
-  cudaError_t e = launch_pdl(k, dim3(nblocks), dim3(kMsThreads), smem, a.stream, args);
+  cudaError_t e = launch_pdl(k, dim3(nblocks), dim3(kMsThreads), smem, a.stream, args, !env->graph_mode);
   env->launches += 1;
   if (e != cudaSuccess) return cuda_fail(e, "msrooms_step_kernel launch");
   if (reset) {

@@ -201,7 +201,7 @@ GPT_API int gpt_step_many(gpt_env* env, const void* actions, int32_t n_steps, in
  * n_steps steps, only actions are read and outputs written per step; results are bit-identical to n_steps
  * single-step launches.  gpt_set_fused_steps(env, 0) forces one launch per step (A/B measurements). */
 GPT_API int gpt_set_fused_steps(gpt_env* env, int enable);
-/* Graph mode (Taxi table kernel and ROOMS, Philox mode, no track_stats): the Philox step counter moves from the launch
+/* Graph mode (every family; Philox mode, no track_stats; Taxi with the table kernel): the Philox step counter moves from the launch
  * parameters into device memory and a one-thread tick kernel advances it after every step, so that gpt_step() calls
  * captured into a CUDA graph draw fresh random numbers on every replay.  gpt_step_many then issues one launch per
  * step and gpt_step_host is unavailable.  Call outside of stream capture (it synchronises `stream`). */

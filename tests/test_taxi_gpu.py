@@ -378,18 +378,29 @@ def test_fused_launch_ragged_sizes_and_stats(b):
     assert a.launch_count == l0 + 5
 
 
-@pytest.mark.parametrize("family", ["taxi", "rooms"])
+@pytest.mark.parametrize("family", ["taxi", "rooms", "msrooms", "crooms", "tag", "car"])
 def test_cuda_graph_capture_and_replay(family):
     """Graph mode: step() calls captured into a CUDA graph draw fresh random numbers on every replay (the Philox step
     counter lives in device memory) — the replayed trajectory equals an eagerly stepped twin env, bit for bit."""
-    from gym_po.envs import RoomsEnv, TaxiVecEnv
-    b, K, n_act = 3000, 4, (5 if family == "taxi" else 8)
-    mk = (lambda: TaxiVecEnv(b, time_limit=9, hansen_obs=True, device=DEV, seed=3)) if family == "taxi" else \
-         (lambda: RoomsEnv(b, "8", obs_type="grid", obs_n=5, goal_xy=None, time_limit=9, device=DEV, seed=3))
+    from gym_po.envs import CarVecEnv, CRoomsEnv, MultistoryFourRoomsEnv, RoomsEnv, TagVecEnv, TaxiVecEnv
+    b, K = 3000, 4
+    mk, n_act = {
+        "taxi": (lambda: TaxiVecEnv(b, time_limit=9, hansen_obs=True, device=DEV, seed=3), 5),
+        "rooms": (lambda: RoomsEnv(b, "8", obs_type="grid", obs_n=5, goal_xy=None, time_limit=9, device=DEV, seed=3), 8),
+        "msrooms": (lambda: MultistoryFourRoomsEnv(b, grid_z=2, obs_type="vector_mdp_goal", goal_xyz=None, time_limit=9, device=DEV, seed=3), 4),
+        "crooms": (lambda: CRoomsEnv(b, "4", obs_type="vector_mdp", time_limit=9, device=DEV, seed=3, precision="float32"), 0),
+        "tag": (lambda: TagVecEnv(b, time_limit=9, device=DEV, seed=3), 0),
+        "car": (lambda: CarVecEnv(b, time_limit=9, device=DEV, seed=3), -1),
+    }[family]
     env, twin = mk(), mk()
     env.reset(seed=3); twin.reset(seed=3)
     env.set_graph_mode(True)
-    static_a = torch.zeros((K, env.capacity), dtype=torch.int8, device=DEV)
+    if n_act > 0:
+        static_a = torch.zeros((K, env.capacity), dtype=torch.int8, device=DEV)
+        draw = lambda gen: torch.randint(0, n_act, static_a.shape, dtype=torch.int8, device=DEV, generator=gen)
+    else:
+        static_a = torch.zeros((K, env.capacity) + ((2,) if n_act == 0 else ()), dtype=torch.float32, device=DEV)
+        draw = lambda gen: torch.rand(static_a.shape, device=DEV, generator=gen) * 2 - 1
     first = env.step(static_a[0])                                      # one eager step in graph mode
     rec = [[torch.zeros_like(x) for x in first[:4]] for _ in range(K)]
     twin.step(static_a[0])
@@ -402,7 +413,7 @@ def test_cuda_graph_capture_and_replay(family):
                 dst.copy_(src)
     gen = torch.Generator(device=DEV).manual_seed(5)
     for rep in range(6):
-        static_a.copy_(torch.randint(0, n_act, static_a.shape, dtype=torch.int8, device=DEV, generator=gen))
+        static_a.copy_(draw(gen))
         g.replay()
         torch.cuda.synchronize()
         for i in range(K):
@@ -414,7 +425,7 @@ def test_cuda_graph_capture_and_replay(family):
         assert torch.equal(sa[k], sb[k]), k
     assert env.rng_counter == twin.rng_counter          # read back from the device
     env.set_graph_mode(False)                            # and back to launch-parameter counters
-    a = torch.randint(0, n_act, (env.capacity,), dtype=torch.int8, device=DEV, generator=gen)
+    a = draw(gen)[0]
     for x, y in zip(env.step(a)[:4], twin.step(a)[:4]):
         assert torch.equal(x, y)
     with pytest.raises(ValueError):
