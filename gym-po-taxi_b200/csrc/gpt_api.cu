@@ -420,6 +420,7 @@ int gpt_set_graph_mode(gpt_env* env, int enable, void* stream) {
   if (!env) return fail(GPT_E_ARG, "gpt_set_graph_mode: NULL env");
   cudaError_t e = cudaSetDevice(env->cfg.device);
   if (e != cudaSuccess) return cuda_fail(e, "cudaSetDevice");
+  if (enable && env->graph_mode) return GPT_OK;   // already on: the device counter is the truth, leave it alone
   if (enable) {
     if (!graph_mode_family(env))
       return fail(GPT_E_ARG, "gpt_set_graph_mode: needs Philox mode without track_stats (Taxi: a map small enough for the table kernel)");

@@ -11,6 +11,10 @@ The reference's author stacks gymnasium's ``RecordEpisodeStatistics`` and ``Norm
 step: nothing is copied to the host.  Semantics follow gymnasium 0.27-0.29 (restated in oracle/wrappers.py); the
 normalised reward is float32 (gymnasium returns float64).  ``stats()`` gives whole-job episode statistics, summed
 over ranks with one NCCL all-reduce of an 8-double vector (the only collective on this path).
+
+CUDA graphs: ``RecordEpisodeStatistics.step`` can be captured together with a graph-mode env (its launch has no
+per-step host state); ``NormalizeReward`` cannot — its two launches alternate between the halves of a double buffer
+chosen on the host.
 """
 from __future__ import annotations
 

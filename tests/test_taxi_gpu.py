@@ -424,6 +424,8 @@ def test_cuda_graph_capture_and_replay(family):
     for k in sa:
         assert torch.equal(sa[k], sb[k]), k
     assert env.rng_counter == twin.rng_counter          # read back from the device
+    env.set_graph_mode(True)                             # enabling twice must not rewind the device counter
+    assert env.rng_counter == twin.rng_counter
     env.set_graph_mode(False)                            # and back to launch-parameter counters
     a = draw(gen)[0]
     for x, y in zip(env.step(a)[:4], twin.step(a)[:4]):
