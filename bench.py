@@ -222,9 +222,9 @@ def run_b200(args):
     # the whole cpuset: the CPU baseline of the same run uses every host core)
     numa = bind_to_gpu_numa_node(local_rank) if world > 1 else "not bound (single process)"
     if world > 1:
-        # keep stdout to the one JSON line: some images export NCCL_DEBUG=VERSION, which prints a banner to stdout
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"
+        # keep stdout to the one JSON line: with NCCL_DEBUG >= VERSION (this image exports WARN) NCCL prints its
+        # version banner and warnings to stdout unless told otherwise
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
     wl = WORKLOADS[args.workload]
     b = 1 << args.log2_envs
