@@ -215,6 +215,11 @@ def run_b200(args):
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    # stdout must carry exactly one JSON line, but libraries print there too (NCCL's version banner at init):
+    # point fd 1 at stderr while the run is in progress and restore it for the final line
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     from gym_po.sharding import bind_to_gpu_numa_node
@@ -222,9 +227,6 @@ def run_b200(args):
     # the whole cpuset: the CPU baseline of the same run uses every host core)
     numa = bind_to_gpu_numa_node(local_rank) if world > 1 else "not bound (single process)"
     if world > 1:
-        # keep stdout to the one JSON line: with NCCL_DEBUG >= VERSION (this image exports WARN) NCCL prints its
-        # version banner and warnings to stdout unless told otherwise
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
     wl = WORKLOADS[args.workload]
     b = 1 << args.log2_envs
@@ -381,7 +383,10 @@ def run_b200(args):
             line["cpu_baseline"] = cpu_reference(wl["cpu_family"], seconds_target=args.cpu_seconds)
         else:
             line["cpu_baseline"] = None
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
         print(json.dumps(line), flush=True)
+        os.dup2(2, 1)
     if world > 1:
         dist.destroy_process_group()
 
