@@ -78,6 +78,9 @@ CASES = [
     ("msrooms_vghansen_rg", "MultistoryFourRoomsEnv", {"grid_z": 2, "obs_type": "vector_goal_hansen", "goal_xyz": None, "time_limit": 40}, 4, 300),
     ("msrooms_vmdp_goal_rg", "MultistoryFourRoomsEnv", {"grid_z": 2, "obs_type": "vector_mdp_goal", "goal_xyz": None, "time_limit": 30,
                                                         "step_reward": -0.1, "wall_reward": -1.0}, 4, 300),
+    ("msrooms_room_goal_rg", "MultistoryFourRoomsEnv", {"grid_z": 2, "obs_type": "room_goal", "goal_xyz": None, "time_limit": 30}, 4, 200),
+    ("msrooms_vhansen8_ord", "MultistoryFourRoomsEnv", {"grid_z": 3, "obs_type": "vector_hansen8", "action_type": "ordinal", "time_limit": 60,
+                                                         "action_failure_probability": 0.1}, 8, 250),
     # car-flag.  n_act -1 = float32 forces [B,1] steered towards the flags, -2 = float64 forces
     ("car_f32", "CarVecEnv", {"time_limit": 60}, -1, 400),
     ("car_f64", "CarVecEnv", {"time_limit": 45}, -2, 300),
