@@ -24,7 +24,9 @@ for p in (ROOT, os.path.join(ROOT, "gym-po-taxi_b200")):
         sys.path.insert(0, p)
 
 METRIC, UNIT = "env_steps_per_sec", "env-steps/s"
-SLOTS = 8  # distinct action vectors / rollout-storage slots cycled through (footprint > L2)
+MAX_SLOTS = 10  # action / rollout-storage slots cycled through = steps fused per launch (footprint > L2)
+# configurations also timed (briefly) after the headline so that the driver-run line carries them
+EXTRA_WORKLOADS = ("rooms_hansen8", "rooms_grid5", "rooms_grid9", "crooms", "tag", "msrooms")
 
 # algorithmic bytes per env-step (DESIGN.md "Algorithmic bytes")
 WORKLOADS = {
@@ -145,23 +147,36 @@ class ClockSampler(threading.Thread):
 
 
 # ------------------------------------------------------------------------------------------------
-def cpu_reference(family, seconds_target=12.0, envs=1 << 16):
-    """Times the oracle port (numpy restatement of the reference step) on every available host core."""
+def cpu_reference(family, total_envs, *, steps=None, seconds_target=12.0, warmup=3, max_seconds=150.0):
+    """Times the reference's CPU vectorized step on every available host core: one process per core (numpy
+    elementwise ops are single-threaded), each with total_envs/cores envs, started together.  The UNMODIFIED
+    reference (baseline/_ref, kind "reference") when it is installed and implements the family, else the numpy
+    oracle port (kind "port").  `steps` given: exactly that many steps of the whole batch (capped so that the run
+    stays under max_seconds); else as many as fit seconds_target."""
+    sys.path.insert(0, ROOT)
+    from oracle import cpu_bench
+    kind = "reference" if (cpu_bench.reference_installed() and family in cpu_bench.REFERENCE_FAMILIES) else "port"
     cores = len(os.sched_getaffinity(0))
-    # calibrate: single short run to size the sample
-    t = time.monotonic()
-    out = subprocess.run([sys.executable, "-m", "oracle.cpu_bench", "--family", family, "--envs", str(envs), "--steps", "10",
-                          "--warmup", "3"], capture_output=True, text=True, cwd=ROOT)
-    if out.returncode != 0:
-        raise RuntimeError("oracle.cpu_bench failed: " + out.stderr[-2000:])
-    r = json.loads(out.stdout.strip().splitlines()[-1])
-    per_step = (r["t1"] - r["t0"]) / r["steps"]
-    startup = time.monotonic() - t
-    steps = max(20, int(seconds_target / max(per_step, 1e-6) / 1.3))  # 1.3: all-core runs are slower than single
-    start_at = time.monotonic() + startup + 3.0
-    procs = [subprocess.Popen([sys.executable, "-m", "oracle.cpu_bench", "--family", family, "--envs", str(envs), "--steps",
-                               str(steps), "--warmup", "10", "--seed", str(i), "--start-at", repr(start_at)],
-                              stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, cwd=ROOT) for i in range(cores)]
+    per = max(1, -(-total_envs // cores))
+    procs = [subprocess.Popen([sys.executable, "-m", "oracle.cpu_bench", "--impl", kind, "--family", family, "--envs", str(per),
+                               "--warmup", str(max(1, warmup)), "--seed", str(i), "--sync-stdin"],
+                              stdin=subprocess.PIPE, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, cwd=ROOT)
+             for i in range(cores)]
+    per_step = []
+    for p in procs:
+        line = p.stdout.readline()
+        if not line.startswith("READY"):
+            raise RuntimeError("oracle.cpu_bench worker failed: " + p.stderr.read()[-2000:])
+        per_step.append(float(line.split()[1]))
+    est = max(per_step)   # s per step of the whole batch with all cores busy (the warm-ups ran concurrently)
+    if steps is None:
+        n = max(3, int(seconds_target / max(est, 1e-6)))
+    else:
+        n = max(1, min(steps, int(max_seconds / max(est, 1e-6))))
+    start_at = time.monotonic() + 0.3
+    for p in procs:
+        p.stdin.write(f"GO {start_at!r} {n}\n")
+        p.stdin.flush()
     res = []
     for p in procs:
         so, se = p.communicate()
@@ -170,11 +185,12 @@ def cpu_reference(family, seconds_target=12.0, envs=1 << 16):
         res.append(json.loads(so.strip().splitlines()[-1]))
     wall = max(x["t1"] for x in res) - min(x["t0"] for x in res)
     total = sum(x["envs"] * x["steps"] for x in res)
-    single = envs / per_step
-    return {"value": total / wall, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": f"{cores} processes x {envs} envs x {steps} steps of the numpy oracle port (oracle/), "
-                      f"episode phases de-synchronised; single-core rate {single:.3e}",
-            "single_core_value": single, "wall_s": wall}
+    what = ("the unmodified reference (baseline/_ref/gym_po via oracle.ref_loader)" if kind == "reference"
+            else "the numpy oracle port (oracle/)")
+    return {"value": total / wall, "unit": UNIT, "cores": cores, "kind": kind,
+            "sample": f"{cores} processes x {per} envs (= {per * cores} envs, the whole batch) x {n} steps of {what}, "
+                      f"episode phases de-synchronised",
+            "envs": per * cores, "steps": n, "ms_per_step": wall / n * 1e3, "wall_s": wall}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -207,6 +223,108 @@ def make_env(workload, b, rank, seed=0):
     raise KeyError(workload)
 
 
+def steps_per_launch_for(k):
+    """Steps fused into one launch: the largest divisor of K in [4, 10], so that the K timed steps are whole
+    launches of equal length (no ragged 8+8+4); K without such a divisor falls back to launches of up to 8."""
+    for t in range(min(k, MAX_SLOTS), 3, -1):
+        if k % t == 0:
+            return t
+    return min(8, k)
+
+
+class Workload:
+    """One env family at B envs per GPU with its synthetic action slots and rollout storage."""
+
+    def __init__(self, name, b, rank, dev, k):
+        import torch
+        self.name, self.b, self.wl = name, b, WORKLOADS[name]
+        self.env = make_env(name, b, rank)
+        self.cap = self.env.capacity
+        self.slots = steps_per_launch_for(k)
+        gen = torch.Generator(device=dev).manual_seed(1234 + rank)
+        wl = self.wl
+        if wl["n_act"]:
+            self.actions = torch.randint(0, wl["n_act"], (self.slots, self.cap), dtype=torch.int8, device=dev, generator=gen)
+        else:
+            cols = wl.get("act_cols", 2)
+            self.actions = torch.rand((self.slots, self.cap, cols) if cols > 1 else (self.slots, self.cap), device=dev, generator=gen) * 2 - 1
+        # rollout storage: outputs of step t go to slot t % slots (like an RL rollout buffer); with the action
+        # slots this makes the per-step footprint rotate through > L2-size memory
+        self.out = {}
+        for nm in ("obs", "reward", "terminated", "truncated"):
+            a = self.env._arrays[nm]
+            self.out[nm] = torch.zeros((self.slots,) + tuple(a.shape), dtype=a.dtype, device=dev)
+        self.env.reset(seed=0)
+        # de-synchronise episode phases (after a synchronised reset every env would truncate on the same step)
+        self.env._arrays["elapsed"][:b] = torch.randint(0, self.env.time_limit + 1, (b,), device=dev, generator=gen, dtype=torch.int32)
+        self.footprint = sum(t.numel() * t.element_size() for t in self.out.values()) + self.actions.numel() * self.actions.element_size()
+
+    def run_steps(self, k):
+        done = 0
+        while done < k:
+            n = min(self.slots, k - done)
+            self.env.step_many(self.actions[:n], self.out)
+            done += n
+
+    def close(self):
+        self.env.close()
+        self.out = self.actions = self.env = None
+
+
+def timed_blocks(w, k, world, dev, min_total_ms, min_repeats=7, max_repeats=400):
+    """R >= 7 back-to-back repeats of the K-step block, each between its own pair of CUDA events on the launching
+    stream (torch's current stream); barrier + synchronize on both sides of the timed region; one UNTIMED block
+    between the barrier and the first event (the first launches after an idle wait run at ramping clocks).  Returns
+    the per-repeat times in ms (max over ranks) and the launches of one block."""
+    import torch
+    import torch.distributed as dist
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    w.run_steps(k)
+    e1.record()
+    torch.cuda.synchronize()
+    est = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(est, op=dist.ReduceOp.MAX)   # every rank must run the same number of repeats
+    reps = int(min(max_repeats, max(min_repeats, -(-min_total_ms // max(float(est.item()), 1e-3)))))
+    evs = [torch.cuda.Event(enable_timing=True) for _ in range(reps + 1)]
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    w.run_steps(k)                     # untimed
+    l0 = w.env.launch_count
+    evs[0].record()
+    for r in range(reps):
+        w.run_steps(k)                 # exactly K steps
+        evs[r + 1].record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    launches = (w.env.launch_count - l0) // reps
+    ms = torch.tensor([evs[r].elapsed_time(evs[r + 1]) for r in range(reps)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    return [float(x) for x in ms.tolist()], launches
+
+
+def device_numbers(w, k, ms_list, launches, world, peak):
+    """env-steps/s and the roofline figures of one timed leg (median repeat)."""
+    wl = w.wl
+    ms = statistics.median(ms_list)
+    spl = k / max(launches, 1)
+    # Fused multi-step launches keep the state in registers for T steps: the state bytes move once per LAUNCH, so
+    # the algorithmic bytes are restated downward — never count bytes that are not moved.
+    alg = wl["alg_bytes"]
+    if spl > 1.0:
+        alg = wl["alg_bytes"] - wl.get("state_bytes", 0) + wl.get("state_bytes", 0) / spl
+    per_launch_s = ms * 1e-3 / max(launches, 1)
+    achieved = alg * spl * w.cap / per_launch_s / 1e9
+    return {"value": w.b * world * k / (ms * 1e-3), "ms_per_step": ms / k, "ms_per_step_best": min(ms_list) / k,
+            "ms_per_step_worst": max(ms_list) / k, "repeats": len(ms_list), "launches": launches, "steps_per_launch": spl,
+            "alg_bytes_per_env_step": alg, "kernel_us": per_launch_s * 1e6, "achieved": achieved, "frac": achieved / peak}
+
+
 def run_b200(args):
     import numpy as np
     import torch
@@ -230,157 +348,159 @@ def run_b200(args):
         dist.init_process_group("nccl", device_id=dev)
     wl = WORKLOADS[args.workload]
     b = 1 << args.log2_envs
-    env = make_env(args.workload, b, rank)
-    cap = env.capacity
-    gen = torch.Generator(device=dev).manual_seed(1234 + rank)
-    if wl["n_act"]:
-        actions = torch.randint(0, wl["n_act"], (SLOTS, cap), dtype=torch.int8, device=dev, generator=gen)
-    else:
-        cols = wl.get("act_cols", 2)
-        actions = torch.rand((SLOTS, cap, cols) if cols > 1 else (SLOTS, cap), device=dev, generator=gen) * 2 - 1
-    # rollout storage: outputs of step t go to slot t % SLOTS (like an RL rollout buffer); with the
-    # action slots this makes the per-step footprint rotate through > L2-size memory
-    out = {}
-    for name in ("obs", "reward", "terminated", "truncated"):
-        a = env._arrays[name]
-        out[name] = torch.zeros((SLOTS,) + tuple(a.shape), dtype=a.dtype, device=dev)
-    env.reset(seed=0)
-    # de-synchronise episode phases (after a synchronised reset every env would truncate on the same step)
-    env._arrays["elapsed"][:b] = torch.randint(0, env.time_limit + 1, (b,), device=dev, generator=gen, dtype=torch.int32)
-
-    def run_steps(k):
-        done = 0
-        while done < k:
-            n = min(SLOTS, k - done)
-            env.step_many(actions[:n], out)
-            done += n
+    k = args.steps
+    peak, peak_src = measured_peak_gbs()
+    w = Workload(args.workload, b, rank, dev, k)
+    env, cap = w.env, w.cap
 
     sampler = ClockSampler(local_rank)
     sampler.start()
     # warm-up: W steps, then a fixed ~1 s of load so clocks are sampled under the same kernel
-    run_steps(max(3, args.warmup))
+    w.run_steps(max(3, args.warmup))
     torch.cuda.synchronize()
     sampler.active.set()
     t_end = time.monotonic() + (0.0 if args.quick else 1.0)
     while time.monotonic() < t_end:
-        run_steps(SLOTS * 16)
+        w.run_steps(w.slots * 16)
         torch.cuda.synchronize()
 
-    # ---- timed region: exactly K steps, CUDA events on the launching stream, barrier + sync on both sides
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    launches0 = env.launch_count
-    ev0.record()
-    run_steps(args.steps)
-    ev1.record()
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    ms = ev0.elapsed_time(ev1)
-    launches = env.launch_count - launches0
-    t = torch.tensor([ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_max = float(t.item())
+    # ---- timed region (see timed_blocks): repeats of exactly K steps; the median repeat is the reported one
+    ms_list, launches = timed_blocks(w, k, world, dev, args.min_timed_ms)
+    head = device_numbers(w, k, ms_list, launches, world, peak)
 
     # ---- when step_many ran as fused launches, also time one launch per step (what env.step() costs)
     single = None
-    if launches < args.steps:
+    if launches < k:
         env.set_fused_steps(False)
-        run_steps(SLOTS * 4)
-        torch.cuda.synchronize()
-        k1 = min(args.steps, 1000)
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        run_steps(k1)
-        e1.record()
-        torch.cuda.synchronize()
-        ts = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(ts, op=dist.ReduceOp.MAX)
-        single = (k1, float(ts.item()))
+        w.run_steps(w.slots * 4)
+        ms1, l1 = timed_blocks(w, k, world, dev, args.min_timed_ms)
+        single = device_numbers(w, k, ms1, l1, world, peak)
         env.set_fused_steps(True)
 
     # ---- end-to-end: public API with HOST buffers (pinned), H2D + step + D2H inside the timed region
-    if args.e2e_steps is not None:
-        e2e_steps = max(1, args.e2e_steps)
-    else:
-        e2e_steps = 1 if args.quick else max(3, min(args.steps, 100))
-    host_actions = env.pinned_actions(SLOTS)          # the steps' inputs live in pinned host memory
+    host_actions = env.pinned_actions(w.slots)          # the steps' inputs live in pinned host memory
     hrng = np.random.default_rng(99 + rank)
     if wl["n_act"]:
-        host_actions[:] = hrng.integers(0, wl["n_act"], size=(SLOTS, b)).astype(np.int8)
+        host_actions[:] = hrng.integers(0, wl["n_act"], size=(w.slots, b)).astype(np.int8)
     else:
         host_actions[:] = hrng.uniform(-1, 1, size=host_actions.shape).astype(np.float32)
+    e2e_k = args.e2e_steps if args.e2e_steps is not None else k
+    e2e_reps = 1 if args.quick else 7
     for i in range(3):
-        env.step_host(host_actions[i % SLOTS])
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    for i in range(e2e_steps):
-        obs, rew, term, trunc, _ = env.step_host(host_actions[i % SLOTS])   # H2D actions, step, D2H results
-    torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - t0
-    te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+        env.step_host(host_actions[i % w.slots])
+    e2e_times = []
+    for r in range(e2e_reps):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for i in range(e2e_k):
+            obs, rew, term, trunc, _ = env.step_host(host_actions[i % w.slots])   # H2D actions, step, D2H results
+        torch.cuda.synchronize()
+        e2e_times.append(time.perf_counter() - t0)
+    te = torch.tensor(e2e_times, dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_s = float(te.item())
+    e2e_s = statistics.median(te.tolist())
     h2d, d2h = env.host_bytes_per_step()
-    sampler.active.clear()
-    sampler.stop()
-
+    clocks_head = sampler.summary()
+    slots, footprint = w.slots, w.footprint
     # episode statistics all-reduce (the only collective on this path; logging cadence, outside the timed region)
     if world > 1:
         st = env.stats_tensor()
         dist.all_reduce(st)
+    w.close()
+    del w, env
+    torch.cuda.empty_cache()
+
+    # ---- the other BASELINE.json configurations, driver-visible (short: repeats until >= 10 ms each)
+    extra = {}
+    if not args.quick and not args.no_workloads:
+        if world == 1:
+            todo = [(n, args.log2_envs) for n in EXTRA_WORKLOADS if n != args.workload] + [("rooms_hansen8", args.log2_envs - 1)]
+        else:   # configs[2]: FourRooms hansen8 sharded over the GPUs, 2^21 envs per GPU (2^24 in total on 8)
+            todo = [("rooms_hansen8", 21)]
+        for name, lg in todo:
+            i0 = len(sampler.samples)
+            x = Workload(name, 1 << lg, rank, dev, k)
+            x.run_steps(x.slots * 8)
+            torch.cuda.synchronize()
+            t_end = time.monotonic() + 0.25
+            while time.monotonic() < t_end:
+                x.run_steps(x.slots * 8)
+                torch.cuda.synchronize()
+            msx, lx = timed_blocks(x, k, world, dev, 10.0)
+            d = device_numbers(x, k, msx, lx, world, peak)
+            smp = sampler.samples[i0:]
+            extra[f"{name}_2p{lg}"] = {
+                "value": d["value"], "unit": UNIT, "envs_per_gpu": 1 << lg, "envs_total": (1 << lg) * world,
+                "kernel_us": d["kernel_us"], "steps_per_launch": d["steps_per_launch"],
+                "alg_bytes_per_env_step": d["alg_bytes_per_env_step"], "achieved": d["achieved"], "frac": d["frac"],
+                "repeats": d["repeats"], "ms_per_step": d["ms_per_step"], "dtype": x.wl["dtype"], "desc": x.wl["desc"],
+                "clocks": {"sm_mhz": statistics.median(smp) if smp else None, "samples": len(smp)}}
+            x.close()
+            del x
+            torch.cuda.empty_cache()
+    sampler.active.clear()
+    sampler.stop()
+    clocks_all = sampler.summary()
 
     if rank == 0:
         total_envs = b * world
-        value = total_envs * args.steps / (ms_max * 1e-3)
-        peak, peak_src = measured_peak_gbs()
-        # Fused multi-step launches (gpt_step_many keeps the state in registers for T steps): the state bytes move
-        # once per LAUNCH, so the algorithmic bytes are restated downward — never count bytes that are not moved.
-        steps_per_launch = args.steps / max(launches, 1)
-        alg_bytes = wl["alg_bytes"]
-        if steps_per_launch > 1.0:
-            alg_bytes = wl["alg_bytes"] - wl.get("state_bytes", 0) + wl.get("state_bytes", 0) / steps_per_launch
-        per_launch_s = ms_max * 1e-3 / max(launches, 1)
-        achieved = alg_bytes * steps_per_launch * cap / per_launch_s / 1e9
+        spl = head["steps_per_launch"]
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
-            "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "metric": METRIC, "value": head["value"], "unit": UNIT, "n_gpus": world, "steps": k, "warmup": max(3, args.warmup),
+            "ms_per_step": head["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": wl["dtype"], "data": "synthetic",
             "config": {"workload": wl["desc"], "name": args.workload, "envs_per_gpu": b, "envs_total": total_envs,
-                       "rng": "philox4x32-10", "l2": f"inputs rotate over {SLOTS} action slots and outputs over {SLOTS} "
-                       "rollout slots (footprint > 126 MB L2); " + ("the state arrays are re-read every step" if steps_per_launch <= 1.0 else
-                       f"fused launches of {steps_per_launch:g} steps: state read and written once per launch, actions read and outputs written every step"),
+                       "rng": "philox4x32-10",
+                       "action_stream": "open loop: pre-generated synthetic action slots resident in HBM (north_star: 'synthetic action streams')"
+                                        + (f"; gpt_step_many fuses {spl:g} consecutive steps per launch — the closed-loop "
+                                           "one-launch-per-step rate of env.step() is reported as single_step_launches" if spl > 1 else ""),
+                       "l2": f"inputs rotate over {slots} action slots and outputs over {slots} rollout slots "
+                             f"(footprint {footprint / 1e6:.0f} MB per GPU > 126 MB L2); "
+                             + ("the state arrays are re-read every step" if spl <= 1.0 else
+                                f"state read and written once per launch of {spl:g} steps, actions read and outputs written every step"),
+                       "timing": f"median of {head['repeats']} back-to-back repeats of the {k}-step block, each between its own CUDA "
+                                 "events (max over ranks per repeat); barrier + synchronize on both sides; one untimed block after the barrier",
                        "episode_phases": "de-synchronised (elapsed ~ U[0,time_limit]) before warm-up"},
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": peak_src, "alg_bytes_per_env_step": alg_bytes,
-                         "steps_per_launch": steps_per_launch, "kernel_us": per_launch_s * 1e6, "frac_of_nominal_8TBs": achieved / 8000.0},
-            "e2e": {"value": total_envs * e2e_steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d * world,
-                    "d2h_bytes_per_step": d2h * world, "steps": e2e_steps, "api": "env.step_host(numpy) -> gpt_step_host",
-                    "host_numa": numa},
+            "roofline": {"bound": "hbm", "achieved": head["achieved"], "peak": peak, "unit": "GB/s", "frac": head["frac"],
+                         "traffic": None, "peak_source": peak_src, "alg_bytes_per_env_step": head["alg_bytes_per_env_step"],
+                         "steps_per_launch": spl, "kernel_us": head["kernel_us"], "frac_of_nominal_8TBs": head["achieved"] / 8000.0,
+                         "frac_best_repeat": head["frac"] * head["ms_per_step"] / head["ms_per_step_best"],
+                         "frac_worst_repeat": head["frac"] * head["ms_per_step"] / head["ms_per_step_worst"]},
+            "repeats": head["repeats"], "ms_per_step_best": head["ms_per_step_best"], "ms_per_step_worst": head["ms_per_step_worst"],
+            "e2e": {"value": total_envs * e2e_k / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d * world,
+                    "d2h_bytes_per_step": d2h * world, "steps": e2e_k, "repeats": e2e_reps,
+                    "api": "env.step_host(numpy) -> gpt_step_host", "host_numa": numa,
+                    "pcie_gbs_achieved": (h2d + d2h) * world * e2e_k / e2e_s / 1e9},
             "gpu_launches": launches * world,
-            "clocks": sampler.summary(),
+            "clocks": clocks_head,
         }
         if single is not None:
-            k1, ms1 = single
-            ach1 = wl["alg_bytes"] * cap / (ms1 * 1e-3 / k1) / 1e9
-            line["single_step_launches"] = {"value": total_envs * k1 / (ms1 * 1e-3), "unit": UNIT, "steps": k1, "kernel_us": ms1 * 1e3 / k1,
-                                            "alg_bytes_per_env_step": wl["alg_bytes"], "achieved": ach1, "frac": ach1 / peak,
-                                            "note": "same workload with one launch per step (gpt_step): state read and written every step"}
+            line["single_step_launches"] = {
+                "value": single["value"], "unit": UNIT, "steps": k, "repeats": single["repeats"], "kernel_us": single["kernel_us"],
+                "alg_bytes_per_env_step": single["alg_bytes_per_env_step"], "achieved": single["achieved"], "frac": single["frac"],
+                "note": "same workload with one launch per step (gpt_step, what a closed-loop env.step() costs): state read and written every step"}
+        # DRAM traffic of the dominant kernel from the committed ncu --set full capture — only when the capture was
+        # taken at this run's steps per launch (the bytes are per launch)
         traffic_file = os.path.join(ROOT, "profiles", f"traffic_{args.workload}.json")
         if os.path.exists(traffic_file):
             try:
-                line["roofline"]["traffic"] = json.load(open(traffic_file)).get("dram_bytes_per_launch")
+                tr = json.load(open(traffic_file))
+                if abs(float(tr.get("steps_per_launch", -1)) - spl) < 1e-9 and int(tr.get("envs", cap)) == cap:
+                    line["roofline"]["traffic"] = tr.get("dram_bytes_per_launch")
+                    line["roofline"]["traffic_source"] = tr.get("source")
+                else:
+                    line["roofline"]["traffic_note"] = (f"committed capture is for {tr.get('steps_per_launch')} steps per launch, "
+                                                        f"this run used {spl:g}: not comparable, left null")
             except Exception:
                 pass
+        if extra:
+            line["workloads"] = extra
+            line["clocks_all_workloads"] = clocks_all
         if world == 1 and not args.no_cpu and not args.quick:
-            line["cpu_baseline"] = cpu_reference(wl["cpu_family"], seconds_target=args.cpu_seconds)
+            line["cpu_baseline"] = cpu_reference(wl["cpu_family"], total_envs, seconds_target=args.cpu_seconds)
         else:
             line["cpu_baseline"] = None
         sys.stdout.flush()
@@ -392,23 +512,22 @@ def run_b200(args):
 
 
 def run_reference(args):
-    """Reference arm: the reference's own CPU implementation of the path.  The reference is pure Python
-    and cannot travel to the GPU box, so this times the oracle port (oracle/, a numpy restatement pinned
-    bit-exactly to the reference by tests/golden) on all host cores.  Rank 0 only."""
+    """Reference arm: the reference's own CPU implementation of the path — the unmodified package installed in
+    baseline/_ref (kind "reference"; the numpy oracle port only if that directory is missing) — on all host cores:
+    K steps of the same workload (the whole batch of envs_total envs, split over one process per core).  Rank 0 only."""
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if rank != 0:
         return
     wl = WORKLOADS[args.workload]
-    # K "steps" each a bounded sample; the run as a whole is bounded to args.cpu_seconds
-    cb = cpu_reference(wl["cpu_family"], seconds_target=args.cpu_seconds)
     b = 1 << args.log2_envs
+    cb = cpu_reference(wl["cpu_family"], b * world, steps=args.steps, warmup=max(3, args.warmup))
     line = {
-        "impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps,
-        "warmup": max(3, args.warmup), "ms_per_step": None, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": world, "steps": cb["steps"],
+        "warmup": max(3, args.warmup), "ms_per_step": cb["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "int64", "data": "synthetic",
         "config": {"workload": wl["desc"], "name": args.workload, "envs_per_gpu": b, "envs_total": b * world,
-                   "note": "CPU arm: bounded sample of the same workload on all host cores"},
+                   "note": "CPU arm: the same batch (envs_total envs) stepped by the reference's numpy code, one process per host core"},
         "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
         "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -426,8 +545,10 @@ def main():
     ap.add_argument("--log2-envs", type=int, default=22, help="log2 of envs per GPU")
     ap.add_argument("--e2e-steps", type=int, default=None)
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--min-timed-ms", type=float, default=25.0, help="repeat the K-step block until at least this much GPU time (and >= 7 repeats)")
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--quick", action="store_true", help="profiling runs: no load phase, no e2e, no CPU baseline")
+    ap.add_argument("--no-workloads", action="store_true", help="skip the short runs of the other BASELINE configurations")
+    ap.add_argument("--quick", action="store_true", help="profiling runs: no load phase, one e2e repeat, no CPU baseline, no other workloads")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
