@@ -100,6 +100,15 @@ int upload_blob(gpt_env* env, const std::vector<uint8_t>& blob) {
   return GPT_OK;
 }
 
+// debug range check of a discrete action array (gpt_check_actions): counts bytes outside [0, n)
+__global__ void count_bad_actions_kernel(const int8_t* a, int64_t n_rows, int n_actions, unsigned long long* out) {
+  unsigned long long bad = 0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_rows; i += (int64_t)gridDim.x * blockDim.x)
+    bad += (unsigned)(int)a[i] >= (unsigned)n_actions ? 1ull : 0ull;
+  for (int o = 16; o > 0; o >>= 1) bad += __shfl_xor_sync(0xFFFFFFFFu, bad, o);
+  if ((threadIdx.x & 31u) == 0 && bad) atomicAdd(out, bad);
+}
+
 // graph mode: advances the device-resident Philox step counter after a step (one thread; captured into the graph)
 __global__ void tick_kernel(uint64_t* counter, uint64_t n) { *counter += n; }
 
@@ -178,6 +187,8 @@ static int host_path_init(gpt_env* env) {
     e = cudaEventCreateWithFlags(&h.done[i], cudaEventDisableTiming);
     if (e != cudaSuccess) return cuda_fail(e, "cudaEventCreate(host path)");
   }
+  cudaError_t ef = cudaEventCreateWithFlags(&h.fork, cudaEventDisableTiming);
+  if (ef != cudaSuccess) return cuda_fail(ef, "cudaEventCreate(host path)");
   const size_t abytes = (size_t)env->capacity * env->action_cols * elem_size(env->action_dtype);
   cudaError_t e = cudaMalloc(&h.d_actions, abytes);
   if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc(host path actions)");
@@ -270,9 +281,11 @@ int gpt_destroy(gpt_env* env) {
   if (env->d_blob) cudaFree(env->d_blob);
   if (env->d_stats) cudaFree(env->d_stats);
   if (env->d_counter) cudaFree(env->d_counter);
+  if (env->d_bad) cudaFree(env->d_bad);
   if (env->host.ready) {
     for (int i = 0; i < HostPath::kStreams; ++i) {
       if (env->host.done[i]) cudaEventDestroy(env->host.done[i]);
+      if (i == 0 && env->host.fork) cudaEventDestroy(env->host.fork);
       if (env->host.streams[i]) cudaStreamDestroy(env->host.streams[i]);
     }
     if (env->host.d_actions) cudaFree(env->host.d_actions);
@@ -328,6 +341,14 @@ int gpt_reset(gpt_env* env, int has_seed, uint64_t seed, void* stream) {
   a.mode = kModeReset;
   a.n_tiles = env->n_tiles;
   a.stream = (cudaStream_t)stream;
+  // reset() runs the ordinary step kernel on a poisoned `elapsed` (every env truncates), and that kernel indexes the
+  // shared-memory tables with whatever the state arrays hold: clear them first, so that a caller who bound freshly
+  // cudaMalloc'ed (uninitialised) memory cannot make the first reset read out of bounds.
+  for (const ArraySlot& sl : env->arrays) {
+    if (sl.desc.role != GPT_ROLE_STATE || !sl.ptr) continue;
+    cudaError_t e = cudaMemsetAsync(sl.ptr, 0, (size_t)env->capacity * sl.desc.cols * sl.desc.elem_size, a.stream);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(state arrays)");
+  }
   if (env->graph_mode && has_seed) {  // the seed restarts the counter: mirror it to the device (not capturable, like reset itself)
     cudaError_t e = cudaMemcpyAsync(env->d_counter, &env->counter, sizeof(uint64_t), cudaMemcpyHostToDevice, a.stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(a.stream);
@@ -468,6 +489,16 @@ int gpt_step_host(gpt_env* env, const gpt_host_io* io) {
   if (n_chunks < 1) n_chunks = 1;
   const int32_t per = (env->n_tiles + n_chunks - 1) / n_chunks;
   int rc = GPT_OK;
+  // The internal streams are non-blocking: order them behind whatever the caller queued on ITS stream (gpt_reset,
+  // gpt_step, set_state / set_replay copies) before the first H2D copy, and the caller's stream behind them at the end.
+  cudaStream_t caller = (cudaStream_t)io->stream;
+  e = cudaEventRecord(h.fork, caller);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaEventRecord(host path fork)");
+  const int used = n_chunks < HostPath::kStreams ? n_chunks : HostPath::kStreams;
+  for (int i = 0; i < used; ++i) {
+    e = cudaStreamWaitEvent(h.streams[i], h.fork, 0);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaStreamWaitEvent(host path fork)");
+  }
   for (int c = 0; c < n_chunks && rc == GPT_OK; ++c) {
     const int32_t t0 = c * per;
     const int32_t nt = (t0 + per <= env->n_tiles) ? per : env->n_tiles - t0;
@@ -496,7 +527,12 @@ int gpt_step_host(gpt_env* env, const gpt_host_io* io) {
     if (e != cudaSuccess) { rc = cuda_fail(e, "D2H outputs"); break; }
   }
   env->counter += 1;
-  for (int i = 0; i < HostPath::kStreams; ++i) {
+  for (int i = 0; i < used; ++i) {  // join: later work on the caller's stream sees this step's state
+    e = cudaEventRecord(h.done[i], h.streams[i]);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(caller, h.done[i], 0);
+    if (e != cudaSuccess && rc == GPT_OK) rc = cuda_fail(e, "cudaStreamWaitEvent(host path join)");
+  }
+  for (int i = 0; i < used; ++i) {
     e = cudaStreamSynchronize(h.streams[i]);
     if (e != cudaSuccess && rc == GPT_OK) rc = cuda_fail(e, "cudaStreamSynchronize(host path)");
   }
@@ -541,5 +577,63 @@ int gpt_stats_reset(gpt_env* env, void* stream) {
   return e == cudaSuccess ? GPT_OK : cuda_fail(e, "cudaMemsetAsync(stats)");
 }
 int64_t gpt_launch_count(const gpt_env* env) { return env ? env->launches : 0; }
+
+int gpt_table_read(const gpt_env* env, const char* name, void* host_out, int64_t capacity_bytes, int64_t* n_bytes) {
+  if (!env || !name || !n_bytes) return fail(GPT_E_ARG, "gpt_table_read: NULL argument");
+  const gpt_config& c = env->cfg;
+  const std::string nm(name);
+  int64_t off = -1, bytes = 0;
+  if (c.family == GPT_FAMILY_TAXI && env->taxi_use_table) {
+    if (nm == "reset_alias") { off = env->taxi_alias_off; bytes = (int64_t)c.taxi_n_valid * 8; }
+  } else if (c.family == GPT_FAMILY_ROOMS) {
+    if (nm == "slip_alias") { off = env->rl.alias_off; bytes = (int64_t)c.rooms_n_actions * 64; }
+    if (nm == "spawn_cells" || nm == "goal_cells") { off = env->rl.valid_off; bytes = (int64_t)env->rl.n_valid * 2; }
+  } else if (c.family == GPT_FAMILY_MSROOMS) {
+    if (nm == "slip_alias") { off = env->ms.alias_off; bytes = (int64_t)c.rooms_n_actions * 64; }
+    if (nm == "spawn_cells") { off = env->ms.avalid_off; bytes = (int64_t)env->ms.n_agent * 2; }
+    if (nm == "goal_cells") { off = env->ms.gvalid_off; bytes = (int64_t)env->ms.n_goal * 2; }
+  }
+  if (off < 0) return fail(GPT_E_ARG, "gpt_table_read: this env has no table named " + nm);
+  *n_bytes = bytes;
+  if (!host_out) return GPT_OK;   // size query
+  if (capacity_bytes < bytes) return fail(GPT_E_ARG, "gpt_table_read: host buffer too small");
+  cudaError_t e = cudaSetDevice(c.device);
+  if (e == cudaSuccess) e = cudaMemcpy(host_out, env->d_blob + off, (size_t)bytes, cudaMemcpyDeviceToHost);
+  return e == cudaSuccess ? GPT_OK : cuda_fail(e, "cudaMemcpy(table)");
+}
+
+int gpt_check_actions(gpt_env* env, const void* actions, void* stream, int64_t* n_bad) {
+  if (!env || !actions || !n_bad) return fail(GPT_E_ARG, "gpt_check_actions: NULL argument");
+  const gpt_config& c = env->cfg;
+  int n = 0;
+  switch (c.family) {
+    case GPT_FAMILY_TAXI: n = 5; break;
+    case GPT_FAMILY_ROOMS: case GPT_FAMILY_MSROOMS: n = c.rooms_n_actions; break;
+    case GPT_FAMILY_CROOMS: n = env->action_dtype == GPT_DT_I8 ? c.rooms_n_actions : 0; break;
+    case GPT_FAMILY_CAR: n = c.car_num_actions; break;
+    default: n = 0;
+  }
+  *n_bad = 0;
+  if (n <= 0 || env->action_dtype != GPT_DT_I8) return GPT_OK;   // continuous actions: nothing to range-check
+  cudaError_t e = cudaSetDevice(c.device);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaSetDevice");
+  if (!env->d_bad) {
+    e = cudaMalloc((void**)&env->d_bad, sizeof(unsigned long long));
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc(action check)");
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  e = cudaMemsetAsync(env->d_bad, 0, sizeof(unsigned long long), st);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(action check)");
+  const int64_t B = c.num_envs;
+  count_bad_actions_kernel<<<(unsigned)((B + 255) / 256 < 1184 ? (B + 255) / 256 : 1184), 256, 0, st>>>((const int8_t*)actions, B, n, env->d_bad);
+  env->launches += 1;
+  unsigned long long bad = 0;
+  e = cudaGetLastError();
+  if (e == cudaSuccess) e = cudaMemcpyAsync(&bad, env->d_bad, sizeof(bad), cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  if (e != cudaSuccess) return cuda_fail(e, "gpt_check_actions");
+  *n_bad = (int64_t)bad;
+  return GPT_OK;
+}
 
 }  // extern "C"

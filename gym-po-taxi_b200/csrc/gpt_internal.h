@@ -25,6 +25,7 @@ struct HostPath {  // gpt_step_host(): chunked H2D -> step -> D2H pipeline
   static constexpr int kStreams = 4;
   cudaStream_t streams[kStreams] = {};
   cudaEvent_t done[kStreams] = {};
+  cudaEvent_t fork = nullptr;   // recorded on the caller's stream: the internal streams wait for it
   void* d_actions = nullptr;  // device staging for the host actions (capacity rows)
   int n_chunks = 2;
   bool ready = false;
@@ -47,6 +48,7 @@ struct gpt_env {
   // graph mode (gpt_set_graph_mode): the Philox step counter lives in device memory and a tick kernel advances it
   bool graph_mode = false;
   uint64_t* d_counter = nullptr;
+  unsigned long long* d_bad = nullptr;   // gpt_check_actions scratch
   gpt::HostPath host;
 
   // ---- taxi ----

@@ -8,6 +8,7 @@ libgpt_b200.so's fused kernels.
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import numpy as np
 import torch
@@ -24,6 +25,11 @@ _NUMPY_DTYPES = {
     N.DT_F64: np.float64,
 }
 
+
+#: GPT_DEBUG_ACTIONS=1: range-check discrete actions before every step and raise IndexError like the reference
+#: (numpy fancy indexing, extended_taxi.py:248 / rooms.py:210); the hot kernels only mask the action byte.  Costs a
+#: device synchronisation per step — a debugging aid, off by default.
+DEBUG_ACTIONS = os.environ.get("GPT_DEBUG_ACTIONS", "0") not in ("", "0")
 
 # raw cudaStream_t of torch's current stream without building a Stream object (about 1 us cheaper per step)
 _raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
@@ -122,6 +128,40 @@ class DeviceVecEnv:
     def _on_device(self):
         return torch.cuda.device(self.device)
 
+    def _n_discrete_actions(self):
+        """Number of discrete actions (None for continuous-action envs) — used by the debug range check."""
+        if self._action_dtype is not torch.int8:
+            return None
+        space = getattr(self, "single_action_space", None)
+        return getattr(space, "n", None)
+
+    def _debug_check_actions(self, actions):
+        n = self._n_discrete_actions()
+        if n is None:
+            return
+        t = actions if isinstance(actions, torch.Tensor) else torch.as_tensor(np.asarray(actions))
+        t = t[: self.num_envs]
+        if t.numel() and bool(((t < 0) | (t >= n)).any()):   # before any narrowing cast to int8
+            bad = t[(t < 0) | (t >= n)][0].item()
+            raise IndexError(f"index {bad} is out of bounds for axis 0 with size {n}")
+
+    def check_actions(self, actions: torch.Tensor) -> int:
+        """Number of entries of an int8 device action tensor ``[capacity]`` outside ``[0, n)`` (``gpt_check_actions``;
+        synchronises the stream)."""
+        bad = C.c_int64()
+        with self._on_device():
+            N.check(N.lib.gpt_check_actions(self._h, C.c_void_p(actions.data_ptr()), self._stream(), C.byref(bad)))
+        return bad.value
+
+    def read_table(self, name: str, dtype) -> np.ndarray:
+        """Host copy of one of the handle's static device tables (``gpt_table_read``; diagnostics / parity tests)."""
+        n = C.c_int64()
+        N.check(N.lib.gpt_table_read(self._h, name.encode(), None, 0, C.byref(n)))
+        buf = np.empty(n.value, dtype=np.uint8)
+        with self._on_device():
+            N.check(N.lib.gpt_table_read(self._h, name.encode(), buf.ctypes.data_as(C.c_void_p), buf.nbytes, C.byref(n)))
+        return buf.view(dtype)
+
     def _device_actions(self, actions):
         t = actions
         if not isinstance(t, torch.Tensor):
@@ -156,6 +196,8 @@ class DeviceVecEnv:
         overwritten by the next ``step`` — ``clone()`` to keep them.
         """
         a = actions
+        if DEBUG_ACTIONS:
+            self._debug_check_actions(actions)
         # fast path: a contiguous device tensor of the action dtype with `capacity` rows goes straight to the library
         if not (type(a) is torch.Tensor and a.dtype is self._action_dtype and a.shape == self._action_shape_cap
                 and a.device == self.device and a.is_contiguous()):
@@ -220,7 +262,7 @@ class DeviceVecEnv:
             }
             self._host_np = {k: v.numpy() for k, v in self._host.items()}
             self._host_io = N.GptHostIO(*(C.c_void_p(self._host[k].data_ptr())
-                                          for k in ("actions", "obs", "reward", "terminated", "truncated")))
+                                          for k in ("actions", "obs", "reward", "terminated", "truncated")), None)
         return self._host_np
 
     def host_action_buffer(self) -> np.ndarray:
@@ -263,9 +305,14 @@ class DeviceVecEnv:
             addr = self._pinned_pointer(actions)
             if addr is not None:
                 io = N.GptHostIO(C.c_void_p(addr), self._host_io.obs, self._host_io.reward, self._host_io.terminated,
-                                 self._host_io.truncated)
+                                 self._host_io.truncated, None)
             else:
                 np.copyto(hn["actions"], actions, casting="unsafe")
+        if DEBUG_ACTIONS:
+            self._debug_check_actions(actions)
+        # the library orders its internal streams behind (and the caller's stream after) the work on torch's current
+        # stream: reset() / step() / set_state() followed by step_host() is race free
+        io.stream = self._stream()
         with self._on_device():
             N.check(N.lib.gpt_step_host(self._h, C.byref(io)))
         return (self._shape_obs(hn["obs"]), hn["reward"], hn["terminated"].view(np.bool_),

@@ -11,7 +11,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("GPT_B200_LIB", os.path.join(_HERE, "..", "lib", "libgpt_b200.so"))
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 ENV_ALIGN = 512
 
 FAMILY_TAXI, FAMILY_ROOMS, FAMILY_CROOMS, FAMILY_TAG, FAMILY_CAR, FAMILY_MSROOMS = 0, 1, 2, 3, 4, 5
@@ -58,7 +58,7 @@ class GptArrayDesc(C.Structure):
 
 class GptHostIO(C.Structure):
     _fields_ = [("actions", C.c_void_p), ("obs", C.c_void_p), ("reward", C.c_void_p),
-                ("terminated", C.c_void_p), ("truncated", C.c_void_p)]
+                ("terminated", C.c_void_p), ("truncated", C.c_void_p), ("stream", C.c_void_p)]
 
 
 class GptWrapIO(C.Structure):
@@ -99,6 +99,8 @@ SIGNATURES = {
     "gpt_last_error": (C.c_char_p, []),
     "gpt_abi_version": (C.c_int, []),
     "gpt_launch_count": (C.c_int64, [C.c_void_p]),
+    "gpt_check_actions": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_int64)]),
+    "gpt_table_read": (C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_int64, C.POINTER(C.c_int64)]),
 }
 
 

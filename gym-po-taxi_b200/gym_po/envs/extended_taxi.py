@@ -253,6 +253,9 @@ class TaxiVecEnv(DeviceVecEnv):
 
     def set_state(self, s, elapsed, ndrop):
         b = self.num_envs
+        s = np.asarray(s)
+        if s.size and (s.min() < 0 or s.max() >= self.ns):   # the kernels index their tables with it unchecked
+            raise ValueError(f"set_state: state ids must be in [0, {self.ns})")
         self._arrays["s"][:b].copy_(torch.as_tensor(np.asarray(s)).to(torch.int32))
         self._arrays["elapsed"][:b].copy_(torch.as_tensor(np.asarray(elapsed)).to(torch.int32))
         self._arrays["ndrop"][:b].copy_(torch.as_tensor(np.asarray(ndrop)).to(torch.uint8))
@@ -278,7 +281,7 @@ class TaxiVecEnv(DeviceVecEnv):
         s = self.s[torch.as_tensor(idx, device=self.device)].cpu().numpy()
         name = None
         last = getattr(self, "_last_actions", None)
-        if last is not None and not bool(self._terminated[0] | self._truncated[0]):   # reference :280
+        if last is not None and not bool(self._terminated[0]):   # cleared on done[0] = terminated only (reference :280)
             name = self.ACTION_NAMES[int(torch.as_tensor(last).reshape(-1)[0])]
         img = render_taxi(self._map_rows, s, self.nlocs, self.np_locs, self.cols, self.hansen, name)
         if self.render_mode == "human":  # pragma: no cover - needs a display

@@ -161,6 +161,9 @@ class RoomsEnv(DeviceVecEnv):
     def set_state(self, agent, goal, elapsed):
         b, w = self.num_envs, int(self.grid.shape[1])
         agent = np.asarray(agent)
+        for name, yx in (("agent", agent),) + ((("goal", np.asarray(goal)),) if self.fixed_goal is None else ()):
+            if yx.size and (yx.min() < 0 or (yx[:, 0] >= self.grid.shape[0]).any() or (yx[:, 1] >= w).any()):
+                raise ValueError(f"set_state: {name} positions must lie inside the {self.grid.shape[0]}x{w} grid")
         self._arrays["pos"][:b].copy_(torch.as_tensor(agent[:, 0] * w + agent[:, 1]).to(torch.int16))
         if self.fixed_goal is None:
             goal = np.asarray(goal)

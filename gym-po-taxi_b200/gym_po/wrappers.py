@@ -8,8 +8,10 @@ The reference's author stacks gymnasium's ``RecordEpisodeStatistics`` and ``Norm
     info["episode"]["r"], info["episode"]["l"], info["_episode"]      # device tensors
 
 — but run as fused CUDA kernels (csrc/gpt_wrappers.cu) on the env's own output tensors, on the same stream as the
-step: nothing is copied to the host.  Semantics follow gymnasium 0.27-0.29 (restated in oracle/wrappers.py); the
-normalised reward is float32 (gymnasium returns float64).  ``stats()`` gives whole-job episode statistics, summed
+step: nothing is copied to the host.  Semantics follow gymnasium 0.29 (``returns = returns*gamma*(1-terminated) +
+reward``; 0.27 / 0.28 instead zero the returns on terminated|truncated AFTER normalising) as restated in
+oracle/wrappers.py — gymnasium itself is not available here, so this parity is unpinned; the normalised reward is
+float32 (gymnasium returns float64).  ``stats()`` gives whole-job episode statistics, summed
 over ranks with one NCCL all-reduce of an 8-double vector (the only collective on this path).
 
 CUDA graphs: ``RecordEpisodeStatistics.step`` can be captured together with a graph-mode env (its launch has no
@@ -76,6 +78,25 @@ class _DeviceWrapper:
     def reset(self, **kwargs):
         return self.env.reset(**kwargs)
 
+    # every stepping entry point goes through the wrapper's kernel; the multi-step / host-buffer paths would skip it
+    # (statistics and the return RMS would silently stop updating), so they are refused instead of forwarded
+    def _post(self, result):
+        raise NotImplementedError
+
+    def step(self, actions):
+        return self._post(self.env.step(actions))
+
+    def step_dlpack(self, actions):
+        return self._post(self.env.step_dlpack(actions))
+
+    def step_many(self, *a, **k):
+        raise NotImplementedError(f"{type(self).__name__}.step_many would bypass the wrapper kernel: call step() per step, "
+                                  "or use env.unwrapped.step_many() and forgo the wrapper's statistics")
+
+    def step_host(self, *a, **k):
+        raise NotImplementedError(f"{type(self).__name__}.step_host would bypass the wrapper kernel: call step() with "
+                                  "device actions, or use env.unwrapped.step_host()")
+
     def _launch(self, reward, terminated, truncated):
         """reward / terminated / truncated: views of tensors with ``capacity`` rows (the env's output arrays)."""
         for name, t in (("reward", reward), ("terminated", terminated), ("truncated", truncated)):
@@ -107,8 +128,8 @@ class RecordEpisodeStatistics(_DeviceWrapper):
     def __init__(self, env):
         super().__init__(env)
 
-    def step(self, actions):
-        obs, reward, terminated, truncated, info = self.env.step(actions)
+    def _post(self, result):
+        obs, reward, terminated, truncated, info = result
         self._launch(reward, terminated, truncated)
         b = self.num_envs
         info = dict(info)
@@ -143,8 +164,8 @@ class NormalizeReward(_DeviceWrapper):
         super().__init__(env, gamma, epsilon)
         self.gamma, self.epsilon = gamma, epsilon
 
-    def step(self, actions):
-        obs, reward, terminated, truncated, info = self.env.step(actions)
+    def _post(self, result):
+        obs, reward, terminated, truncated, info = result
         self._launch(reward, terminated, truncated)
         return obs, self._t["norm_reward"][: self.num_envs], terminated, truncated, info
 

@@ -21,7 +21,12 @@
  *     The library never allocates or frees per-env memory and never allocates inside gpt_step().
  *     The handle owns only the packed static tables (map, wall bits, thresholds; <= 64 KB).
  *   - every per-env array has `capacity` rows, capacity = num_envs rounded up to GPT_ENV_ALIGN;
- *     rows >= num_envs are padding the kernels may read and write (keep them initialised to 0).
+ *     rows >= num_envs are padding the kernels may read and write.
+ *   - STATE arrays index the kernels' shared-memory tables: they must hold in-range values.  gpt_reset() clears
+ *     every bound STATE array itself before it runs, so freshly allocated memory is fine as long as gpt_reset() is
+ *     the first call; a caller that calls gpt_step() without a reset (legal in the reference) or writes the state
+ *     arrays directly (set_state) must zero-initialise them / keep the values in range — the hot kernels do not
+ *     range-check.
  *   - calls on one handle are not thread-safe (neither is the reference); handles are independent.
  *   - gpt_reset / gpt_step / gpt_step_many are ASYNCHRONOUS on the given CUDA stream; no hidden
  *     device synchronisation.  `stream` is a cudaStream_t passed as void* (0 = legacy default).
@@ -42,7 +47,7 @@ extern "C" {
 #define GPT_API
 #endif
 
-#define GPT_ABI_VERSION 1
+#define GPT_ABI_VERSION 2
 #define GPT_ENV_ALIGN 512 /* envs per warp tile: 32 lanes x 16 envs */
 
 /* error codes */
@@ -169,6 +174,9 @@ typedef struct gpt_host_io {
   float* reward;       /* out: [B] */
   uint8_t* terminated; /* out: [B] */
   uint8_t* truncated;  /* out: [B] */
+  void* stream;        /* the caller's cudaStream_t (0 = legacy default): the call's internal copy/compute streams
+                          start after all work queued on it (gpt_reset, gpt_step, state uploads) and it is made to
+                          wait for them, so step_host may be mixed freely with the stream-asynchronous calls */
 } gpt_host_io;
 
 /* --- lifecycle ----------------------------------------------------------------------------
@@ -252,6 +260,16 @@ GPT_API int gpt_wrap_state_ptr(gpt_wrap* w, void** device_ptr, int32_t* rms_offs
 GPT_API int64_t gpt_wrap_launch_count(const gpt_wrap* w);
 
 /* --- diagnostics -------------------------------------------------------------------------- */
+/* Debug range check of a discrete action array [capacity] int8 (the reference raises IndexError for an action
+ * outside [0, n), extended_taxi.py:248 / rooms.py:210; the hot kernels mask the byte instead): *n_bad = number of
+ * the first num_envs bytes outside [0, n).  Synchronises `stream`.  Continuous-action envs report 0. */
+GPT_API int gpt_check_actions(gpt_env* env, const void* actions, void* stream, int64_t* n_bad);
+/* Copies one of the handle's static device tables to host memory, so that a test can rebuild on the host the
+ * random draws a Philox-mode kernel consumes from the very tables the kernel reads.  Names: "reset_alias" (Taxi:
+ * uint32 pairs {threshold, state | alias_state << 16} per valid state), "slip_alias" (ROOMS / MSROOMS: per intended
+ * action 8 columns of uint32 pairs {threshold, dir | alias_dir << 8}), "spawn_cells" / "goal_cells" (uint16 flat
+ * cell ids).  host_out = NULL only queries *n_bytes. */
+GPT_API int gpt_table_read(const gpt_env* env, const char* name, void* host_out, int64_t capacity_bytes, int64_t* n_bytes);
 GPT_API const char* gpt_last_error(void);
 GPT_API int gpt_abi_version(void);
 /* number of kernel launches issued by this handle since creation (bench.py's gpu_launches) */

@@ -10,6 +10,11 @@ over PCG64).  The call sites and their order are:
 * Gaussian noise       ``normal(scale=s, size=shape)``                        rooms/crooms.py:178,194,324
 * tag target           ``integers(4)``                                        ant_tag.py:109
 * car respawn          ``uniform(-0.2, 0.2, (b,1))``, ``choice([-1,1], b)`` x2  car_flag.py:100-110
+
+Every call also carries keyword *context* (``where`` = bool mask of the envs the draw is for, ``kind`` = which
+reference call site, ``action`` / ``cumsum`` for the slip).  ``GeneratorDraws`` and ``RecordedDraws`` ignore it — the
+reference's generator knows nothing about env indices; a per-env counter-based source (tests/philox_host.py, which
+rebuilds on the host the draws the Philox-mode CUDA kernels consume) needs it.
 """
 from __future__ import annotations
 
@@ -30,22 +35,27 @@ class GeneratorDraws:
     def reseed(self, seed):
         self.gen = make_generator(seed)
 
-    def multinomial_argmax(self, n, pvals, b):
-        return self.gen.multinomial(n, pvals, b).argmax(-1)
+    def multinomial_argmax(self, n, pvals, b, **ctx):
+        # row chunks: Generator.multinomial fills rows sequentially from the bit stream, so chunked calls return the
+        # same values as one call, without the reference's [b, ns] int64 temporary (16.8 GB at b = 2^22)
+        step = max(1, (1 << 24) // max(len(pvals), 1))
+        if b <= step:
+            return self.gen.multinomial(n, pvals, b).argmax(-1)
+        return np.concatenate([self.gen.multinomial(n, pvals, min(step, b - i)).argmax(-1) for i in range(0, b, step)])
 
-    def integers(self, high, size=None):
+    def integers(self, high, size=None, **ctx):
         return self.gen.integers(high, size=size)
 
-    def random(self, b):
+    def random(self, b, **ctx):
         return self.gen.random(b)
 
-    def choice(self, values, b):
+    def choice(self, values, b, **ctx):
         return self.gen.choice(values, b)
 
-    def normal(self, scale, size):
+    def normal(self, scale, size, **ctx):
         return self.gen.normal(scale=scale, size=size)
 
-    def uniform(self, low, high, size):
+    def uniform(self, low, high, size, **ctx):
         return self.gen.uniform(low, high, size)
 
 
@@ -75,22 +85,22 @@ class RecordedDraws:
             raise RuntimeError(f"draw {self.pos - 1} ({kind}): size {np.shape(v)} != requested {size}")
         return v.copy()
 
-    def multinomial_argmax(self, n, pvals, b):
+    def multinomial_argmax(self, n, pvals, b, **ctx):
         return self._next("multinomial_argmax", (b,))
 
-    def integers(self, high, size=None):
+    def integers(self, high, size=None, **ctx):
         return self._next("integers", () if size is None else (size,))
 
-    def random(self, b):
+    def random(self, b, **ctx):
         return self._next("random", (b,))
 
-    def choice(self, values, b):
+    def choice(self, values, b, **ctx):
         return self._next("choice", (b,))
 
-    def normal(self, scale, size):
+    def normal(self, scale, size, **ctx):
         return self._next("normal", size).reshape(size)
 
-    def uniform(self, low, high, size):
+    def uniform(self, low, high, size, **ctx):
         return self._next("uniform", size).reshape(size)
 
     @property

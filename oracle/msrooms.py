@@ -144,10 +144,10 @@ class MSRoomsOracle:
         if self.fixed_goal is not None:
             self.goal[mask] = self.fixed_goal
         else:
-            cells = self.rng.choice(self.goal_cells, b)
+            cells = self.rng.choice(self.goal_cells, b, where=mask, kind="reset_goal")
             self.goal[mask] = np.stack(np.unravel_index(cells, self.grid.shape), -1)
             self.draws["reset_goal"][mask] = cells
-        cells = self.rng.choice(self.agent_cells, b)
+        cells = self.rng.choice(self.agent_cells, b, where=mask, kind="reset_agent")
         self.agent[mask] = np.stack(np.unravel_index(cells, self.grid.shape), -1)
         self.draws["reset_agent"][mask] = cells
 
@@ -177,7 +177,7 @@ class MSRoomsOracle:
         action = np.asarray(action)
         self.draws = self._blank_draws()
         self.elapsed += 1
-        u = self.rng.random(self.num_envs)
+        u = self.rng.random(self.num_envs, kind="slip", action=action, cumsum=self.P.cumsum(axis=1))
         self.draws["u"][:] = u
         target = self.agent + self.dirs[slip_sample(self.P[action], u)]
         blocked = self.grid[target[:, 0], target[:, 1], target[:, 2]] == WALL

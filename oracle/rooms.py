@@ -190,10 +190,10 @@ class RoomsOracle:
         if self.fixed_goal is not None:
             self.goal[mask] = self.fixed_goal
         else:
-            cells = self.rng.choice(self.valid_cells, b)
+            cells = self.rng.choice(self.valid_cells, b, where=mask, kind="reset_goal")
             self.goal[mask] = np.stack(np.unravel_index(cells, self.grid.shape), -1)
             self.draws["reset_goal"][mask] = cells
-        cells = self.rng.choice(self.valid_cells, b)
+        cells = self.rng.choice(self.valid_cells, b, where=mask, kind="reset_agent")
         self.agent[mask] = np.stack(np.unravel_index(cells, self.grid.shape), -1)
         self.draws["reset_agent"][mask] = cells
 
@@ -223,7 +223,7 @@ class RoomsOracle:
         action = np.asarray(action)
         self.draws = self._blank_draws()
         self.elapsed += 1
-        u = self.rng.random(self.num_envs)
+        u = self.rng.random(self.num_envs, kind="slip", action=action, cumsum=self.P.cumsum(axis=1))
         self.draws["u"][:] = u
         actual = slip_sample(self.P[action], u)
         target = self.agent + self.dirs[actual]

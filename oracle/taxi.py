@@ -157,13 +157,13 @@ class TaxiOracle:
         respawn = goal_move & ~(terminated | truncated)
         b = int(respawn.sum())
         if b:
-            new_p = self.rng.integers(self.nlocs, size=b)
-            new_d = self.rng.integers(self.nlocs, size=b)
+            new_p = self.rng.integers(self.nlocs, size=b, where=respawn, kind="new_p")
+            new_d = self.rng.integers(self.nlocs, size=b, where=respawn, kind="new_d")
             while True:
                 clash = new_p == new_d
                 if not clash.any():
                     break
-                new_d[clash] = self.rng.integers(self.nlocs, size=int(clash.sum()))
+                new_d[clash] = self.rng.integers(self.nlocs, size=int(clash.sum()), kind="redraw_d")
             self.s[respawn] = self.encode(r[respawn], c[respawn], new_p, new_d)
             self.draws["new_p"][respawn] = new_p
             self.draws["new_d"][respawn] = new_d
@@ -175,7 +175,7 @@ class TaxiOracle:
         """extended_taxi.py:344-352"""
         b = int(mask.sum())
         if b:
-            fresh = self.rng.multinomial_argmax(self.ns, self.state_distribution, b)
+            fresh = self.rng.multinomial_argmax(self.ns, self.state_distribution, b, where=mask, kind="reset_state")
             self.s[mask] = fresh
             self.elapsed[mask] = 0
             self.ndrop[mask] = 0

@@ -97,7 +97,7 @@ def test_exhaustive_cell_x_slipped_action(action_type, n_act, obs_type, goal_xyz
     b = len(cases)
 
     class Fixed(oracle.GeneratorDraws):
-        def random(self, n):
+        def random(self, n, **ctx):
             return u.copy()
 
     kw = dict(grid_z=floors, obs_type=obs_type, action_type=action_type, goal_xyz=goal_xyz)

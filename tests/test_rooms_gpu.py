@@ -121,7 +121,7 @@ def test_exhaustive_cell_x_slipped_action(action_type, n_act):
         b = len(cases)
 
         class Fixed(oracle.GeneratorDraws):
-            def random(self, n):
+            def random(self, n, **ctx):
                 return u.copy()
 
         kw = dict(layout=layout, obs_type="hansen8", action_type=action_type, goal_xy=(0, 0))
