@@ -595,7 +595,7 @@ int gpt_table_read(const gpt_env* env, const char* name, void* host_out, int64_t
   }
   if (off < 0) return fail(GPT_E_ARG, "gpt_table_read: this env has no table named " + nm);
   *n_bytes = bytes;
-  if (!host_out) return GPT_OK;   // size query
+  if (!host_out || bytes == 0) return GPT_OK;   // size query / empty table (e.g. goal_cells of a fixed-goal env)
   if (capacity_bytes < bytes) return fail(GPT_E_ARG, "gpt_table_read: host buffer too small");
   cudaError_t e = cudaSetDevice(c.device);
   if (e == cudaSuccess) e = cudaMemcpy(host_out, env->d_blob + off, (size_t)bytes, cudaMemcpyDeviceToHost);

@@ -768,6 +768,9 @@ int taxi_launch(gpt_env* env, const LaunchArgs& a) {
     grid = (int)(((int64_t)a.n_tiles * kTileEnvs + envs_per_cta - 1) / envs_per_cta);
     kernel = (const void*)km;
     args[0] = (void*)&M;
+    // tuning knob: extra dynamic shared memory per CTA lowers the resident CTAs per SM (wave quantisation experiments)
+    static const int pad_kb = getenv("GPT_TAXI_PAD_KB") ? atoi(getenv("GPT_TAXI_PAD_KB")) : 0;
+    smem += (size_t)pad_kb * 1024;
   } else if (env->taxi_use_table) {
     using K = void (*)(const TaxiParams);
     // launch shape: GPT_TAXI_SHAPE = "<quads per thread>x<threads>" (tuning knob; default 2x128)

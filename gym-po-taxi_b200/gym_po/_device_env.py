@@ -158,6 +158,8 @@ class DeviceVecEnv:
         n = C.c_int64()
         N.check(N.lib.gpt_table_read(self._h, name.encode(), None, 0, C.byref(n)))
         buf = np.empty(n.value, dtype=np.uint8)
+        if n.value == 0:
+            return buf.view(dtype)
         with self._on_device():
             N.check(N.lib.gpt_table_read(self._h, name.encode(), buf.ctypes.data_as(C.c_void_p), buf.nbytes, C.byref(n)))
         return buf.view(dtype)

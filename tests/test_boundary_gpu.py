@@ -37,10 +37,9 @@ def test_step_host_is_ordered_after_the_callers_stream(family):
     got = [env.step_host(acts[0])]         # must wait for that reset
     got[0] = [np.array(x) for x in got[0][:4]]
     _busy()
-    o = env.step(torch.as_tensor(acts[1], device=DEV))   # device step behind a sleep ...
-    got.append(None)
+    o = [x.clone() for x in env.step(torch.as_tensor(acts[1], device=DEV))[:4]]   # device step behind a sleep ...
     h = env.step_host(acts[2])                           # ... and the host step must see its state
-    got[1] = [x.cpu().numpy().copy() for x in o[:4]]
+    got.append([x.cpu().numpy() for x in o])
     got.append([np.array(x) for x in h[:4]])
     for t in (3, 4, 5):
         o = env.step(torch.as_tensor(acts[t], device=DEV))   # the caller's stream waits for the host path
