@@ -591,7 +591,7 @@ int gpt_table_read(const gpt_env* env, const char* name, void* host_out, int64_t
   } else if (c.family == GPT_FAMILY_MSROOMS) {
     if (nm == "slip_alias") { off = env->ms.alias_off; bytes = (int64_t)c.rooms_n_actions * 64; }
     if (nm == "spawn_cells") { off = env->ms.avalid_off; bytes = (int64_t)env->ms.n_agent * 2; }
-    if (nm == "goal_cells") { off = env->ms.gvalid_off; bytes = (int64_t)env->ms.n_goal * 2; }
+    if (nm == "goal_cells") { off = env->ms.gvalid_off; bytes = c.ms_goal_cell < 0 ? (int64_t)env->ms.n_goal * 2 : 0; }   // fixed goal: no table
   }
   if (off < 0) return fail(GPT_E_ARG, "gpt_table_read: this env has no table named " + nm);
   *n_bytes = bytes;

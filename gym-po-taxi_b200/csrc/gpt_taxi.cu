@@ -280,7 +280,7 @@ __device__ __noinline__ uint32_t taxi_fix(const TaxiParams& P, const uint2* alia
 // boundary: the kernel neither loads nor tracks it and stores 0 (a counter injected with set_state is ignored here;
 // the single-step kernel keeps the reference's arithmetic).
 template <bool STATS, int QPT, int THREADS, bool ONE>
-__global__ void __launch_bounds__(THREADS, STATS ? 1 : GPT_TAXI_MINB_MULTI) taxi_table_multi_kernel(const __grid_constant__ TaxiMultiParams M) {
+__global__ void __launch_bounds__(THREADS, STATS ? 1 : GPT_TAXI_MINB_MULTI * 128 / THREADS) taxi_table_multi_kernel(const __grid_constant__ TaxiMultiParams M) {
   constexpr bool REPLAY = false;   // replayed draws are per step: replay mode uses the single-step kernel
   const TaxiParams& P = M.p;
   const int32_t n_steps = M.n_steps;
@@ -762,8 +762,18 @@ int taxi_launch(gpt_env* env, const LaunchArgs& a) {
     const bool one = c.taxi_n_dropoffs == 1;
     KM km = c.track_stats ? (one ? (KM)taxi_table_multi_kernel<true, 2, 128, true> : (KM)taxi_table_multi_kernel<true, 2, 128, false>)
                           : (one ? (KM)taxi_table_multi_kernel<false, 2, 128, true> : (KM)taxi_table_multi_kernel<false, 2, 128, false>);
-    const int qpt = 2;
+    int qpt = 2;
     threads = 128;
+    // tuning knob GPT_TAXI_MULTI_SHAPE = <quads per thread><threads> (default 2128)
+    static const int mshape = getenv("GPT_TAXI_MULTI_SHAPE") ? atoi(getenv("GPT_TAXI_MULTI_SHAPE")) : 0;
+    if (!c.track_stats && one) {
+      switch (mshape) {
+        case 1128: km = (KM)taxi_table_multi_kernel<false, 1, 128, true>; qpt = 1; threads = 128; break;
+        case 1256: km = (KM)taxi_table_multi_kernel<false, 1, 256, true>; qpt = 1; threads = 256; break;
+        case 2256: km = (KM)taxi_table_multi_kernel<false, 2, 256, true>; qpt = 2; threads = 256; break;
+        default: break;
+      }
+    }
     const int64_t envs_per_cta = (int64_t)threads * kQuad * qpt;
     grid = (int)(((int64_t)a.n_tiles * kTileEnvs + envs_per_cta - 1) / envs_per_cta);
     kernel = (const void*)km;
