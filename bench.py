@@ -308,6 +308,51 @@ def timed_blocks(w, k, world, dev, min_total_ms, min_repeats=7, max_repeats=400)
     return [float(x) for x in ms.tolist()], launches
 
 
+def pcie_ceiling(env, host_actions, b, world, dev, reps):
+    """Copy-only lower bound of one end-to-end step (see the call site).  Max over ranks."""
+    import torch
+    import torch.distributed as dist
+    hn = env._ensure_host()
+    host = env._host                                    # pinned torch tensors behind step_host's numpy views
+    names = ("obs", "reward", "terminated", "truncated")
+    d_out = [env._arrays[n][:b] for n in names]
+    d_act = torch.empty_like(host["actions"], device=dev)
+    h_act = torch.from_numpy(host_actions[0])           # pinned (pinned_actions)
+    s1, s2 = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+
+    def step():
+        with torch.cuda.stream(s1):
+            d_act.copy_(h_act, non_blocking=True)
+        with torch.cuda.stream(s2):
+            for n, d in zip(names, d_out):
+                host[n].copy_(d, non_blocking=True)
+        s1.synchronize()
+        s2.synchronize()
+
+    def timed(fn, n):
+        for _ in range(2):
+            fn()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(n):
+            fn()
+        torch.cuda.synchronize()
+        t = torch.tensor([(time.perf_counter() - t0) / n], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    step_s = timed(step, reps)
+    nbytes = sum(host[n].numel() * host[n].element_size() for n in names)
+    big_h = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
+    big_d = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    d2h_s = timed(lambda: (big_h.copy_(big_d, non_blocking=True), torch.cuda.current_stream().synchronize()), max(3, reps // 2))
+    h2d_s = timed(lambda: (big_d.copy_(big_h, non_blocking=True), torch.cuda.current_stream().synchronize()), max(3, reps // 2))
+    return {"step_s": step_s, "raw_d2h_gbs": nbytes / d2h_s / 1e9, "raw_h2d_gbs": nbytes / h2d_s / 1e9}
+
+
 def device_numbers(w, k, ms_list, launches, world, peak):
     """env-steps/s and the roofline figures of one timed leg (median repeat)."""
     wl = w.wl
@@ -403,6 +448,10 @@ def run_b200(args):
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_s = statistics.median(te.tolist())
     h2d, d2h = env.host_bytes_per_step()
+    # ---- what the box's PCIe / host memory gives for the SAME bytes with no kernel in between: all ranks at once, the
+    # step's H2D (actions) and D2H (obs, reward, terminated, truncated) copies on two streams, synchronised per step
+    # like step_host; and one large contiguous copy each way (raw link rate)
+    pcie = pcie_ceiling(env, host_actions, b, world, dev, max(5, min(e2e_k, 50)))
     clocks_head = sampler.summary()
     slots, footprint = w.slots, w.footprint
     # episode statistics all-reduce (the only collective on this path; logging cadence, outside the timed region)
@@ -473,7 +522,12 @@ def run_b200(args):
             "e2e": {"value": total_envs * e2e_k / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d * world,
                     "d2h_bytes_per_step": d2h * world, "steps": e2e_k, "repeats": e2e_reps,
                     "api": "env.step_host(numpy) -> gpt_step_host", "host_numa": numa,
-                    "pcie_gbs_achieved": (h2d + d2h) * world * e2e_k / e2e_s / 1e9},
+                    "pcie_gbs_achieved": (h2d + d2h) * world * e2e_k / e2e_s / 1e9,
+                    "pcie_bound": total_envs / pcie["step_s"], "frac_of_pcie": (total_envs * e2e_k / e2e_s) / (total_envs / pcie["step_s"]),
+                    "pcie_bound_note": "env-steps/s if a step were ONLY its host<->device copies (same pinned buffers, same sizes, all ranks at "
+                                       "once, two streams, synchronised per step); raw = one contiguous copy of the same total bytes each way",
+                    "pcie_copy_gbs": (h2d + d2h) * world / pcie["step_s"] / 1e9, "pcie_raw_h2d_gbs": pcie["raw_h2d_gbs"] * world,
+                    "pcie_raw_d2h_gbs": pcie["raw_d2h_gbs"] * world},
             "gpu_launches": launches * world,
             "clocks": clocks_head,
         }

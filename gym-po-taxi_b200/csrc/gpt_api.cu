@@ -583,7 +583,7 @@ int gpt_table_read(const gpt_env* env, const char* name, void* host_out, int64_t
   const gpt_config& c = env->cfg;
   const std::string nm(name);
   int64_t off = -1, bytes = 0;
-  if (c.family == GPT_FAMILY_TAXI && env->taxi_use_table) {
+  if (c.family == GPT_FAMILY_TAXI) {
     if (nm == "reset_alias") { off = env->taxi_alias_off; bytes = (int64_t)c.taxi_n_valid * 8; }
   } else if (c.family == GPT_FAMILY_ROOMS) {
     if (nm == "slip_alias") { off = env->rl.alias_off; bytes = (int64_t)c.rooms_n_actions * 64; }

@@ -52,7 +52,7 @@ struct gpt_env {
   gpt::HostPath host;
 
   // ---- taxi ----
-  uint32_t taxi_cdf_off = 0, taxi_vs_off = 0, taxi_rep_shift = 0, taxi_trans_off = 0, taxi_hobs_off = 0, taxi_alias_off = 0, taxi_trans16_off = 0, taxi_single_bytes = 0;
+  uint32_t taxi_rep_shift = 0, taxi_trans_off = 0, taxi_hobs_off = 0, taxi_alias_off = 0, taxi_trans16_off = 0, taxi_single_bytes = 0;
   bool taxi_use_table = false;
   int taxi_shape = 0;  // launch-shape tuning knob (GPT_TAXI_SHAPE), 0 = default
   // ---- rooms / crooms ----

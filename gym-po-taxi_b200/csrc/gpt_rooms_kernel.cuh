@@ -379,6 +379,9 @@ rooms_step_kernel(const __grid_constant__ RoomsParams P) {
   const int64_t orow = MULTI ? (int64_t)t * P.out_stride : 0;
   const uint64_t ctr = (DEVCTR ? ctr_dev : (((uint64_t)P.rng.step_hi << 32) | P.rng.step_lo)) + (uint32_t)t;   // Philox step counter of this step
   const uint32_t ctr_lo = (uint32_t)ctr, ctr_hi = (uint32_t)(ctr >> 32) & 0x00FFFFFFu;
+#ifdef GPT_EXPERIMENT_SHARE_PHILOX
+  uint4 slip_prev = make_uint4(0, 0, 0, 0);
+#endif
 #pragma unroll
   for (int j = 0; j < QPT; ++j) {
     const int64_t q = base + j * kQuadStride;
@@ -391,10 +394,18 @@ rooms_step_kernel(const __grid_constant__ RoomsParams P) {
     uint32_t o32b[4] = {0, 0, 0, 0}; // second word for 8-byte vector obs
 
     uint4 slip = make_uint4(0, 0, 0, 0);
+#ifdef GPT_EXPERIMENT_SHARE_PHILOX   // timing experiment only (wrong draws): one block per TWO quads
+    if (!REPLAY && (j & 1) == 0) {
+      const uint64_t gq = (uint64_t)(P.env_offset + q) >> 2;
+      slip_prev = philox4x32_10(make_uint4((uint32_t)gq, (uint32_t)(gq >> 32), ctr_lo, ctr_hi), P.rng);
+    }
+    slip = (j & 1) ? make_uint4(slip_prev.x >> 16, slip_prev.y >> 16, slip_prev.z >> 16, slip_prev.w >> 16) : make_uint4(slip_prev.x << 16, slip_prev.y << 16, slip_prev.z << 16, slip_prev.w << 16);
+#else
     if (!REPLAY) {  // one Philox block feeds the slip draws of the 4 envs of this quad
       const uint64_t gq = (uint64_t)(P.env_offset + q) >> 2;
       slip = philox4x32_10(make_uint4((uint32_t)gq, (uint32_t)(gq >> 32), ctr_lo, ctr_hi), P.rng);
     }
+#endif
     const uint32_t slipv[4] = {slip.x, slip.y, slip.z, slip.w};
 
     // ---- transition of the 4 envs: straight-line code, no branches, so the compiler can interleave the

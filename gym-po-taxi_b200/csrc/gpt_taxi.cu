@@ -12,7 +12,7 @@
 // 512 B (int32/float32 streams) or 128 B (byte streams) contiguous segment.
 //
 // Two kernels implement the same step:
-//   * taxi_table_kernel (used when ns <= 8192, i.e. both reference maps): the complete (state, action) ->
+//   * taxi_table_kernel (used when ns <= 2048, i.e. both reference maps): the complete (state, action) ->
 //     (next state, delivered?, illegal?) relation is tabulated on the host (ns x 6 uint16, 6 KB for the
 //     5x5 map) and lives in shared memory, so the per-env main path is ONE data-dependent LDS plus ~20
 //     ALU instructions.  The rare branches (autoreset ~0.5 % of env-steps, passenger respawn) are NOT in
@@ -26,7 +26,9 @@
 //         hansen_encodings, extended_taxi.py:102-114, which also decides motion — SURVEY.md A.1),
 //         bits 8-15 = index of the named location on that cell (0xFF none).  Replicated per lane
 //         (REP = 32) when small so that the data-dependent lookups are bank-conflict free.
-//     reset_cdf uint32[n_valid], valid_states uint16[n_valid]: Philox-mode autoreset sampler.
+//     alias uint2[n_valid]: Philox-mode autoreset sampler — Walker alias table of the law of
+//         argmax(multinomial(ns, uniform over the valid states)) (extended_taxi.py:348-350), built on the host from
+//         the thresholds in gpt_config.taxi_reset_cdf: {threshold, state | alias state << 16} per column.
 #include <cstdlib>
 
 #include "gpt_internal.h"
@@ -49,7 +51,7 @@ struct TaxiParams {
   const int8_t* rp_new_p;
   const int8_t* rp_new_d;
   const uint8_t* blob;
-  uint32_t blob_bytes, cdf_off, vs_off, rep_shift;
+  uint32_t blob_bytes, rep_shift;
   uint32_t trans_off, hobs_off;   // fused kernel: 32-bit transition table / per-state observation table offsets in the blob
   uint32_t trans16_off, alias_off, single_bytes;   // single-step kernel: compact table, reset alias table, bytes to stage
   FastDiv div_pd;                 // divide by (nlocs+1)*nlocs
@@ -64,8 +66,7 @@ struct TaxiParams {
 
 struct TaxiTables {
   const uint16_t* cell;
-  const uint32_t* cdf;
-  const uint16_t* valid;
+  const uint2* alias;
   uint32_t rep_shift, rep_lane;
   __device__ __forceinline__ uint32_t lookup(uint32_t c) const { return cell[(c << rep_shift) | rep_lane]; }
 };
@@ -116,13 +117,10 @@ __device__ __forceinline__ void taxi_env(const TaxiParams& P, const TaxiTables& 
       uint32_t fresh;
       if (REPLAY) {
         fresh = (uint32_t)P.rp_reset_state[env];
-      } else {  // inverse CDF of the law of argmax(multinomial(ns, uniform over valid states))
-        int lo = 0, hi = P.n_valid - 1;
-        while (lo < hi) {
-          const int mid = (lo + hi) >> 1;
-          if (rnd.x <= T.cdf[mid]) hi = mid; else lo = mid + 1;
-        }
-        fresh = T.valid[lo];
+      } else {  // the law of argmax(multinomial(ns, uniform over valid states)) through its alias table (as taxi_fix_inline)
+        const uint64_t w = (uint64_t)rnd.x * (uint32_t)P.n_valid;
+        const uint2 e = T.alias[(uint32_t)(w >> 32)];
+        fresh = ((uint32_t)w < e.x) ? (e.y & 0xFFFFu) : (e.y >> 16);
       }
       const uint32_t t = fdiv(fresh, P.div_nlocs);
       d = fresh - t * nlocs;
@@ -179,8 +177,7 @@ __global__ void __launch_bounds__(256) taxi_arith_kernel(const __grid_constant__
   stage_tables_wait(&bar);
   TaxiTables T;
   T.cell = reinterpret_cast<const uint16_t*>(smem);
-  T.cdf = reinterpret_cast<const uint32_t*>(smem + P.cdf_off);
-  T.valid = reinterpret_cast<const uint16_t*>(smem + P.vs_off);
+  T.alias = reinterpret_cast<const uint2*>(smem + P.alias_off);
   T.rep_shift = P.rep_shift;
   T.rep_lane = P.rep_shift ? lane : 0u;
 
@@ -240,7 +237,7 @@ struct TaxiMultiParams {
   int64_t out_stride;   // rows between consecutive steps' outputs (0 = overwrite in place)
 };
 
-// Rare branch, out of line (one copy per kernel): full reset (extended_taxi.py:344-352) or passenger respawn
+// Rare branch: full reset (extended_taxi.py:344-352) or passenger respawn
 // (:354-364) -> new state id.  `t` = step index inside a fused launch.
 template <bool REPLAY, bool DEVCTR = false>
 __device__ __forceinline__ uint32_t taxi_fix_inline(const TaxiParams& P, const uint2* alias, int64_t env, uint32_t t, uint32_t cur, bool full, uint64_t ctr_dev = 0) {
@@ -263,15 +260,7 @@ __device__ __forceinline__ uint32_t taxi_fix_inline(const TaxiParams& P, const u
   d += d >= p ? 1u : 0u;
   return (cell * (uint32_t)(P.nlocs + 1) + p) * (uint32_t)P.nlocs + d;
 }
-// out-of-line copy for the single-step kernel (its registers are dead at the call site)
-template <bool REPLAY>
-__device__ __noinline__ uint32_t taxi_fix(const TaxiParams& P, const uint2* alias, int64_t env, uint32_t t, uint32_t cur, bool full) {
-  return taxi_fix_inline<REPLAY>(P, alias, env, t, cur, full);
-}
-
-#ifndef GPT_TAXI_FIX_INLINE_SINGLE
-#define GPT_TAXI_FIX_INLINE_SINGLE 1   // measured: 253.9 -> 256.4 G (0 = out-of-line call)
-#endif
+// (inlined in the single-step kernel too: measured 253.9 -> 256.4 G against an out-of-line call)
 #ifndef GPT_TAXI_MINB_MULTI
 #define GPT_TAXI_MINB_MULTI 6   // 72 registers; measured on B200 (2^22 envs, 8 steps per launch): 4 -> 412 G, 6 -> 417 G, 7 -> 418 G
 #endif
@@ -533,11 +522,7 @@ __global__ void __launch_bounds__(THREADS, (STATS || QPT > 2) ? 1 : 1280 / THREA
     int32_t cur = 0;
 #pragma unroll
     for (int i = 0; i < 4 * QPT; ++i) cur = i == b ? keep_s[i] : cur;
-#if GPT_TAXI_FIX_INLINE_SINGLE
     const uint32_t fresh = taxi_fix_inline<REPLAY, DEVCTR>(P, alias, env, 0u, (uint32_t)cur, full, ctr_dev);   // same sampler as the fused kernel
-#else
-    const uint32_t fresh = taxi_fix<REPLAY>(P, alias, env, 0u, (uint32_t)cur, full);   // same sampler as the fused kernel
-#endif
     if (full) {
       P.elapsed[env] = 0;
       P.ndrop[env] = 0;
@@ -581,6 +566,32 @@ int taxi_create(gpt_env* env, const gpt_config* c) {
     if (c->taxi_reset_cdf) cdf[i] = c->taxi_reset_cdf[i];
   }
   cdf.back() = 0xFFFFFFFFu;
+  // Walker alias table of the reset law (Philox mode): column j = {threshold, valid[j] | valid[alias_j] << 16}
+  std::vector<uint32_t> alias((size_t)c->taxi_n_valid * 2, 0u);
+  {
+    const int n = c->taxi_n_valid;
+    std::vector<double> q(n);
+    for (int j = 0; j < n; ++j) {
+      const double hi = j == n - 1 ? 4294967296.0 : (double)cdf[j] + 1.0, lo = j == 0 ? 0.0 : (double)cdf[j - 1] + 1.0;
+      q[j] = (hi > lo ? hi - lo : 0.0) / 4294967296.0 * n;
+    }
+    std::vector<int> small, large, al(n);
+    std::vector<double> pr(n, 1.0);
+    for (int j = 0; j < n; ++j) { al[j] = j; (q[j] < 1.0 ? small : large).push_back(j); }
+    while (!small.empty() && !large.empty()) {
+      const int sidx = small.back(), lidx = large.back();
+      small.pop_back();
+      pr[sidx] = q[sidx];
+      al[sidx] = lidx;
+      q[lidx] = (q[lidx] + q[sidx]) - 1.0;
+      if (q[lidx] < 1.0) { large.pop_back(); small.push_back(lidx); }
+    }
+    for (int j = 0; j < n; ++j) {
+      const double t = pr[j] * 4294967296.0;
+      alias[(size_t)j * 2] = t >= 4294967295.0 ? 0xFFFFFFFFu : (t <= 0 ? 0u : (uint32_t)t);
+      alias[(size_t)j * 2 + 1] = (uint32_t)valid[j] | ((uint32_t)valid[al[j]] << 16);
+    }
+  }
   std::vector<uint8_t> blob;
   env->taxi_use_table = ns <= kTableMaxStates;
   if (env->taxi_use_table) {
@@ -618,39 +629,12 @@ int taxi_create(gpt_env* env, const gpt_config* c) {
     // kernel's 32-bit table last
     env->taxi_trans16_off = blob_append(blob, trans16);
     env->taxi_hobs_off = blob_append(blob, hobs);
-    // Walker alias table of the reset law (Philox mode): column j = {threshold, valid[j] | valid[alias_j] << 16}
-    std::vector<uint32_t> alias((size_t)c->taxi_n_valid * 2, 0u);
-    {
-      const int n = c->taxi_n_valid;
-      std::vector<double> q(n);
-      for (int j = 0; j < n; ++j) {
-        const double hi = j == n - 1 ? 4294967296.0 : (double)cdf[j] + 1.0, lo = j == 0 ? 0.0 : (double)cdf[j - 1] + 1.0;
-        q[j] = (hi > lo ? hi - lo : 0.0) / 4294967296.0 * n;
-      }
-      std::vector<int> small, large, al(n);
-      std::vector<double> pr(n, 1.0);
-      for (int j = 0; j < n; ++j) { al[j] = j; (q[j] < 1.0 ? small : large).push_back(j); }
-      while (!small.empty() && !large.empty()) {
-        const int sidx = small.back(), lidx = large.back();
-        small.pop_back();
-        pr[sidx] = q[sidx];
-        al[sidx] = lidx;
-        q[lidx] = (q[lidx] + q[sidx]) - 1.0;
-        if (q[lidx] < 1.0) { large.pop_back(); small.push_back(lidx); }
-      }
-      for (int j = 0; j < n; ++j) {
-        const double t = pr[j] * 4294967296.0;
-        alias[(size_t)j * 2] = t >= 4294967295.0 ? 0xFFFFFFFFu : (t <= 0 ? 0u : (uint32_t)t);
-        alias[(size_t)j * 2 + 1] = (uint32_t)valid[j] | ((uint32_t)valid[al[j]] << 16);
-      }
-    }
     env->taxi_alias_off = blob_append(blob, alias);
     env->taxi_single_bytes = align16((uint32_t)blob.size());
     env->taxi_trans_off = blob_append(blob, trans);
   } else {
     blob_append(blob, celltab);
-    env->taxi_cdf_off = blob_append(blob, cdf);
-    env->taxi_vs_off = blob_append(blob, valid);
+    env->taxi_alias_off = blob_append(blob, alias);
   }
   if (int rc = upload_blob(env, blob)) return rc;
 
@@ -714,8 +698,6 @@ int taxi_launch(gpt_env* env, const LaunchArgs& a) {
   }
   P.blob = env->d_blob;
   P.blob_bytes = env->blob_bytes;
-  P.cdf_off = env->taxi_cdf_off;
-  P.vs_off = env->taxi_vs_off;
   P.rep_shift = env->taxi_rep_shift;
   P.env_offset = c.env_offset;
   P.first_tile = a.first_tile;

@@ -53,8 +53,8 @@ def bind_to_gpu_numa_node(device_index: int) -> str:
             bus = bus[4:]
         with open(f"/sys/bus/pci/devices/{bus}/numa_node") as f:
             node = int(f.read().strip())
-        if node < 0:
-            return "no NUMA information for the GPU"
+        if node < 0:   # virtualised PCI topology: ask the driver instead (nvidia-smi topo prints a CPU-affinity column)
+            return _bind_from_smi_topo(device_index)
         with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
             spec = f.read().strip()
         cpus = set()
@@ -68,6 +68,47 @@ def bind_to_gpu_numa_node(device_index: int) -> str:
         return f"bound to NUMA node {node} ({len(cpus)} CPUs)"
     except Exception as e:  # pragma: no cover - depends on the box
         return f"not bound ({type(e).__name__}: {e})"
+
+
+def _parse_cpulist(spec: str) -> set:
+    cpus = set()
+    for part in spec.split(","):
+        lo, _, hi = part.strip().partition("-")
+        cpus.update(range(int(lo), int(hi or lo) + 1))
+    return cpus
+
+
+def _bind_from_smi_topo(device_index: int) -> str:
+    """Fallback of bind_to_gpu_numa_node: the "CPU Affinity" column of ``nvidia-smi topo -m`` for this GPU."""
+    import subprocess
+    try:
+        out = subprocess.run(["nvidia-smi", "topo", "-m"], capture_output=True, text=True, timeout=20).stdout
+    except Exception as e:  # pragma: no cover - depends on the box
+        return f"no NUMA information for the GPU (sysfs: -1; nvidia-smi topo: {type(e).__name__})"
+    return bind_from_topo_text(out, device_index)
+
+
+def bind_from_topo_text(text: str, device_index: int, apply: bool = True) -> str:
+    """Parses the matrix ``nvidia-smi topo -m`` prints (tab separated; header has a "CPU Affinity" column) and pins
+    the process to GPU<device_index>'s CPU list.  Split out (and ``apply=False``) so the CPU tests can feed it text."""
+    import re
+    clean = re.sub(r"\x1b\[[0-9;]*m", "", text)
+    lines = [ln for ln in clean.splitlines() if ln.strip()]
+    header = next((ln for ln in lines if "CPU Affinity" in ln), None)
+    row = next((ln for ln in lines if ln is not header and re.match(rf"^GPU{device_index}\b", ln.strip())), None)
+    if header is None or row is None:
+        return "no NUMA information for the GPU (sysfs: -1; nvidia-smi topo: no CPU Affinity column)"
+    # matrix cells are X / NV# / SYS / NODE / PHB / PXB / PIX: the first all-digit list in the row is the CPU affinity
+    spec = next((c.strip() for c in re.split(r"\t+|\s{2,}", row) if re.fullmatch(r"\d+(-\d+)?(,\d+(-\d+)?)*", c.strip())), None)
+    if spec is None:
+        return "no NUMA information for the GPU (sysfs: -1; nvidia-smi topo: CPU affinity not given)"
+    cpus = _parse_cpulist(spec)
+    cpus &= os.sched_getaffinity(0)
+    if not cpus:
+        return "nvidia-smi topo: the GPU's CPU list has no CPU in this process's cpuset"
+    if apply:
+        os.sched_setaffinity(0, cpus)
+    return f"bound to the GPU's CPU affinity from nvidia-smi topo ({len(cpus)} CPUs)"
 
 
 def allreduce_stats(stats: torch.Tensor) -> dict:

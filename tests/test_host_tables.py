@@ -134,3 +134,18 @@ def test_car_render_matches_reference_frames():
     assert len(set(z["s"][:, 2].tolist())) >= 2                      # with and without the priest indicator
     for s, h, p, frame in zip(z["s"], z["heavens"], z["priests"], z["frames"]):
         np.testing.assert_array_equal(render_car(float(s[0]), float(s[2]), float(h), float(p)), frame)
+
+
+def test_numa_fallback_parses_nvidia_smi_topo():
+    """bind_to_gpu_numa_node's fallback (sysfs numa_node = -1 on virtualised boxes): CPU affinity column of the
+    matrix `nvidia-smi topo -m` prints."""
+    import os
+    from gym_po.sharding import bind_from_topo_text
+    mine = sorted(os.sched_getaffinity(0))
+    spec = f"{mine[0]}-{mine[-1]}"
+    txt = ("\tGPU0\tGPU1\tNIC0\tCPU Affinity\tNUMA Affinity\tGPU NUMA ID\n"
+           f"GPU0\t X \tNV18\tSYS\t{spec}\t0\t\tN/A\nGPU1\tNV18\t X \tSYS\t99990-99999\t1\t\tN/A\nNIC0\tSYS\tSYS\t X \t\t\t\t\n")
+    assert bind_from_topo_text(txt, 0, apply=False).startswith("bound to the GPU's CPU affinity")
+    assert "no CPU in this process's cpuset" in bind_from_topo_text(txt, 1, apply=False)
+    assert "no CPU Affinity column" in bind_from_topo_text("garbage", 0, apply=False)
+    assert "not given" in bind_from_topo_text("\tGPU0\tCPU Affinity\nGPU0\t X \t\tN/A\n", 0, apply=False)
