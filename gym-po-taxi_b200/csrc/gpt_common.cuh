@@ -53,29 +53,57 @@ __host__ __device__ inline void expand_round_keys(RngKey& k, uint64_t seed) {
     y += 0xBB67AE85u;
   }
 }
-__device__ __forceinline__ uint4 philox4x32_10(uint4 c, const RngKey& k) {
+template <int ROUNDS>
+__device__ __forceinline__ uint4 philox4x32(uint4 c, const RngKey& k) {
+  static_assert(ROUNDS >= 7 && ROUNDS <= 10, "Philox4x32 is Crush-resistant from 7 rounds on (Salmon et al., SC'11, Table 2)");
   constexpr uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u;
 #pragma unroll
-  for (int r = 0; r < 10; ++r) {
+  for (int r = 0; r < ROUNDS; ++r) {
     const uint32_t hi0 = __umulhi(M0, c.x), lo0 = M0 * c.x;
     const uint32_t hi1 = __umulhi(M1, c.z), lo1 = M1 * c.z;
     c = make_uint4(hi1 ^ c.y ^ k.rk[2 * r], lo1, hi0 ^ c.w ^ k.rk[2 * r + 1], lo0);
   }
   return c;
 }
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, const RngKey& k) { return philox4x32<10>(c, k); }
+
+// Two independent blocks under the same key with their rounds interleaved: each round key is read once and feeds both
+// blocks (written out so that the compiler keeps the keys in uniform registers instead of copying them around).
+template <int ROUNDS>
+__device__ __forceinline__ void philox4x32_x2(uint4& a, uint4& b, const RngKey& k) {
+  static_assert(ROUNDS >= 7 && ROUNDS <= 10, "see philox4x32");
+  constexpr uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u;
+#pragma unroll
+  for (int r = 0; r < ROUNDS; ++r) {
+    const uint32_t k0 = k.rk[2 * r], k1 = k.rk[2 * r + 1];
+    const uint32_t ah0 = __umulhi(M0, a.x), al0 = M0 * a.x, ah1 = __umulhi(M1, a.z), al1 = M1 * a.z;
+    const uint32_t bh0 = __umulhi(M0, b.x), bl0 = M0 * b.x, bh1 = __umulhi(M1, b.z), bl1 = M1 * b.z;
+    a = make_uint4(ah1 ^ a.y ^ k0, al1, ah0 ^ a.w ^ k1, al0);
+    b = make_uint4(bh1 ^ b.y ^ k0, bl1, bh0 ^ b.w ^ k1, bl0);
+  }
+}
+
+// Rounds.  Episode-level draws (reset state, spawn cells, passenger respawn: a handful per episode) use the standard
+// Philox4x32-10.  The per-step dynamics draws (action slip, Gaussian motion noise, target moves: one block per quad
+// and step, up to 30 % of a fused kernel's instructions) use Philox4x32-7 — the same counter-based generator at the
+// smallest round count that passes BigCrush (Salmon et al., SC'11; Random123 ships it as philox4x32_7), i.e. without
+// the safety margin.  Documented deviation: the law of every draw is unchanged.
+constexpr int kResetRounds = 10;
+constexpr int kStepRounds = 7;
 
 // one Philox block for (global env id, step, stream)
+template <int ROUNDS = kResetRounds>
 __device__ __forceinline__ uint4 env_random(const RngKey& k, uint64_t env, uint32_t stream) {
-  return philox4x32_10(make_uint4((uint32_t)env, (uint32_t)(env >> 32), k.step_lo, k.step_hi ^ (stream << 24)), k);
+  return philox4x32<ROUNDS>(make_uint4((uint32_t)env, (uint32_t)(env >> 32), k.step_lo, k.step_hi ^ (stream << 24)), k);
 }
 
 // Graph mode (DEVCTR kernel instantiations): the step counter comes from device memory instead of the launch parameters.
-template <bool DEVCTR>
+template <bool DEVCTR, int ROUNDS = kResetRounds>
 __device__ __forceinline__ uint4 rnd_block(const RngKey& k, uint64_t ctr_dev, uint64_t id, uint32_t stream) {
   if constexpr (DEVCTR)
-    return philox4x32_10(make_uint4((uint32_t)id, (uint32_t)(id >> 32), (uint32_t)ctr_dev, ((uint32_t)(ctr_dev >> 32) & 0x00FFFFFFu) ^ (stream << 24)), k);
+    return philox4x32<ROUNDS>(make_uint4((uint32_t)id, (uint32_t)(id >> 32), (uint32_t)ctr_dev, ((uint32_t)(ctr_dev >> 32) & 0x00FFFFFFu) ^ (stream << 24)), k);
   else
-    return env_random(k, id, stream);
+    return env_random<ROUNDS>(k, id, stream);
 }
 
 // unbiased-enough bounded integer: floor(u * n / 2^32); bias <= n * 2^-32

@@ -226,8 +226,7 @@ __global__ void __launch_bounds__(128, GPT_CROOMS_MINB) crooms_step_kernel(const
     uint4 slipq = make_uint4(0, 0, 0, 0);
     if (!REPLAY && P.act_kind == kActI8) {  // one Philox block feeds the slip draws of the quad
       const uint64_t gq = (uint64_t)(P.env_offset + q) >> 2;
-      if constexpr (DEVCTR) slipq = rnd_block<true>(P.rng, ctr_dev, gq, 3u);
-      else slipq = philox4x32_10(make_uint4((uint32_t)gq, (uint32_t)(gq >> 32), P.rng.step_lo, P.rng.step_hi ^ (3u << 24)), P.rng);
+      slipq = rnd_block<DEVCTR, kStepRounds>(P.rng, ctr_dev, gq, 3u);
     }
     const uint32_t slipv[4] = {slipq.x, slipq.y, slipq.z, slipq.w};
     // float32 fast mode: 3 Philox blocks per quad = 3 words per env: 24 + 24 bits for the action-noise pair, 16 + 16
@@ -237,9 +236,7 @@ __global__ void __launch_bounds__(128, GPT_CROOMS_MINB) crooms_step_kernel(const
       const uint64_t gq = (uint64_t)(P.env_offset + q) >> 2;
 #pragma unroll
       for (int j = 0; j < 3; ++j) {
-        uint4 b;
-        if constexpr (DEVCTR) b = rnd_block<true>(P.rng, ctr_dev, gq, (uint32_t)(4 + j));
-        else b = philox4x32_10(make_uint4((uint32_t)gq, (uint32_t)(gq >> 32), P.rng.step_lo, P.rng.step_hi ^ ((uint32_t)(4 + j) << 24)), P.rng);
+        const uint4 b = rnd_block<DEVCTR, kStepRounds>(P.rng, ctr_dev, gq, (uint32_t)(4 + j));   // per-step noise: Philox4x32-7
         qw[4 * j] = b.x; qw[4 * j + 1] = b.y; qw[4 * j + 2] = b.z; qw[4 * j + 3] = b.w;
       }
     }
@@ -250,7 +247,7 @@ __global__ void __launch_bounds__(128, GPT_CROOMS_MINB) crooms_step_kernel(const
       // ---- noisy action (crooms.py:175-178 / :188-196) ----
       uint4 r0 = make_uint4(0, 0, 0, 0);
       if constexpr (kFast && !REPLAY) r0 = make_uint4(qw[3 * k], qw[3 * k + 1], qw[3 * k + 2] & 0xFFFF0000u, qw[3 * k + 2] << 16);
-      else if (!REPLAY) r0 = rnd_block<DEVCTR>(P.rng, ctr_dev, (uint64_t)(P.env_offset + env), 0u);
+      else if (!REPLAY) r0 = rnd_block<DEVCTR, kStepRounds>(P.rng, ctr_dev, (uint64_t)(P.env_offset + env), 0u);
       if (P.act_kind == kActI8) {
         uint32_t a = (abytes >> (8 * k)) & 0xFFu;
         a = a < n ? a : n - 1;
@@ -479,9 +476,7 @@ __global__ void __launch_bounds__(128, GPT_TAG_MINB) tag_step_kernel(const __gri
       const uint64_t gq = (uint64_t)(P.env_offset + q) >> 2;
 #pragma unroll
       for (int j = 0; j < 2; ++j) {
-        uint4 b;
-        if constexpr (DEVCTR) b = rnd_block<true>(P.rng, ctr_dev, gq, (uint32_t)(4 + j));
-        else b = philox4x32_10(make_uint4((uint32_t)gq, (uint32_t)(gq >> 32), P.rng.step_lo, P.rng.step_hi ^ ((uint32_t)(4 + j) << 24)), P.rng);
+        const uint4 b = rnd_block<DEVCTR, kStepRounds>(P.rng, ctr_dev, gq, (uint32_t)(4 + j));   // per-step noise: Philox4x32-7
         qw[4 * j] = b.x; qw[4 * j + 1] = b.y; qw[4 * j + 2] = b.z; qw[4 * j + 3] = b.w;
       }
     }
@@ -491,7 +486,7 @@ __global__ void __launch_bounds__(128, GPT_TAG_MINB) tag_step_kernel(const __gri
       ev[k] += 1;
       uint4 r0 = make_uint4(0, 0, 0, 0);
       if constexpr (kFast && !REPLAY) r0 = make_uint4(qw[2 * k], qw[2 * k + 1], qw[2 * k] << 30, 0u);
-      else if (!REPLAY) r0 = rnd_block<DEVCTR>(P.rng, ctr_dev, (uint64_t)(P.env_offset + env), 0u);
+      else if (!REPLAY) r0 = rnd_block<DEVCTR, kStepRounds>(P.rng, ctr_dev, (uint64_t)(P.env_offset + env), 0u);
       V2 z;
       uint32_t choice;
       if constexpr (REPLAY) {
@@ -505,7 +500,7 @@ __global__ void __launch_bounds__(128, GPT_TAG_MINB) tag_step_kernel(const __gri
       } else {
         const double2 zz = normal_pair(r0);
         z = RealTraits<R>::make((R)zz.x * a_std, (R)zz.y * a_std);
-        choice = rnd_block<DEVCTR>(P.rng, ctr_dev, (uint64_t)(P.env_offset + env), 3u).x >> 30;
+        choice = rnd_block<DEVCTR, kStepRounds>(P.rng, ctr_dev, (uint64_t)(P.env_offset + env), 3u).x >> 30;
       }
       push[k].x = (push[k].x + z.x) * a_pow;
       push[k].y = (push[k].y + z.y) * a_pow;

@@ -222,6 +222,18 @@ __global__ void __launch_bounds__(kMsThreads, MULTI ? GPT_MS_MINB_MULTI : GPT_MS
   const int64_t orow = MULTI ? (int64_t)t * P.out_stride : 0;
   const uint64_t ctr = (DEVCTR ? ctr_dev : (((uint64_t)P.rng.step_hi << 32) | P.rng.step_lo)) + (uint32_t)t;
   const uint32_t ctr_lo = (uint32_t)ctr, ctr_hi = (uint32_t)(ctr >> 32) & 0x00FFFFFFu;
+  // slip draws: one Philox4x32-7 block per quad and step (32 bits per env), the blocks of a quad pair computed together
+  static_assert(kMsQpt % 2 == 0, "quads are processed in pairs");
+  uint4 slipq[kMsQpt];
+  if (!REPLAY) {
+#pragma unroll
+    for (int j = 0; j < kMsQpt; j += 2) {
+      const uint64_t g0 = (uint64_t)(P.env_offset + base + j * kQuadStride) >> 2, g1 = (uint64_t)(P.env_offset + base + (j + 1) * kQuadStride) >> 2;
+      slipq[j] = make_uint4((uint32_t)g0, (uint32_t)(g0 >> 32), ctr_lo, ctr_hi);
+      slipq[j + 1] = make_uint4((uint32_t)g1, (uint32_t)(g1 >> 32), ctr_lo, ctr_hi);
+      philox4x32_x2<kStepRounds>(slipq[j], slipq[j + 1], P.rng);
+    }
+  }
 #pragma unroll
   for (int j = 0; j < kMsQpt; ++j) {
     const int64_t q = base + j * kQuadStride;
@@ -232,12 +244,7 @@ __global__ void __launch_bounds__(kMsThreads, MULTI ? GPT_MS_MINB_MULTI : GPT_MS
     uint32_t tw = 0, trw = 0, again = 0;
     uint32_t lo[4] = {0, 0, 0, 0}, hi[4] = {0, 0, 0, 0};
 
-    uint4 slip = make_uint4(0, 0, 0, 0);
-    if (!REPLAY) {  // one Philox block feeds the slip draws of the 4 envs of this quad
-      const uint64_t gq = (uint64_t)(P.env_offset + q) >> 2;
-      slip = philox4x32_10(make_uint4((uint32_t)gq, (uint32_t)(gq >> 32), ctr_lo, ctr_hi), P.rng);
-    }
-    const uint32_t slipv[4] = {slip.x, slip.y, slip.z, slip.w};
+    const uint32_t slipv[4] = {REPLAY ? 0u : slipq[j].x, REPLAY ? 0u : slipq[j].y, REPLAY ? 0u : slipq[j].z, REPLAY ? 0u : slipq[j].w};
 
 #pragma unroll
     for (int k = 0; k < 4; ++k) {  // straight-line transition of the 4 envs

@@ -14,7 +14,8 @@
 //   nb8   uint8 [cells]  bit i = neighbour i (N,NE,E,SE,S,SW,W,NW) is walkable.  Drives BOTH the wall
 //                        collision (blocked = bit of the slipped direction clear) and the Hansen obs.
 //   room  uint8 [cells], sid uint16[cells] (dense cell id), valid uint16[n_valid] (spawn cells)
-//   alias uint2[n*8]     Walker alias table per intended action (Philox-mode slip): {threshold, dir | alias dir << 8}
+//   alias uint2[n*8]     Walker alias table per intended action (Philox-mode slip): {threshold, dir | alias dir << 8};
+//                        the draws are Philox4x32-7 blocks, one per quad and step (gpt_common.cuh kStepRounds)
 //   thr64 double[n*n]    cumsum(P[a]) exactly as numpy computes it (replay mode compares the recorded u)
 //   rows  uint64[H+2*off] walkable-bit rows, padded by the window radius (grid obs only)
 #pragma once
@@ -379,9 +380,18 @@ rooms_step_kernel(const __grid_constant__ RoomsParams P) {
   const int64_t orow = MULTI ? (int64_t)t * P.out_stride : 0;
   const uint64_t ctr = (DEVCTR ? ctr_dev : (((uint64_t)P.rng.step_hi << 32) | P.rng.step_lo)) + (uint32_t)t;   // Philox step counter of this step
   const uint32_t ctr_lo = (uint32_t)ctr, ctr_hi = (uint32_t)(ctr >> 32) & 0x00FFFFFFu;
-#ifdef GPT_EXPERIMENT_SHARE_PHILOX
-  uint4 slip_prev = make_uint4(0, 0, 0, 0);
-#endif
+  // slip draws: one Philox4x32-7 block per quad and step (32 bits per env), the blocks of a quad pair computed together
+  static_assert(QPT % 2 == 0, "quads are processed in pairs");
+  uint4 slipq[QPT];
+  if (!REPLAY) {
+#pragma unroll
+    for (int j = 0; j < QPT; j += 2) {
+      const uint64_t g0 = (uint64_t)(P.env_offset + base + j * kQuadStride) >> 2, g1 = (uint64_t)(P.env_offset + base + (j + 1) * kQuadStride) >> 2;
+      slipq[j] = make_uint4((uint32_t)g0, (uint32_t)(g0 >> 32), ctr_lo, ctr_hi);
+      slipq[j + 1] = make_uint4((uint32_t)g1, (uint32_t)(g1 >> 32), ctr_lo, ctr_hi);
+      philox4x32_x2<kStepRounds>(slipq[j], slipq[j + 1], P.rng);
+    }
+  }
 #pragma unroll
   for (int j = 0; j < QPT; ++j) {
     const int64_t q = base + j * kQuadStride;
@@ -393,20 +403,7 @@ rooms_step_kernel(const __grid_constant__ RoomsParams P) {
     uint32_t o32[4] = {0, 0, 0, 0};  // scalar obs, or packed bytes of the vector obs (lo)
     uint32_t o32b[4] = {0, 0, 0, 0}; // second word for 8-byte vector obs
 
-    uint4 slip = make_uint4(0, 0, 0, 0);
-#ifdef GPT_EXPERIMENT_SHARE_PHILOX   // timing experiment only (wrong draws): one block per TWO quads
-    if (!REPLAY && (j & 1) == 0) {
-      const uint64_t gq = (uint64_t)(P.env_offset + q) >> 2;
-      slip_prev = philox4x32_10(make_uint4((uint32_t)gq, (uint32_t)(gq >> 32), ctr_lo, ctr_hi), P.rng);
-    }
-    slip = (j & 1) ? make_uint4(slip_prev.x >> 16, slip_prev.y >> 16, slip_prev.z >> 16, slip_prev.w >> 16) : make_uint4(slip_prev.x << 16, slip_prev.y << 16, slip_prev.z << 16, slip_prev.w << 16);
-#else
-    if (!REPLAY) {  // one Philox block feeds the slip draws of the 4 envs of this quad
-      const uint64_t gq = (uint64_t)(P.env_offset + q) >> 2;
-      slip = philox4x32_10(make_uint4((uint32_t)gq, (uint32_t)(gq >> 32), ctr_lo, ctr_hi), P.rng);
-    }
-#endif
-    const uint32_t slipv[4] = {slip.x, slip.y, slip.z, slip.w};
+    const uint32_t slipv[4] = {REPLAY ? 0u : slipq[j].x, REPLAY ? 0u : slipq[j].y, REPLAY ? 0u : slipq[j].z, REPLAY ? 0u : slipq[j].w};
 
     // ---- transition of the 4 envs: straight-line code, no branches, so the compiler can interleave the
     //      four dependent lookup chains (thresholds -> move table)

@@ -1,6 +1,6 @@
 """TEST INFRASTRUCTURE — the random draws of the Philox-mode CUDA kernels, rebuilt on the host.
 
-The product kernels draw from Philox4x32-10 keyed by the env seed with counter (global env id | quad id, step
+The product kernels draw from Philox4x32 (10 rounds for episode-level draws, 7 for the per-step slip) keyed by the env seed with counter (global env id | quad id, step
 counter, stream) and map the 32-bit words to env decisions through Walker alias tables / multiply-high
 (csrc/gpt_common.cuh, gpt_taxi.cu ``taxi_fix_inline``, gpt_rooms_kernel.cuh, gpt_msrooms.cu).  ``PhiloxDraws``
 recomputes exactly those decisions with numpy and hands them to the oracle envs through the oracle's draw-source
@@ -21,11 +21,14 @@ W0, W1 = 0x9E3779B9, 0xBB67AE85
 MASK = np.uint64(0xFFFFFFFF)
 
 
-def philox4x32_10(c0, c1, c2, c3, k0, k1):
-    """Vectorised Philox4x32-10.  c*: uint32-valued arrays (any broadcastable shapes), k0/k1: python ints."""
+RESET_ROUNDS, STEP_ROUNDS = 10, 7   # csrc/gpt_common.cuh kResetRounds / kStepRounds
+
+
+def philox4x32_10(c0, c1, c2, c3, k0, k1, rounds=10):
+    """Vectorised Philox4x32-R (default 10 rounds).  c*: uint32-valued arrays (any broadcastable shapes), k0/k1: python ints."""
     c0, c1, c2, c3 = (np.asarray(c, dtype=np.uint64) & MASK for c in (c0, c1, c2, c3))
     c0, c1, c2, c3 = np.broadcast_arrays(c0, c1, c2, c3)
-    for r in range(10):
+    for r in range(rounds):
         p0 = M0 * c0
         p1 = M1 * c2
         hi0, lo0 = p0 >> np.uint64(32), p0 & MASK
@@ -74,13 +77,13 @@ class PhiloxDraws:
         self.k0, self.k1 = self.seed & 0xFFFFFFFF, self.seed >> 32
 
     # one Philox block per (id, step counter, stream), memoised per counter value
-    def _block(self, ids, stream):
-        key = (self.counter, stream, len(ids))
+    def _block(self, ids, stream, rounds=RESET_ROUNDS):
+        key = (self.counter, stream, len(ids), rounds)
         if key not in self._cache:
             self._cache = {k: v for k, v in self._cache.items() if k[0] == self.counter}
             ctr_lo = self.counter & 0xFFFFFFFF
             ctr_hi = ((self.counter >> 32) & 0x00FFFFFF) ^ (stream << 24)
-            self._cache[key] = philox4x32_10(ids & MASK, ids >> np.uint64(32), ctr_lo, ctr_hi, self.k0, self.k1)
+            self._cache[key] = philox4x32_10(ids & MASK, ids >> np.uint64(32), ctr_lo, ctr_hi, self.k0, self.k1, rounds)
         return self._cache[key]
 
     # ---- Taxi (gpt_taxi.cu taxi_fix_inline) -----------------------------------------------------
@@ -107,7 +110,7 @@ class PhiloxDraws:
     def random(self, b, kind=None, action=None, cumsum=None, **ctx):
         assert kind == "slip" and b == self.b
         quad = self.gid >> np.uint64(2)
-        blk = self._block(quad, 0)                             # one block per quad of envs; word k belongs to env 4*quad + k
+        blk = self._block(quad, 0, STEP_ROUNDS)                # one Philox4x32-7 block per quad of envs; word k belongs to env 4*quad + k
         lane = (self.gid & np.uint64(3)).astype(np.int64)
         u32 = np.choose(lane, blk)
         a = np.asarray(action).astype(np.int64) & (self.n_actions - 1)

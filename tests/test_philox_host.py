@@ -16,6 +16,19 @@ def test_philox_known_answers():
         assert tuple(int(x) for x in got) == want
 
 
+KAT7 = [  # Random123 kat_vectors: philox4x32 7 rounds (the per-step slip / noise draws use the 7-round variant)
+    ((0, 0, 0, 0), (0, 0), (0x5f6fb709, 0x0d893f64, 0x4f121f81, 0x4f730a48)),
+    ((0xffffffff,) * 4, (0xffffffff,) * 2, (0x5207ddc2, 0x45165e59, 0x4d8ee751, 0x8c52f662)),
+    ((0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344), (0xa4093822, 0x299f31d0), (0x4dfccaba, 0x190a87f0, 0xc47362ba, 0xb6b5242a)),
+]
+
+
+def test_philox_7_rounds_known_answers():
+    for ctr, key, want in KAT7:
+        got = philox4x32_10(*ctr, *key, rounds=7)
+        assert tuple(int(x) for x in got) == want
+
+
 def test_philox_vectorised_matches_scalar():
     rng = np.random.default_rng(0)
     c = rng.integers(0, 2**32, size=(4, 257), dtype=np.uint64)
