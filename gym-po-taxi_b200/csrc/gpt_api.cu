@@ -109,21 +109,10 @@ __global__ void count_bad_actions_kernel(const int8_t* a, int64_t n_rows, int n_
   if ((threadIdx.x & 31u) == 0 && bad) atomicAdd(out, bad);
 }
 
-// graph mode: advances the device-resident Philox step counter after a step (one thread; captured into the graph)
-__global__ void tick_kernel(uint64_t* counter, uint64_t n) { *counter += n; }
-
 static bool graph_mode_family(const gpt_env* env) {
   const gpt_config& c = env->cfg;
   if (c.rng_mode != GPT_RNG_PHILOX || c.track_stats) return false;
   return c.family != GPT_FAMILY_TAXI || env->taxi_use_table;   // every family; Taxi only with the table kernel
-}
-
-static int tick(gpt_env* env, uint64_t n, cudaStream_t stream) {
-  if (!env->graph_mode) return GPT_OK;
-  tick_kernel<<<1, 1, 0, stream>>>(env->d_counter, n);
-  env->launches += 1;
-  cudaError_t e = cudaGetLastError();
-  return e == cudaSuccess ? GPT_OK : cuda_fail(e, "tick_kernel launch");
 }
 
 static int launch(gpt_env* env, const LaunchArgs& a) {
@@ -355,8 +344,7 @@ int gpt_reset(gpt_env* env, int has_seed, uint64_t seed, void* stream) {
     if (e != cudaSuccess) return cuda_fail(e, "cudaMemcpyAsync(step counter)");
   }
   int rc = launch(env, a);
-  env->counter += 1;
-  if (rc == GPT_OK) rc = tick(env, 1, a.stream);
+  env->counter += 1;   // graph mode: the kernel advanced the device counter itself (this host mirror is not used then)
   return rc;
 }
 
@@ -370,7 +358,6 @@ int gpt_step(gpt_env* env, const void* actions, void* stream) {
   a.stream = (cudaStream_t)stream;
   int rc = launch(env, a);
   env->counter += 1;
-  if (rc == GPT_OK) rc = tick(env, 1, a.stream);
   return rc;
 }
 
@@ -395,7 +382,7 @@ int gpt_step_many(gpt_env* env, const void* actions, int32_t n_steps, int64_t ou
         return fail(GPT_E_ARG, "gpt_step_many: bound output arrays are too small for n_steps*out_stride_rows");
   }
   static const bool no_fuse = getenv("GPT_NO_FUSED_STEPS") != nullptr;
-  const bool fuse = !no_fuse && !env->no_fused_steps && !env->graph_mode && n_steps > 1 &&
+  const bool fuse = !no_fuse && !env->no_fused_steps && n_steps > 1 &&
                     ((env->cfg.family == GPT_FAMILY_TAXI && taxi_can_fuse(env)) || (env->cfg.family == GPT_FAMILY_ROOMS && rooms_can_fuse(env)) ||
                      (env->cfg.family == GPT_FAMILY_MSROOMS && msrooms_can_fuse(env)));
   if (fuse) {  // one launch for all n_steps: state stays in registers, only actions are read and outputs written per step
@@ -425,7 +412,6 @@ int gpt_step_many(gpt_env* env, const void* actions, int32_t n_steps, int64_t ou
     }
     int rc = launch(env, a);
     env->counter += 1;
-    if (rc == GPT_OK) rc = tick(env, 1, a.stream);
     if (rc) return rc;
   }
   return GPT_OK;
@@ -446,10 +432,11 @@ int gpt_set_graph_mode(gpt_env* env, int enable, void* stream) {
     if (!graph_mode_family(env))
       return fail(GPT_E_ARG, "gpt_set_graph_mode: needs Philox mode without track_stats (Taxi: a map small enough for the table kernel)");
     if (!env->d_counter) {
-      e = cudaMalloc((void**)&env->d_counter, sizeof(uint64_t));
+      e = cudaMalloc((void**)&env->d_counter, 2 * sizeof(uint64_t));   // {step counter, arrival count}
       if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc(step counter)");
     }
-    e = cudaMemcpyAsync(env->d_counter, &env->counter, sizeof(uint64_t), cudaMemcpyHostToDevice, (cudaStream_t)stream);
+    e = cudaMemsetAsync(env->d_counter, 0, 2 * sizeof(uint64_t), (cudaStream_t)stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(env->d_counter, &env->counter, sizeof(uint64_t), cudaMemcpyHostToDevice, (cudaStream_t)stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize((cudaStream_t)stream);
     if (e != cudaSuccess) return cuda_fail(e, "cudaMemcpyAsync(step counter)");
     env->graph_mode = true;

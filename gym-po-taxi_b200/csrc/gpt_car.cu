@@ -45,6 +45,8 @@ __global__ void __launch_bounds__(128) car_step_kernel(const __grid_constant__ C
   const int64_t q = first + ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * kQuad;
   if (q >= last) return;
   pdl_wait();
+  uint64_t ctr_dev = 0;   // graph mode: step counter from device memory
+  if constexpr (DEVCTR) ctr_dev = devctr_fetch_and_advance(P.ctr_ptr, 1u);
   float4 sv[3];
 #pragma unroll
   for (int i = 0; i < 3; ++i) sv[i] = __ldcs(reinterpret_cast<const float4*>(P.s + q * 3) + i);
@@ -96,8 +98,6 @@ __global__ void __launch_bounds__(128) car_step_kernel(const __grid_constant__ C
         hv = P.rp_heaven[env] > 0;
         pr = P.rp_priest[env] > 0;
       } else {
-        uint64_t ctr_dev = 0;   // graph mode: step counter from device memory (rare path only)
-        if constexpr (DEVCTR) ctr_dev = *P.ctr_ptr;
         const uint4 r = rnd_block<DEVCTR>(P.rng, ctr_dev, (uint64_t)(P.env_offset + env), 0u);
         const double u = (double)(((uint64_t)r.x << 21) ^ (uint64_t)(r.y >> 11)) * (1.0 / 9007199254740992.0);
         p0 = -0.2 + 0.4 * u;          // numpy uniform: low + (high - low) * random()
@@ -211,7 +211,7 @@ int car_launch(gpt_env* env, const LaunchArgs& a) {
     k = kind == kCarF32 ? (K)car_step_kernel<float, kCarF32, false, true>
                         : (kind == kCarF64 ? (K)car_step_kernel<double, kCarF64, false, true> : (K)car_step_kernel<double, kCarDiscrete, false, true>);
   void* args[] = {(void*)&P};
-  cudaError_t e = launch_pdl((const void*)k, dim3(nblocks), dim3(threads), 0, a.stream, args, !env->graph_mode);
+  cudaError_t e = launch_pdl((const void*)k, dim3(nblocks), dim3(threads), 0, a.stream, args);
   env->launches += 1;
   if (e != cudaSuccess) return cuda_fail(e, "car_step_kernel launch");
   if (reset) {

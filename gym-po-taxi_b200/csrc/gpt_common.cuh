@@ -191,6 +191,31 @@ __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepc
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 // ------------------------------------------------------------------------------------------
+// Graph mode (DEVCTR kernel instantiations): the Philox step counter lives in device memory — a captured CUDA graph
+// replays the same launch parameters, so the kernel itself has to find "which step is this" and advance it.
+//   ctr[0] = step counter, ctr[1] = arrival count of the running grid.
+// Every thread reads the counter; behind the CTA's barrier (all of the CTA's reads are done) thread 0 announces the CTA
+// on the arrival count, and the LAST CTA to arrive — by then every CTA of the grid has read the counter — stores
+// counter + n_steps and clears the arrival count.  The next launch reads it after stream order / griddepcontrol.wait
+// (= this grid complete and its writes visible), so PDL and fused multi-step launches work under capture and no
+// separate tick kernel is needed.  Call once, by all non-exited threads of the CTA, after pdl_wait().
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t devctr_fetch_and_advance(const uint64_t* ctr_ptr, uint32_t n_steps) {
+  unsigned long long* c = (unsigned long long*)ctr_ptr;
+  const unsigned long long v = __ldcg(c);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    if (atomicAdd(reinterpret_cast<unsigned int*>(c + 1), 1u) == gridDim.x - 1u) {
+      __threadfence();
+      *reinterpret_cast<volatile unsigned int*>(c + 1) = 0u;
+      *reinterpret_cast<volatile unsigned long long*>(c) = v + n_steps;
+    }
+  }
+  return (uint64_t)v;
+}
+
+// ------------------------------------------------------------------------------------------
 // episode statistics: per-thread partial sums -> warp shuffle reduce -> one atomicAdd per warp and field
 // stats[0] episodes, [1] sum of returns, [2] sum of lengths, [3] sum of squared returns, [4] env-steps
 // ------------------------------------------------------------------------------------------

@@ -161,7 +161,7 @@ int crooms_launch(gpt_env* env, const LaunchArgs& a) {
     if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(crooms)");
   }
   void* args[] = {(void*)&P};
-  cudaError_t e = launch_pdl(k, dim3(nblocks), dim3(threads), smem, a.stream, args, !env->graph_mode);
+  cudaError_t e = launch_pdl(k, dim3(nblocks), dim3(threads), smem, a.stream, args);
   env->launches += 1;
   if (e != cudaSuccess) return cuda_fail(e, "crooms_step_kernel launch");
   return GPT_OK;
@@ -232,7 +232,7 @@ int tag_launch(gpt_env* env, const LaunchArgs& a) {
   P.ctr_ptr = env->d_counter;
   void* k = c.c_state_f32 ? tag_pick_f32(replay, devctr) : tag_pick_rr<double>(replay, devctr);
   void* args[] = {(void*)&P};
-  cudaError_t e = launch_pdl(k, dim3(nblocks), dim3(threads), 0, a.stream, args, !env->graph_mode);
+  cudaError_t e = launch_pdl(k, dim3(nblocks), dim3(threads), 0, a.stream, args);
   env->launches += 1;
   if (e != cudaSuccess) return cuda_fail(e, "tag_step_kernel launch");
   return GPT_OK;

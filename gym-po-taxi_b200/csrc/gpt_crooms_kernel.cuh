@@ -181,7 +181,7 @@ __global__ void __launch_bounds__(128, GPT_CROOMS_MINB) crooms_step_kernel(const
 
   pdl_wait();
   uint64_t ctr_dev = 0;   // graph mode: step counter from device memory
-  if constexpr (DEVCTR) ctr_dev = *P.ctr_ptr;
+  if constexpr (DEVCTR) ctr_dev = devctr_fetch_and_advance(P.ctr_ptr, 1u);
   V2 pos[4], gpos[4], vel[4], push[4];
   int32_t ev[4] = {0, 0, 0, 0};
   uint32_t abytes = 0;
@@ -456,7 +456,7 @@ __global__ void __launch_bounds__(128, GPT_TAG_MINB) tag_step_kernel(const __gri
   const bool reset_all = P.mode == kModeReset;
   pdl_wait();
   uint64_t ctr_dev = 0;   // graph mode: step counter from device memory
-  if constexpr (DEVCTR) ctr_dev = *P.ctr_ptr;
+  if constexpr (DEVCTR) ctr_dev = devctr_fetch_and_advance(P.ctr_ptr, 1u);
   float rv[4] = {0.f, 0.f, 0.f, 0.f};
   uint32_t tw = 0, trw = 0, again = reset_all ? 0xFu : 0u;
   int32_t ev[4] = {0, 0, 0, 0};

@@ -45,7 +45,8 @@ struct gpt_env {
   uint64_t counter = 0;  // Philox step counter
   int64_t launches = 0;
   bool no_fused_steps = false;   // gpt_set_fused_steps(env, 0)
-  // graph mode (gpt_set_graph_mode): the Philox step counter lives in device memory and a tick kernel advances it
+  // graph mode (gpt_set_graph_mode): the Philox step counter lives in device memory; the DEVCTR kernels read and advance
+  // it themselves (devctr_fetch_and_advance).  d_counter[0] = step counter, d_counter[1] = arrival count of the grid.
   bool graph_mode = false;
   uint64_t* d_counter = nullptr;
   unsigned long long* d_bad = nullptr;   // gpt_check_actions scratch
@@ -122,7 +123,7 @@ std::vector<uint32_t> build_slip_alias(int n_actions, const double* cumsum_rows)
 
 // Launch with the programmatic-stream-serialization attribute (see pdl_wait in gpt_common.cuh).
 // GPT_NO_PDL=1 falls back to a plain launch (A/B measurements).
-inline cudaError_t launch_pdl(const void* func, dim3 grid, dim3 block, size_t smem, cudaStream_t stream, void** args, bool allow_pdl = true) {
+inline cudaError_t launch_pdl(const void* func, dim3 grid, dim3 block, size_t smem, cudaStream_t stream, void** args) {
   static const bool no_pdl = getenv("GPT_NO_PDL") != nullptr;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid;
@@ -133,7 +134,7 @@ inline cudaError_t launch_pdl(const void* func, dim3 grid, dim3 block, size_t sm
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = (no_pdl || !allow_pdl) ? 0 : 1;   // graph mode launches plainly: a tick kernel separates the steps anyway
+  cfg.numAttrs = no_pdl ? 0 : 1;
   return cudaLaunchKernelExC(&cfg, func, args);
 }
 

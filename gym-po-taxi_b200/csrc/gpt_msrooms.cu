@@ -209,7 +209,7 @@ __global__ void __launch_bounds__(kMsThreads, MULTI ? GPT_MS_MINB_MULTI : GPT_MS
   }
   const int32_t n_steps = MULTI ? P.n_steps : 1;
   uint64_t ctr_dev = 0;   // graph mode: step counter from device memory
-  if constexpr (DEVCTR) ctr_dev = *P.ctr_ptr;
+  if constexpr (DEVCTR) ctr_dev = devctr_fetch_and_advance(P.ctr_ptr, (uint32_t)n_steps);
 #pragma unroll 1
   for (int32_t t = 0; t < n_steps; ++t) {
   uint32_t a_next[kMsQpt];
@@ -515,6 +515,12 @@ template <int OB>
 static void* ms_pick(bool rgoal, bool merged, bool replay, bool multi, bool devctr) {
   using K = void (*)(const MsParams);
   K k;
+  if (devctr && multi) {  // graph mode, fused multi-step launch
+    if (rgoal) k = (K)msrooms_step_kernel<OB, true, false, false, true, true>;
+    else if (merged && OB == 4) k = (K)msrooms_step_kernel<4, false, true, false, true, true>;
+    else k = (K)msrooms_step_kernel<OB, false, false, false, true, true>;
+    return (void*)k;
+  }
   if (devctr) {  // graph mode: single step, Philox, step counter in device memory
     if (rgoal) k = (K)msrooms_step_kernel<OB, true, false, false, false, true>;
     else if (merged && OB == 4) k = (K)msrooms_step_kernel<4, false, true, false, false, true>;
@@ -597,7 +603,7 @@ int msrooms_launch(gpt_env* env, const LaunchArgs& a) {
   P.n_steps = a.n_steps;
   P.act_stride = env->capacity;
   P.out_stride = a.out_stride_rows;
-  const bool devctr = env->graph_mode && !multi && !replay;
+  const bool devctr = env->graph_mode && !replay;
   P.ctr_ptr = env->d_counter;
   void* k = nullptr;
   switch (L.obs_bytes) {
@@ -613,7 +619,7 @@ int msrooms_launch(gpt_env* env, const LaunchArgs& a) {
     if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(msrooms)");
   }
   void* args[] = {(void*)&P};
-  cudaError_t e = launch_pdl(k, dim3(nblocks), dim3(kMsThreads), smem, a.stream, args, !env->graph_mode);
+  cudaError_t e = launch_pdl(k, dim3(nblocks), dim3(kMsThreads), smem, a.stream, args);
   env->launches += 1;
   if (e != cudaSuccess) return cuda_fail(e, "msrooms_step_kernel launch");
   if (reset) {

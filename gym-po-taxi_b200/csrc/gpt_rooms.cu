@@ -349,16 +349,16 @@ int rooms_launch(gpt_env* env, const LaunchArgs& a) {
   P.n_steps = a.n_steps;
   P.act_stride = env->capacity;
   P.out_stride = a.out_stride_rows;
-  const bool devctr = env->graph_mode && !multi && !replay && !c.track_stats;   // graph mode: step counter in device memory
+  const bool devctr = env->graph_mode && !replay && !c.track_stats;   // graph mode: step counter in device memory
   P.ctr_ptr = env->d_counter;
-  void* k = pick_kernel(c.rooms_obs_kind, P.grid_n, rgoal, replay, devctr ? 3 : (multi ? 2 : (c.track_stats != 0 ? 1 : 0)));
+  void* k = pick_kernel(c.rooms_obs_kind, P.grid_n, rgoal, replay, devctr ? (multi ? 4 : 3) : (multi ? 2 : (c.track_stats != 0 ? 1 : 0)));
   if (!k) return fail(GPT_E_ARG, "rooms: no kernel for this obs kind");
   if (smem > 40 * 1024) {  // static + dynamic shared memory above 48 KB needs the opt-in
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(rooms)");
   }
   void* args[] = {(void*)&P};
-  cudaError_t e = launch_pdl(k, dim3(nblocks), dim3(threads), smem, a.stream, args, !env->graph_mode);
+  cudaError_t e = launch_pdl(k, dim3(nblocks), dim3(threads), smem, a.stream, args);
   env->launches += 1;
   if (e != cudaSuccess) return cuda_fail(e, "rooms_step_kernel launch");
   if (reset) {

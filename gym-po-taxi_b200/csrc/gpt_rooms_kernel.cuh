@@ -365,7 +365,7 @@ rooms_step_kernel(const __grid_constant__ RoomsParams P) {
   const int32_t n_steps = MULTI ? P.n_steps : 1;
   // DEVCTR (graph mode): the step counter comes from device memory, so that a captured CUDA graph can be replayed
   uint64_t ctr_dev = 0;
-  if constexpr (DEVCTR) ctr_dev = *P.ctr_ptr;
+  if constexpr (DEVCTR) ctr_dev = devctr_fetch_and_advance(P.ctr_ptr, (uint32_t)n_steps);
   const size_t obs_row = OBS == GPT_OBS_GRID ? (size_t)(gn * gn)
                          : (OBS == GPT_OBS_VEC_MDP ? 2 : ((OBS == GPT_OBS_VEC_HANSEN || OBS == GPT_OBS_VEC_HANSEN_GOAL) ? (size_t)P.hansen_n : 4));
 #pragma unroll 1
@@ -529,10 +529,13 @@ static void* pick_rr2(bool rgoal, bool replay) {
   return (void*)k;
 }
 // variant: 0 = plain single step, 1 = single step with in-kernel statistics, 2 = fused multi-step (Philox mode),
-// 3 = single step with the device-resident step counter (graph mode, Philox)
+// 3 = single step with the device-resident step counter (graph mode, Philox), 4 = fused multi-step in graph mode
 template <int OBS, int GRID_N>
 static void* pick_rr(bool rgoal, bool replay, int variant) {
   using K = void (*)(const RoomsParams);
+  if (variant == 4)
+    return replay ? nullptr
+                  : (void*)(rgoal ? (K)rooms_step_kernel<OBS, true, false, GRID_N, false, true, true> : (K)rooms_step_kernel<OBS, false, false, GRID_N, false, true, true>);
   if (variant == 3)
     return replay ? nullptr
                   : (void*)(rgoal ? (K)rooms_step_kernel<OBS, true, false, GRID_N, false, false, true> : (K)rooms_step_kernel<OBS, false, false, GRID_N, false, false, true>);

@@ -268,7 +268,7 @@ __device__ __forceinline__ uint32_t taxi_fix_inline(const TaxiParams& P, const u
 // delivered bit of the table entry, there is no passenger respawn and the dropoff counter is 0 at every step
 // boundary: the kernel neither loads nor tracks it and stores 0 (a counter injected with set_state is ignored here;
 // the single-step kernel keeps the reference's arithmetic).
-template <bool STATS, int QPT, int THREADS, bool ONE>
+template <bool STATS, int QPT, int THREADS, bool ONE, bool DEVCTR = false>
 __global__ void __launch_bounds__(THREADS, STATS ? 1 : GPT_TAXI_MINB_MULTI * 128 / THREADS) taxi_table_multi_kernel(const __grid_constant__ TaxiMultiParams M) {
   constexpr bool REPLAY = false;   // replayed draws are per step: replay mode uses the single-step kernel
   const TaxiParams& P = M.p;
@@ -291,6 +291,8 @@ __global__ void __launch_bounds__(THREADS, STATS ? 1 : GPT_TAXI_MINB_MULTI * 128
   const int64_t base = first + wtile * kEnvsPerWarp + lane * kQuad;
   if (base >= last) return;
   pdl_wait();   // the previous launch's writes are complete and visible from here on
+  uint64_t ctr_dev = 0;   // graph mode: step counter from device memory, advanced by n_steps for the next launch
+  if constexpr (DEVCTR) ctr_dev = devctr_fetch_and_advance(P.ctr_ptr, (uint32_t)n_steps);
   uint32_t off[QPT][4], ndv[QPT][4], a4[QPT];   // off = state id << kRowShift
   int32_t ev[QPT][4];
   float ret[STATS ? QPT : 1][4];
@@ -384,7 +386,7 @@ __global__ void __launch_bounds__(THREADS, STATS ? 1 : GPT_TAXI_MINB_MULTI * 128
         for (int i = 0; i < 4 * QPT; ++i) cur = i == idx ? off[i >> 2][i & 3] : cur;
         const int64_t env = base + j * kQuadStride + k;
         // inlined: a CALL here would wait for the in-flight action prefetch (ncu: 20 % of all stall samples)
-        const uint32_t fresh = taxi_fix_inline<REPLAY>(P, alias, env, (uint32_t)t, cur >> kRowShift, full);
+        const uint32_t fresh = taxi_fix_inline<REPLAY, DEVCTR>(P, alias, env, (uint32_t)t, cur >> kRowShift, full, ctr_dev);
         P.obs[orow + env] = (int32_t)hobs[fresh];
 #pragma unroll
         for (int i = 0; i < 4 * QPT; ++i) {
@@ -416,7 +418,7 @@ constexpr uint32_t kT16State = 0x1FFFu, kT16Goal = 1u << 13, kT16Bad = 1u << 14;
 constexpr int kT16Cols = 6;  // actions 0..4 + "no-op" column for out-of-range action bytes
 
 // DEVCTR (graph mode): the Philox step counter is read from device memory instead of the launch parameters, so that
-// a captured CUDA graph can be replayed (a one-thread tick kernel advances the counter after every step).
+// a captured CUDA graph can be replayed (the kernel advances the counter itself: devctr_fetch_and_advance).
 template <bool HANSEN, bool REPLAY, bool STATS, int QPT, int THREADS, bool DEVCTR = false>
 __global__ void __launch_bounds__(THREADS, (STATS || QPT > 2) ? 1 : 1280 / THREADS) taxi_table_kernel(const __grid_constant__ TaxiParams P) {
   extern __shared__ __align__(128) uint8_t smem[];
@@ -435,7 +437,7 @@ __global__ void __launch_bounds__(THREADS, (STATS || QPT > 2) ? 1 : 1280 / THREA
 
   pdl_wait();   // the previous step's writes are complete and visible from here on
   uint64_t ctr_dev = 0;
-  if constexpr (DEVCTR) ctr_dev = *P.ctr_ptr;
+  if constexpr (DEVCTR) ctr_dev = devctr_fetch_and_advance(P.ctr_ptr, 1u);
   int4 s4[QPT], e4[QPT];
   uint32_t nd4[QPT], a4[QPT];
   float4 ret4[QPT];
@@ -748,7 +750,11 @@ int taxi_launch(gpt_env* env, const LaunchArgs& a) {
     threads = 128;
     // tuning knob GPT_TAXI_MULTI_SHAPE = <quads per thread><threads> (default 2128)
     static const int mshape = getenv("GPT_TAXI_MULTI_SHAPE") ? atoi(getenv("GPT_TAXI_MULTI_SHAPE")) : 0;
-    if (!c.track_stats && one) {
+    const bool devctr_multi = env->graph_mode && !c.track_stats;   // graph mode: step counter in device memory
+    if (devctr_multi) {
+      M.p.ctr_ptr = env->d_counter;
+      km = one ? (KM)taxi_table_multi_kernel<false, 2, 128, true, true> : (KM)taxi_table_multi_kernel<false, 2, 128, false, true>;
+    } else if (!c.track_stats && one) {
       switch (mshape) {
         case 1128: km = (KM)taxi_table_multi_kernel<false, 1, 128, true>; qpt = 1; threads = 128; break;
         case 1256: km = (KM)taxi_table_multi_kernel<false, 1, 256, true>; qpt = 1; threads = 256; break;
@@ -798,7 +804,7 @@ int taxi_launch(gpt_env* env, const LaunchArgs& a) {
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(taxi)");
   }
-  cudaError_t e = launch_pdl(kernel, dim3(grid), dim3(threads), smem, a.stream, args, !env->graph_mode);
+  cudaError_t e = launch_pdl(kernel, dim3(grid), dim3(threads), smem, a.stream, args);
   env->launches += 1;
   if (e != cudaSuccess) return cuda_fail(e, "taxi step kernel launch");
   if (table_reset) {

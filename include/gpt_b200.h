@@ -209,10 +209,11 @@ GPT_API int gpt_step_many(gpt_env* env, const void* actions, int32_t n_steps, in
  * n_steps steps, only actions are read and outputs written per step; results are bit-identical to n_steps
  * single-step launches.  gpt_set_fused_steps(env, 0) forces one launch per step (A/B measurements). */
 GPT_API int gpt_set_fused_steps(gpt_env* env, int enable);
-/* Graph mode (every family; Philox mode, no track_stats; Taxi with the table kernel): the Philox step counter moves from the launch
- * parameters into device memory and a one-thread tick kernel advances it after every step, so that gpt_step() calls
- * captured into a CUDA graph draw fresh random numbers on every replay.  gpt_step_many then issues one launch per
- * step and gpt_step_host is unavailable.  Call outside of stream capture (it synchronises `stream`). */
+/* Graph mode (every family; Philox mode, no track_stats; Taxi with the table kernel): the Philox step counter moves from the
+ * launch parameters into device memory and the step kernels read AND advance it themselves (the last CTA of a grid to
+ * fetch it stores counter + steps), so that gpt_step() / gpt_step_many() calls captured into a CUDA graph draw fresh
+ * random numbers on every replay — programmatic dependent launch and the fused multi-step launches keep working under
+ * capture.  gpt_step_host is unavailable in graph mode.  Call outside of stream capture (it synchronises `stream`). */
 GPT_API int gpt_set_graph_mode(gpt_env* env, int enable, void* stream);
 /* end-to-end: H2D(actions) -> fused step -> D2H(obs, reward, terminated, truncated), chunked and
  * pipelined on internal streams; returns after the results are in the host buffers. */

@@ -432,3 +432,43 @@ def test_cuda_graph_capture_and_replay(family):
         assert torch.equal(x, y)
     with pytest.raises(ValueError):
         TaxiVecEnv(64, device=DEV, rng_mode="replay").set_graph_mode(True)
+
+
+@pytest.mark.parametrize("family", ["taxi", "rooms", "msrooms"])
+def test_cuda_graph_captures_fused_launches(family):
+    """Graph mode keeps the fused multi-step launches (and PDL): a captured step_many() is ONE kernel whose Philox step
+    counter advances by T on the device at every replay; trajectories equal an eagerly stepped twin, bit for bit."""
+    from gym_po.envs import MultistoryFourRoomsEnv, RoomsEnv, TaxiVecEnv
+    b, T = 5000, 6
+    mk, n_act = {
+        "taxi": (lambda: TaxiVecEnv(b, time_limit=11, num_passengers=2, device=DEV, seed=4), 5),
+        "rooms": (lambda: RoomsEnv(b, "4", obs_type="hansen8", time_limit=11, device=DEV, seed=4), 8),
+        "msrooms": (lambda: MultistoryFourRoomsEnv(b, grid_z=2, time_limit=11, device=DEV, seed=4), 4),
+    }[family]
+    env, twin = mk(), mk()
+    env.reset(seed=4); twin.reset(seed=4)
+    env.set_graph_mode(True)
+    names = ("obs", "reward", "terminated", "truncated")
+    static_a = torch.zeros((T, env.capacity), dtype=torch.int8, device=DEV)
+    out = {n: torch.zeros((T,) + tuple(env._arrays[n].shape), dtype=env._arrays[n].dtype, device=DEV) for n in names}
+    ref = {n: torch.zeros_like(out[n]) for n in names}
+    l0 = env.launch_count
+    env.step_many(static_a, out)                      # eager, in graph mode: one fused launch
+    assert env.launch_count - l0 == 1
+    twin.step_many(static_a, ref)
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        env.step_many(static_a, out)
+    gen = torch.Generator(device=DEV).manual_seed(6)
+    for rep in range(5):
+        static_a.copy_(torch.randint(0, n_act, static_a.shape, dtype=torch.int8, device=DEV, generator=gen))
+        g.replay()
+        twin.step_many(static_a, ref)
+        torch.cuda.synchronize()
+        for n in names:
+            assert torch.equal(out[n], ref[n]), (n, rep)
+    sa, sb = env.get_state(), twin.get_state()
+    for k in sa:
+        assert torch.equal(sa[k], sb[k]), k
+    assert env.rng_counter == twin.rng_counter == 1 + T * 7
