@@ -224,7 +224,7 @@ def make_env(workload, b, rank, seed=0):
 
 
 def steps_per_launch_for(k):
-    """Steps fused into one launch: the largest divisor of K in [4, 10], so that the K timed steps are whole
+    """Steps fused into one launch: the largest divisor of K in [4, MAX_SLOTS], so that the K timed steps are whole
     launches of equal length (no ragged 8+8+4); K without such a divisor falls back to launches of up to 8."""
     for t in range(min(k, MAX_SLOTS), 3, -1):
         if k % t == 0:
@@ -590,6 +590,7 @@ def run_reference(args):
 
 
 def main():
+    global MAX_SLOTS
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=2000)
@@ -600,10 +601,12 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=None)
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--min-timed-ms", type=float, default=25.0, help="repeat the K-step block until at least this much GPU time (and >= 7 repeats)")
+    ap.add_argument("--max-steps-per-launch", type=int, default=MAX_SLOTS, help="upper bound of the steps fused into one gpt_step_many launch (= rollout slots)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-workloads", action="store_true", help="skip the short runs of the other BASELINE configurations")
     ap.add_argument("--quick", action="store_true", help="profiling runs: no load phase, one e2e repeat, no CPU baseline, no other workloads")
     args = ap.parse_args()
+    MAX_SLOTS = max(1, args.max_steps_per_launch)
     if args.impl == "reference":
         run_reference(args)
     else:
