@@ -502,7 +502,7 @@ def run_b200(args):
             "ms_per_step": head["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": wl["dtype"], "data": "synthetic",
             "config": {"workload": wl["desc"], "name": args.workload, "envs_per_gpu": b, "envs_total": total_envs,
-                       "rng": "philox4x32-10",
+                       "rng": "philox4x32-7",
                        "action_stream": "open loop: pre-generated synthetic action slots resident in HBM (north_star: 'synthetic action streams')"
                                         + (f"; gpt_step_many fuses {spl:g} consecutive steps per launch — the closed-loop "
                                            "one-launch-per-step rate of env.step() is reported as single_step_launches" if spl > 1 else ""),

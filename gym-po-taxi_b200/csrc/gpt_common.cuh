@@ -1,6 +1,6 @@
 // gpt_common.cuh — device helpers shared by the fused env-step kernels (sm_100a).
 //
-//   * Philox4x32-10 counter RNG (no RNG state in HBM: key = seed, counter = (global env id, step, stream))
+//   * Philox4x32-7 counter RNG (no RNG state in HBM: key = seed, counter = (global env id, step, stream))
 //   * streaming 128/64/32-bit global loads / stores (every per-env byte is touched once per step)
 //   * TMA bulk copy (cp.async.bulk + mbarrier) that stages the packed static tables into shared memory
 //   * exact division of small integers by run-time constants via multiply-high
@@ -22,26 +22,13 @@ constexpr int kTileEnvs = kWarp * kEnvsPerThread;  // 512 == GPT_ENV_ALIGN
 constexpr int kQuadStride = kWarp * kQuad;     // 128 envs between a thread's consecutive quads
 
 // ------------------------------------------------------------------------------------------
-// Philox4x32-10 (Salmon et al., SC'11).  ctr = {env_lo, env_hi, step_lo, step_hi^stream}, key = seed.
+// Philox4x32 (Salmon et al., SC'11).  ctr = {env_lo, env_hi, step_lo, step_hi^stream}, key = seed.
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
-  constexpr uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
-#pragma unroll
-  for (int r = 0; r < 10; ++r) {
-    const uint32_t hi0 = __umulhi(M0, c.x), lo0 = M0 * c.x;
-    const uint32_t hi1 = __umulhi(M1, c.z), lo1 = M1 * c.z;
-    c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
-    k.x += W0;
-    k.y += W1;
-  }
-  return c;
-}
-
 // The key is the same for every thread of a launch, so the host expands the ten round keys once
 // (key + r*W) and passes them in the kernel parameters: each round reads its key straight from the
 // constant bank instead of spending two integer adds per round per call.
 struct RngKey {
-  uint32_t rk[20];             // rk[2r], rk[2r+1] = Philox key words of round r
+  uint32_t rk[20];             // rk[2r], rk[2r+1] = Philox key words of round r (the first kRounds rounds are used)
   uint32_t step_lo, step_hi;   // step counter (incremented by the host once per launch / per step)
 };
 __host__ __device__ inline void expand_round_keys(RngKey& k, uint64_t seed) {
@@ -65,7 +52,6 @@ __device__ __forceinline__ uint4 philox4x32(uint4 c, const RngKey& k) {
   }
   return c;
 }
-__device__ __forceinline__ uint4 philox4x32_10(uint4 c, const RngKey& k) { return philox4x32<10>(c, k); }
 
 // Two independent blocks under the same key with their rounds interleaved: each round key is read once and feeds both
 // blocks (written out so that the compiler keeps the keys in uniform registers instead of copying them around).
@@ -83,13 +69,14 @@ __device__ __forceinline__ void philox4x32_x2(uint4& a, uint4& b, const RngKey& 
   }
 }
 
-// Rounds.  Episode-level draws (reset state, spawn cells, passenger respawn: a handful per episode) use the standard
-// Philox4x32-10.  The per-step dynamics draws (action slip, Gaussian motion noise, target moves: one block per quad
-// and step, up to 30 % of a fused kernel's instructions) use Philox4x32-7 — the same counter-based generator at the
-// smallest round count that passes BigCrush (Salmon et al., SC'11; Random123 ships it as philox4x32_7), i.e. without
-// the safety margin.  Documented deviation: the law of every draw is unchanged.
-constexpr int kResetRounds = 10;
-constexpr int kStepRounds = 7;
+// Rounds.  Every draw of every family uses Philox4x32-7: the same counter-based generator at the smallest round count
+// that passes BigCrush (Salmon et al., SC'11, Table 2; Random123 ships it as philox4x32_7), i.e. without the three
+// rounds of safety margin of the default Philox4x32-10.  The per-step slip / noise blocks were up to 30 % of a fused
+// kernel's instructions at 10 rounds, and the rare respawn path — taken by ~30 % of the warp iterations under a random
+// policy — is latency the whole warp waits for.  Documented deviation: the law of every draw is
+// unchanged; tests/philox_host.py restates the generator and checks it against Random123's known-answer vectors.
+constexpr int kRounds = 7;
+constexpr int kResetRounds = kRounds, kStepRounds = kRounds;
 
 // one Philox block for (global env id, step, stream)
 template <int ROUNDS = kResetRounds>

@@ -265,8 +265,8 @@ __device__ __forceinline__ uint32_t rooms_respawn_inline(const RoomsParams& P, c
   } else {
     const uint64_t ctr = (DEVCTR ? ctr_dev : (((uint64_t)P.rng.step_hi << 32) | P.rng.step_lo)) + t;   // step index inside a fused launch
     const uint64_t ge = (uint64_t)(P.env_offset + env);
-    const uint4 r = philox4x32_10(make_uint4((uint32_t)ge, (uint32_t)(ge >> 32), (uint32_t)ctr,
-                                             ((uint32_t)(ctr >> 32) & 0x00FFFFFFu) ^ (1u << 24)), P.rng);
+    const uint4 r = philox4x32<kRounds>(make_uint4((uint32_t)ge, (uint32_t)(ge >> 32), (uint32_t)ctr,
+                                                                ((uint32_t)(ctr >> 32) & 0x00FFFFFFu) ^ (1u << 24)), P.rng);
     if (RGOAL) gcell = valid[bounded(r.y, (uint32_t)P.n_valid)];
     cell = valid[bounded(r.x, (uint32_t)P.n_valid)];
   }

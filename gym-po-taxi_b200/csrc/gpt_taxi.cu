@@ -248,7 +248,7 @@ __device__ __forceinline__ uint32_t taxi_fix_inline(const TaxiParams& P, const u
   }
   const uint64_t ctr = (DEVCTR ? ctr_dev : (((uint64_t)P.rng.step_hi << 32) | P.rng.step_lo)) + t;   // Philox step counter of this step
   const uint64_t ge = (uint64_t)(P.env_offset + env);
-  const uint4 rnd = philox4x32_10(make_uint4((uint32_t)ge, (uint32_t)(ge >> 32), (uint32_t)ctr, (uint32_t)(ctr >> 32) & 0x00FFFFFFu), P.rng);
+  const uint4 rnd = philox4x32<kRounds>(make_uint4((uint32_t)ge, (uint32_t)(ge >> 32), (uint32_t)ctr, (uint32_t)(ctr >> 32) & 0x00FFFFFFu), P.rng);
   if (full) {  // the law of argmax(multinomial(ns, uniform over valid states)), sampled through its alias table
     const uint64_t w = (uint64_t)rnd.x * (uint32_t)P.n_valid;
     const uint2 e = alias[(uint32_t)(w >> 32)];

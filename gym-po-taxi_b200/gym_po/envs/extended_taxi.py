@@ -8,7 +8,7 @@ the whole step runs in one fused CUDA kernel (csrc/gpt_taxi.cu) behind the C ABI
 Differences a caller can observe (also listed in INTEGRATION.md):
 * inputs/outputs are CUDA ``torch`` tensors: obs int32, reward float32, terminated/truncated bool;
   they are views of buffers the next ``step`` overwrites;
-* random numbers come from Philox4x32-10 (``rng_mode='philox'``) instead of numpy's PCG64.  The
+* random numbers come from Philox4x32-7 (``rng_mode='philox'``) instead of numpy's PCG64.  The
   *laws* are the reference's (including its argmax-of-multinomial reset distribution); streams
   differ.  ``rng_mode='replay'`` consumes pre-drawn values for bit-exact comparison.
 """

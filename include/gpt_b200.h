@@ -66,7 +66,7 @@ extern "C" {
 #define GPT_FAMILY_MSROOMS 5 /* MultistoryFourRoomsEnv              rooms/msrooms.py:257-428 */
 
 /* random-number modes */
-#define GPT_RNG_PHILOX 0 /* Philox4x32-10, key = seed, counter = (global env id, step, stream) */
+#define GPT_RNG_PHILOX 0 /* Philox4x32-7, key = seed, counter = (global env id | quad id, step, stream) */
 #define GPT_RNG_REPLAY 1 /* consume pre-drawn values from the bound REPLAY arrays (parity tests) */
 
 /* ROOMS / CROOMS observation kinds (substring dispatch of rooms/rooms.py:19-67 resolved by the host) */

@@ -1,6 +1,6 @@
 """TEST INFRASTRUCTURE — the random draws of the Philox-mode CUDA kernels, rebuilt on the host.
 
-The product kernels draw from Philox4x32 (10 rounds for episode-level draws, 7 for the per-step slip) keyed by the env seed with counter (global env id | quad id, step
+The product kernels draw from Philox4x32-7 keyed by the env seed with counter (global env id | quad id, step
 counter, stream) and map the 32-bit words to env decisions through Walker alias tables / multiply-high
 (csrc/gpt_common.cuh, gpt_taxi.cu ``taxi_fix_inline``, gpt_rooms_kernel.cuh, gpt_msrooms.cu).  ``PhiloxDraws``
 recomputes exactly those decisions with numpy and hands them to the oracle envs through the oracle's draw-source
@@ -21,10 +21,10 @@ W0, W1 = 0x9E3779B9, 0xBB67AE85
 MASK = np.uint64(0xFFFFFFFF)
 
 
-RESET_ROUNDS, STEP_ROUNDS = 10, 7   # csrc/gpt_common.cuh kResetRounds / kStepRounds
+RESET_ROUNDS = STEP_ROUNDS = 7   # csrc/gpt_common.cuh kRounds: every draw is Philox4x32-7
 
 
-def philox4x32_10(c0, c1, c2, c3, k0, k1, rounds=10):
+def philox4x32(c0, c1, c2, c3, k0, k1, rounds=10):
     """Vectorised Philox4x32-R (default 10 rounds).  c*: uint32-valued arrays (any broadcastable shapes), k0/k1: python ints."""
     c0, c1, c2, c3 = (np.asarray(c, dtype=np.uint64) & MASK for c in (c0, c1, c2, c3))
     c0, c1, c2, c3 = np.broadcast_arrays(c0, c1, c2, c3)
@@ -83,7 +83,7 @@ class PhiloxDraws:
             self._cache = {k: v for k, v in self._cache.items() if k[0] == self.counter}
             ctr_lo = self.counter & 0xFFFFFFFF
             ctr_hi = ((self.counter >> 32) & 0x00FFFFFF) ^ (stream << 24)
-            self._cache[key] = philox4x32_10(ids & MASK, ids >> np.uint64(32), ctr_lo, ctr_hi, self.k0, self.k1, rounds)
+            self._cache[key] = philox4x32(ids & MASK, ids >> np.uint64(32), ctr_lo, ctr_hi, self.k0, self.k1, rounds)
         return self._cache[key]
 
     # ---- Taxi (gpt_taxi.cu taxi_fix_inline) -----------------------------------------------------

@@ -1,7 +1,7 @@
-"""CPU: the host restatement of Philox4x32-10 (tests/philox_host.py) against the Random123 known-answer vectors."""
+"""CPU: the host restatement of Philox4x32 (7 and 10 rounds) (tests/philox_host.py) against the Random123 known-answer vectors."""
 import numpy as np
 
-from philox_host import mulhi, philox4x32_10
+from philox_host import mulhi, philox4x32
 
 KAT = [  # Random123 kat_vectors: philox4x32 10 rounds — counter, key -> output
     ((0, 0, 0, 0), (0, 0), (0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8)),
@@ -12,7 +12,7 @@ KAT = [  # Random123 kat_vectors: philox4x32 10 rounds — counter, key -> outpu
 
 def test_philox_known_answers():
     for ctr, key, want in KAT:
-        got = philox4x32_10(*ctr, *key)
+        got = philox4x32(*ctr, *key)
         assert tuple(int(x) for x in got) == want
 
 
@@ -25,16 +25,16 @@ KAT7 = [  # Random123 kat_vectors: philox4x32 7 rounds (the per-step slip / nois
 
 def test_philox_7_rounds_known_answers():
     for ctr, key, want in KAT7:
-        got = philox4x32_10(*ctr, *key, rounds=7)
+        got = philox4x32(*ctr, *key, rounds=7)
         assert tuple(int(x) for x in got) == want
 
 
 def test_philox_vectorised_matches_scalar():
     rng = np.random.default_rng(0)
     c = rng.integers(0, 2**32, size=(4, 257), dtype=np.uint64)
-    out = philox4x32_10(c[0], c[1], c[2], c[3], 0x12345678, 0x9abcdef0)
+    out = philox4x32(c[0], c[1], c[2], c[3], 0x12345678, 0x9abcdef0)
     for i in (0, 100, 256):
-        one = philox4x32_10(int(c[0, i]), int(c[1, i]), int(c[2, i]), int(c[3, i]), 0x12345678, 0x9abcdef0)
+        one = philox4x32(int(c[0, i]), int(c[1, i]), int(c[2, i]), int(c[3, i]), 0x12345678, 0x9abcdef0)
         assert [int(x[i]) for x in out] == [int(x) for x in one]
 
 
