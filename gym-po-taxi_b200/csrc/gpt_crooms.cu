@@ -154,7 +154,9 @@ int crooms_launch(gpt_env* env, const LaunchArgs& a) {
   if (grid) smem = P.stage_off + (size_t)warps * kQuadStride * P.grid_n * P.grid_n;
   const bool devctr = env->graph_mode && !replay;   // graph mode: step counter in device memory
   P.ctr_ptr = env->d_counter;
-  void* k = c.c_state_f32 ? crooms_pick_f32(c.rooms_obs_kind, replay, devctr) : crooms_pick_obs<double>(c.rooms_obs_kind, replay, devctr);
+  // the constructor's default configuration has its own instantiation (flags folded at compile time)
+  const bool spec = P.act_kind == kActF32 && P.has_noise && !P.use_velocity && !P.rgoal;
+  void* k = c.c_state_f32 ? crooms_pick_f32(c.rooms_obs_kind, replay, devctr, spec) : crooms_pick_obs<double>(c.rooms_obs_kind, replay, devctr);
   if (!k) return fail(GPT_E_ARG, "crooms: no kernel for this obs kind");
   if (smem > 40 * 1024) {  // static + dynamic shared memory above 48 KB needs the opt-in
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -5,7 +5,7 @@
 
 namespace gpt {
 
-void* crooms_pick_f32(int obs, bool replay, bool devctr) { return crooms_pick_obs<float>(obs, replay, devctr); }
+void* crooms_pick_f32(int obs, bool replay, bool devctr, bool spec) { return crooms_pick_obs<float>(obs, replay, devctr, spec); }
 void* tag_pick_f32(bool replay, bool devctr) { return tag_pick_rr<float>(replay, devctr); }
 
 }  // namespace gpt

@@ -154,10 +154,14 @@ __device__ GPT_CONT_RESPAWN_ATTR uint32_t crooms_respawn(const CRoomsParams& P, 
 #ifndef GPT_CROOMS_MINB
 #define GPT_CROOMS_MINB 7   // measured on B200 (2^22 envs, f32): 1 -> 83 G, 6 -> 106 G, 7 -> 113.5 G, 8 -> 110.6 G env-steps/s
 #endif
-template <typename R, int OBS, bool REPLAY, bool DEVCTR = false>
+// SPEC: the configuration the constructor defaults to (yx float32 actions, action noise, no velocity, fixed goal) as
+// compile-time constants — the per-env transition becomes ONE basic block, so the four envs of a quad interleave.
+template <typename R, int OBS, bool REPLAY, bool DEVCTR = false, bool SPEC = false>
 __global__ void __launch_bounds__(128, GPT_CROOMS_MINB) crooms_step_kernel(const __grid_constant__ CRoomsParams P) {
   using V2 = typename RealTraits<R>::V2;
   constexpr bool kFast = sizeof(R) == 4;   // float32 fast mode: reciprocal multiply, squared distances, MUFU noise
+  const bool rgoal = SPEC ? false : P.rgoal != 0, use_velocity = SPEC ? false : P.use_velocity != 0, has_noise = SPEC ? true : P.has_noise != 0;
+  const int act_kind = SPEC ? (int)kActF32 : P.act_kind;
   const R cell_size = kFast ? (R)P.f_cell : (R)P.cell_size, inv_cell = kFast ? (R)P.f_inv_cell : (R)0, half = kFast ? (R)P.f_half : (R)(P.cell_size / 2);
   const R a_std = kFast ? (R)P.f_std : (R)P.action_std, a_pow = kFast ? (R)P.f_pow : (R)P.action_power;
   const R max_y = kFast ? (R)P.f_max_y : (R)P.max_y, max_x = kFast ? (R)P.f_max_x : (R)P.max_x;
@@ -196,10 +200,10 @@ __global__ void __launch_bounds__(128, GPT_CROOMS_MINB) crooms_step_kernel(const
     const int4 e4 = ld_stream(reinterpret_cast<const int4*>(P.elapsed + q));
     ev[0] = e4.x; ev[1] = e4.y; ev[2] = e4.z; ev[3] = e4.w;
     RealTraits<R>::load4(P.agent, q, pos);
-    if (P.rgoal) RealTraits<R>::load4(P.goal, q, gpos);
-    if (P.use_velocity) RealTraits<R>::load4(P.velocity, q, vel);
-    if (P.act_kind == kActI8) abytes = ld_stream(reinterpret_cast<const uint32_t*>(reinterpret_cast<const int8_t*>(P.actions) + q));
-    else load_actions4<R>(P.actions, P.act_kind, q, push);
+    if (rgoal) RealTraits<R>::load4(P.goal, q, gpos);
+    if (use_velocity) RealTraits<R>::load4(P.velocity, q, vel);
+    if (act_kind == kActI8) abytes = ld_stream(reinterpret_cast<const uint32_t*>(reinterpret_cast<const int8_t*>(P.actions) + q));
+    else load_actions4<R>(P.actions, act_kind, q, push);
   }
 
   stage_tables_wait(&bar);
@@ -224,7 +228,7 @@ __global__ void __launch_bounds__(128, GPT_CROOMS_MINB) crooms_step_kernel(const
 
   if (!reset_all) {
     uint4 slipq = make_uint4(0, 0, 0, 0);
-    if (!REPLAY && P.act_kind == kActI8) {  // one Philox block feeds the slip draws of the quad
+    if (!REPLAY && act_kind == kActI8) {  // one Philox block feeds the slip draws of the quad
       const uint64_t gq = (uint64_t)(P.env_offset + q) >> 2;
       slipq = rnd_block<DEVCTR, kStepRounds>(P.rng, ctr_dev, gq, 3u);
     }
@@ -248,7 +252,7 @@ __global__ void __launch_bounds__(128, GPT_CROOMS_MINB) crooms_step_kernel(const
       uint4 r0 = make_uint4(0, 0, 0, 0);
       if constexpr (kFast && !REPLAY) r0 = make_uint4(qw[3 * k], qw[3 * k + 1], qw[3 * k + 2] & 0xFFFF0000u, qw[3 * k + 2] << 16);
       else if (!REPLAY) r0 = rnd_block<DEVCTR, kStepRounds>(P.rng, ctr_dev, (uint64_t)(P.env_offset + env), 0u);
-      if (P.act_kind == kActI8) {
+      if (act_kind == kActI8) {
         uint32_t a = (abytes >> (8 * k)) & 0xFFu;
         a = a < n ? a : n - 1;
         uint32_t d8;
@@ -266,7 +270,7 @@ __global__ void __launch_bounds__(128, GPT_CROOMS_MINB) crooms_step_kernel(const
         }
         push[k] = RealTraits<R>::make((R)dir_dy(d8), (R)dir_dx(d8));
       }
-      if (P.has_noise) {
+      if (has_noise) {
         V2 z;
         if constexpr (REPLAY) {
           const double2 zz = P.rp_noise[env];  // already scaled by action_std (numpy normal(scale=std))
@@ -285,7 +289,7 @@ __global__ void __launch_bounds__(128, GPT_CROOMS_MINB) crooms_step_kernel(const
       push[k].y = push[k].y * a_pow;
       // ---- _apply_action (crooms.py:300-331) ----
       V2 target;
-      if (P.use_velocity) {
+      if (use_velocity) {
         vel[k].x = clipd<R>(vel[k].x + push[k].x, (R)-5.0, (R)5.0);
         vel[k].y = clipd<R>(vel[k].y + push[k].y, (R)-5.0, (R)5.0);
         target = RealTraits<R>::make(pos[k].x + vel[k].x, pos[k].y + vel[k].y);
@@ -300,8 +304,10 @@ __global__ void __launch_bounds__(128, GPT_CROOMS_MINB) crooms_step_kernel(const
         const float2 zz = normal_pair_f(r0.z, r0.w);
         const R cy = floor(pos[k].x * inv_cell) * cell_size + half;
         const R cx = floor(pos[k].y * inv_cell) * cell_size + half;
-        const R jy = clipd<R>(cy + zz.x * (R)0.5, cy - half, cy + half - (R)1e-8);
-        const R jx = clipd<R>(cx + zz.y * (R)0.5, cx - half, cx + half - (R)1e-8);
+        // upper bound: the reference's `centre + half - 1e-8` is below float32 resolution; (1 - 2^-23) * (centre + half)
+        // is 1-2 ulp below the cell's far edge, so a clipped jitter never lands in the next (possibly wall) cell
+        const R jy = clipd<R>(cy + zz.x * (R)0.5, cy - half, (cy + half) * (R)0.99999988f);
+        const R jx = clipd<R>(cx + zz.y * (R)0.5, cx - half, (cx + half) * (R)0.99999988f);
         pos[k].x = blocked ? jy : target.x;
         pos[k].y = blocked ? jx : target.y;
         vel[k].x = blocked ? (R)0 : vel[k].x;
@@ -320,8 +326,10 @@ __global__ void __launch_bounds__(128, GPT_CROOMS_MINB) crooms_step_kernel(const
             const double2 zz = normal_pair(rnd_block<DEVCTR>(P.rng, ctr_dev, (uint64_t)(P.env_offset + env), 2u));
             z = RealTraits<R>::make((R)zz.x * (R)0.5, (R)zz.y * (R)0.5);
           }
-          pos[k].x = clipd<R>(cy + z.x, cy - half, cy + half - (R)1e-8);
-          pos[k].y = clipd<R>(cx + z.y, cx - half, cx + half - (R)1e-8);
+          const R hy = kFast ? (cy + half) * (R)0.99999988f : cy + half - (R)1e-8;   // float32: see above
+          const R hx = kFast ? (cx + half) * (R)0.99999988f : cx + half - (R)1e-8;
+          pos[k].x = clipd<R>(cy + z.x, cy - half, hy);
+          pos[k].y = clipd<R>(cx + z.y, cx - half, hx);
           vel[k] = RealTraits<R>::make(0, 0);
         }
       }
@@ -349,15 +357,15 @@ __global__ void __launch_bounds__(128, GPT_CROOMS_MINB) crooms_step_kernel(const
         if (i == k) {
           ev[i] = 0;
           pos[i] = np;
-          if (P.rgoal) gpos[i] = ng;
+          if (rgoal) gpos[i] = ng;
           vel[i] = RealTraits<R>::make(0, 0);
         }
       }
     }
   }
   RealTraits<R>::store4(P.agent, q, pos);
-  if (P.rgoal) RealTraits<R>::store4(P.goal, q, gpos);
-  if (P.use_velocity) RealTraits<R>::store4(P.velocity, q, vel);
+  if (rgoal) RealTraits<R>::store4(P.goal, q, gpos);
+  if (use_velocity) RealTraits<R>::store4(P.velocity, q, vel);
   st_stream(reinterpret_cast<int4*>(P.elapsed + q), make_int4(ev[0], ev[1], ev[2], ev[3]));
   if (!reset_all) {
     st_stream(reinterpret_cast<float4*>(P.reward + q), make_float4(rv[0], rv[1], rv[2], rv[3]));
@@ -568,25 +576,30 @@ __global__ void __launch_bounds__(128, GPT_TAG_MINB) tag_step_kernel(const __gri
 
 // Instantiations: the float64 kernels (bit-exact parity with numpy) live in gpt_crooms.cu, compiled with -fmad=false;
 // the float32 fast-mode kernels live in gpt_crooms_f32.cu, compiled with FMA contraction enabled.
+// `spec` = the launch has the default configuration (see SPEC above); only the float32 Philox kernels carry that
+// instantiation, everything else ignores the hint.
 template <typename R, int OBS>
-static void* crooms_pick_rr(bool replay, bool devctr) {
+static void* crooms_pick_rr(bool replay, bool devctr, bool spec) {
   using K = void (*)(const CRoomsParams);
+  if constexpr (sizeof(R) == 4) {
+    if (spec && !replay) return devctr ? (void*)(K)crooms_step_kernel<R, OBS, false, true, true> : (void*)(K)crooms_step_kernel<R, OBS, false, false, true>;
+  }
   if (devctr) return replay ? nullptr : (void*)(K)crooms_step_kernel<R, OBS, false, true>;   // graph mode (Philox)
   return replay ? (void*)(K)crooms_step_kernel<R, OBS, true> : (void*)(K)crooms_step_kernel<R, OBS, false>;
 }
 template <typename R>
-static void* crooms_pick_obs(int obs, bool replay, bool devctr = false) {
+static void* crooms_pick_obs(int obs, bool replay, bool devctr = false, bool spec = false) {
   switch (obs) {
-    case GPT_OBS_ROOM: return crooms_pick_rr<R, GPT_OBS_ROOM>(replay, devctr);
-    case GPT_OBS_ROOM_GOAL: return crooms_pick_rr<R, GPT_OBS_ROOM_GOAL>(replay, devctr);
-    case GPT_OBS_MDP: return crooms_pick_rr<R, GPT_OBS_MDP>(replay, devctr);
-    case GPT_OBS_MDP_GOAL: return crooms_pick_rr<R, GPT_OBS_MDP_GOAL>(replay, devctr);
-    case GPT_OBS_VEC_MDP: return crooms_pick_rr<R, GPT_OBS_VEC_MDP>(replay, devctr);
-    case GPT_OBS_VEC_MDP_GOAL: return crooms_pick_rr<R, GPT_OBS_VEC_MDP_GOAL>(replay, devctr);
-    case GPT_OBS_HANSEN: return crooms_pick_rr<R, GPT_OBS_HANSEN>(replay, devctr);
-    case GPT_OBS_VEC_HANSEN: return crooms_pick_rr<R, GPT_OBS_VEC_HANSEN>(replay, devctr);
-    case GPT_OBS_VEC_HANSEN_GOAL: return crooms_pick_rr<R, GPT_OBS_VEC_HANSEN_GOAL>(replay, devctr);
-    case GPT_OBS_GRID: return crooms_pick_rr<R, GPT_OBS_GRID>(replay, devctr);
+    case GPT_OBS_ROOM: return crooms_pick_rr<R, GPT_OBS_ROOM>(replay, devctr, spec);
+    case GPT_OBS_ROOM_GOAL: return crooms_pick_rr<R, GPT_OBS_ROOM_GOAL>(replay, devctr, spec);
+    case GPT_OBS_MDP: return crooms_pick_rr<R, GPT_OBS_MDP>(replay, devctr, spec);
+    case GPT_OBS_MDP_GOAL: return crooms_pick_rr<R, GPT_OBS_MDP_GOAL>(replay, devctr, spec);
+    case GPT_OBS_VEC_MDP: return crooms_pick_rr<R, GPT_OBS_VEC_MDP>(replay, devctr, spec);
+    case GPT_OBS_VEC_MDP_GOAL: return crooms_pick_rr<R, GPT_OBS_VEC_MDP_GOAL>(replay, devctr, spec);
+    case GPT_OBS_HANSEN: return crooms_pick_rr<R, GPT_OBS_HANSEN>(replay, devctr, spec);
+    case GPT_OBS_VEC_HANSEN: return crooms_pick_rr<R, GPT_OBS_VEC_HANSEN>(replay, devctr, spec);
+    case GPT_OBS_VEC_HANSEN_GOAL: return crooms_pick_rr<R, GPT_OBS_VEC_HANSEN_GOAL>(replay, devctr, spec);
+    case GPT_OBS_GRID: return crooms_pick_rr<R, GPT_OBS_GRID>(replay, devctr, spec);
   }
   return nullptr;
 }
@@ -596,7 +609,7 @@ static void* tag_pick_rr(bool replay, bool devctr = false) {
   if (devctr) return replay ? nullptr : (void*)(K)tag_step_kernel<R, false, true>;   // graph mode (Philox)
   return replay ? (void*)(K)tag_step_kernel<R, true> : (void*)(K)tag_step_kernel<R, false>;
 }
-void* crooms_pick_f32(int obs, bool replay, bool devctr);   // gpt_crooms_f32.cu
+void* crooms_pick_f32(int obs, bool replay, bool devctr, bool spec);   // gpt_crooms_f32.cu
 void* tag_pick_f32(bool replay, bool devctr);
 
 }  // namespace gpt

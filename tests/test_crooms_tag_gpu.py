@@ -168,6 +168,40 @@ F32_RTOL = 1e-5
 F32_FLIP_RATE = 2e-4
 
 
+def test_crooms_float32_philox_stays_in_walkable_cells():
+    """float32 fast mode, Philox (the benchmarked CRooms configuration): agents pushed against walls for many steps
+    never end up in a wall cell (the jitter's upper clip must stay strictly inside the cell: `centre + half - 1e-8` is
+    not representable in float32), spawn at cell centres, noise law N(0, action_std^2)."""
+    from gym_po.envs import CRoomsEnv
+    b = 1 << 20
+    env = CRoomsEnv(b, "4", obs_type="vector_mdp", device=DEV, seed=9, precision="float32")
+    obs = env.reset(seed=9)
+    assert obs.dtype == torch.float32
+    grid = torch.as_tensor(env.grid, device=DEV)
+    cells = obs.floor().long()
+    assert bool((grid[cells[:, 0], cells[:, 1]] >= 0).all())
+    assert bool(((obs - obs.floor()) == 0.5).all())
+    gen = torch.Generator(device=DEV).manual_seed(0)
+    blocked = 0
+    for t in range(120):
+        # a constant diagonal push keeps most agents pressed into a corner: lots of rejected moves
+        a = torch.ones((env.capacity, 2), device=DEV) * (1.0 if t % 40 < 20 else -1.0)
+        a += (torch.rand((env.capacity, 2), device=DEV, generator=gen) - 0.5) * 0.2
+        before = env.agent_yx.clone()
+        obs, rew, term, trunc, _ = env.step(a)
+        cells = obs[:b].floor().long()
+        assert bool((grid[cells[:, 0], cells[:, 1]] >= 0).all()), f"agent inside a wall cell at step {t}"
+        stay = (before[:b].floor() == obs[:b].floor()).all(-1) & ~(term[:b] | trunc[:b])
+        blocked += int(stay.sum())
+    assert blocked > 20 * b     # the scenario really exercises the rejection branch
+    start = np.tile([4.5, 4.5], (b, 1))
+    env.set_state(agent=start, goal=None, velocity=None, elapsed=np.zeros(b, dtype=int))
+    obs, *_ = env.step(torch.zeros((env.capacity, 2), dtype=torch.float32, device=DEV))
+    d = (obs[:b] - 4.5).double().cpu().numpy()
+    assert abs(d.mean()) < 1e-3 and abs(d.std() - 0.2) < 1e-3
+    assert abs((np.abs(d) > 0.4).mean() - 0.0455) < 2e-3
+
+
 def _close(g, o):
     o = np.asarray(o, dtype=np.float64)
     return np.abs(g.astype(np.float64) - o) <= F32_RTOL * np.maximum(1.0, np.abs(o))
