@@ -417,9 +417,11 @@ int gpt_step_many(gpt_env* env, const void* actions, int32_t n_steps, int64_t ou
   return GPT_OK;
 }
 
-int gpt_set_fused_steps(gpt_env* env, int enable) {
+int gpt_set_fused_steps(gpt_env* env, int mode) {
   if (!env) return fail(GPT_E_ARG, "gpt_set_fused_steps: NULL env");
-  env->no_fused_steps = !enable;
+  if (mode < GPT_FUSED_OFF || mode > GPT_FUSED_THREADS) return fail(GPT_E_ARG, "gpt_set_fused_steps: mode must be 0..3");
+  env->no_fused_steps = mode == GPT_FUSED_OFF;
+  env->fused_io = mode == GPT_FUSED_TMA ? 1 : (mode == GPT_FUSED_THREADS ? 2 : 0);
   return GPT_OK;
 }
 

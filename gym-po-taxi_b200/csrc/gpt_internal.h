@@ -45,6 +45,7 @@ struct gpt_env {
   uint64_t counter = 0;  // Philox step counter
   int64_t launches = 0;
   bool no_fused_steps = false;   // gpt_set_fused_steps(env, 0)
+  int fused_io = 0;              // gpt_set_fused_steps(env, 2 / 3): 0 = family default, 1 = TMA I/O, 2 = per-thread loads/stores
   // graph mode (gpt_set_graph_mode): the Philox step counter lives in device memory; the DEVCTR kernels read and advance
   // it themselves (devctr_fetch_and_advance).  d_counter[0] = step counter, d_counter[1] = arrival count of the grid.
   bool graph_mode = false;

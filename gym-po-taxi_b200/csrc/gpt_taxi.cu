@@ -413,6 +413,192 @@ __global__ void __launch_bounds__(THREADS, STATS ? 1 : GPT_TAXI_MINB_MULTI * 128
 }
 
 
+// ---- fused multi-step launch with TMA I/O (the default fused path) ----------------------------------------------------
+// Same step as taxi_table_multi_kernel, bit-identical results, but the per-step I/O is moved by the TMA engine instead of
+// per-thread loads and stores: the CTA's action rows [t][1024 envs] are fetched by bulk copies into a ring of
+// kTmaActRows shared-memory rows (one mbarrier per row, refilled as rows are consumed), and every step's outputs are
+// staged in shared memory (obs 4 KB | reward 4 KB | terminated 1 KB | truncated 1 KB) and written with four bulk stores
+// per CTA and step (double-buffered; cp.async.bulk.wait_group.read guards the reuse).  On the rollout access pattern —
+// 86 % writes into 4 output streams x T slots — this moves 6.2 TB/s where per-thread stores reach 5.6 TB/s
+// (scripts/stream_pattern_probe4.cu).  One CTA barrier per step.
+constexpr int kTmaEnvs = 1024;                 // envs per CTA: 128 threads x 2 quads x 4 envs
+constexpr int kTmaStage = kTmaEnvs * 10;       // staging bytes per buffer
+#ifndef GPT_TAXI_TMA_BUFS
+#define GPT_TAXI_TMA_BUFS 2
+#endif
+#ifndef GPT_TAXI_TMA_ACT_ROWS
+#define GPT_TAXI_TMA_ACT_ROWS 4   // 43.5 KB per CTA on the 5x5 map = 5 CTAs per SM (measured: 8 rows = 4 CTAs/SM 91.3 us, 4 rows = 5 CTAs/SM 87.1 us per 10-step launch)
+#endif
+constexpr int kTmaBufs = GPT_TAXI_TMA_BUFS;          // power of two
+constexpr int kTmaActRows = GPT_TAXI_TMA_ACT_ROWS;   // power of two
+#ifndef GPT_TAXI_MINB_TMA
+#define GPT_TAXI_MINB_TMA 4
+#endif
+struct TaxiTmaParams {
+  TaxiMultiParams m;
+  uint32_t tab_bytes;     // bytes of the blob's fused part (hobs | alias | trans), staged at shared offset 0
+  uint32_t stage_off;     // shared-memory offset of the staging buffers (128-byte aligned), the action ring follows
+};
+
+template <bool ONE, bool DEVCTR = false>
+__global__ void __launch_bounds__(128, GPT_TAXI_MINB_TMA) taxi_multi_tma_kernel(const __grid_constant__ TaxiTmaParams TP) {
+  constexpr bool REPLAY = false;
+  constexpr int QPT = 2;
+  const TaxiMultiParams& M = TP.m;
+  const TaxiParams& P = M.p;
+  const int32_t n_steps = M.n_steps;
+  extern __shared__ __align__(128) uint8_t smem[];
+  __shared__ __align__(8) uint64_t bar, abar[kTmaActRows];
+  pdl_launch_dependents();
+  if (threadIdx.x == 0) {
+    mbar_init(&bar, 1);
+#pragma unroll
+    for (int i = 0; i < kTmaActRows; ++i) mbar_init(&abar[i], 1);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {   // static tables: independent of the previous launch, staged before the dependency wait
+    mbar_expect_tx(&bar, TP.tab_bytes);
+    tma_bulk_g2s(smem, P.blob, TP.tab_bytes, &bar);
+  }
+  const uint8_t* trans = smem + P.trans_off;
+  const uint16_t* hobs = reinterpret_cast<const uint16_t*>(smem + P.hobs_off);
+  const uint2* alias = reinterpret_cast<const uint2*>(smem + P.alias_off);
+  uint8_t* stage = smem + TP.stage_off;
+  uint8_t* acts = stage + kTmaBufs * kTmaStage;
+
+  const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  const int64_t first = (int64_t)P.first_tile * kTileEnvs, last = first + (int64_t)P.n_tiles * kTileEnvs;
+  const int64_t tile = first + (int64_t)blockIdx.x * kTmaEnvs;          // the CTA's envs: [tile, tile + valid)
+  const uint32_t valid = (uint32_t)(last - tile < kTmaEnvs ? last - tile : kTmaEnvs);   // 512 or 1024
+  const uint32_t loc = warp * (kQuadStride * QPT) + lane * kQuad;       // thread's first quad inside the CTA tile (+ j*128)
+  const bool active = loc < valid;                                      // whole warps: a warp owns 256 consecutive envs
+  const int64_t base = tile + loc;
+  pdl_wait();   // the previous launch's writes are complete and visible from here on
+  if (threadIdx.x == 0) {   // the first action rows
+    const int rows = n_steps < kTmaActRows ? n_steps : kTmaActRows;
+    for (int r = 0; r < rows; ++r) {
+      mbar_expect_tx(&abar[r], valid);
+      tma_bulk_g2s(acts + r * kTmaEnvs, P.actions + (int64_t)r * M.act_stride + tile, valid, &abar[r]);
+    }
+  }
+  uint64_t ctr_dev = 0;   // graph mode: step counter from device memory, advanced by n_steps for the next launch
+  if constexpr (DEVCTR) ctr_dev = devctr_fetch_and_advance(P.ctr_ptr, (uint32_t)n_steps);
+  uint32_t off[QPT][4], ndv[QPT][4];   // off = state id << kRowShift
+  int32_t ev[QPT][4];
+#pragma unroll
+  for (int j = 0; j < QPT; ++j) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { off[j][k] = 0u; ndv[j][k] = 0u; ev[j][k] = 0; }
+    if (active) {
+      const int64_t q = base + j * kQuadStride;
+      const int4 s4 = ld_stream(reinterpret_cast<const int4*>(P.s + q));
+      const int4 e4 = ld_stream(reinterpret_cast<const int4*>(P.elapsed + q));
+      const uint32_t nd4 = ONE ? 0u : ld_stream(reinterpret_cast<const uint32_t*>(P.ndrop + q));
+      off[j][0] = (uint32_t)s4.x << kRowShift; off[j][1] = (uint32_t)s4.y << kRowShift;
+      off[j][2] = (uint32_t)s4.z << kRowShift; off[j][3] = (uint32_t)s4.w << kRowShift;
+      ev[j][0] = e4.x; ev[j][1] = e4.y; ev[j][2] = e4.z; ev[j][3] = e4.w;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) ndv[j][k] = (nd4 >> (8 * k)) & 0xFFu;
+    }
+  }
+  mbar_wait(&bar, 0);
+
+#pragma unroll 1
+  for (int32_t t = 0; t < n_steps; ++t) {
+    uint8_t* buf = stage + (t & (kTmaBufs - 1)) * kTmaStage;
+    const int slot = t & (kTmaActRows - 1);
+    mbar_wait(&abar[slot], (uint32_t)(t / kTmaActRows) & 1u);
+    if (active) {
+      uint32_t fix_done = 0, fix_goal = 0;   // bit 8k + j: env k of quad j finished its episode / delivered a passenger
+#pragma unroll
+      for (int j = 0; j < QPT; ++j) {
+        const uint32_t lq = loc + j * kQuadStride;
+        const uint32_t a4 = *reinterpret_cast<const uint32_t*>(acts + slot * kTmaEnvs + lq);
+        float rv[4];
+        int32_t ov[4];
+        uint32_t tw = 0, trw = 0, gw = 0;   // terminated / truncated / delivered, one byte per env
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const uint32_t aoff = (k == 0 ? (a4 << 2) : (a4 >> (8 * k - 2))) & 0x1Cu;   // 4 * (action & 7)
+          const uint32_t ent = *reinterpret_cast<const uint32_t*>(trans + off[j][k] + aoff);
+          const uint32_t goal = ent & kTransGoal;
+          if constexpr (!ONE) ndv[j][k] += goal;
+          off[j][k] = ent & kTransRow;
+          ov[k] = (int32_t)(ent >> 16);
+          ev[j][k] += 1;
+          rv[k] = goal ? P.r_goal : ((ent & kTransBad) ? P.r_bad : P.r_any);
+          const uint32_t term = ONE ? goal : (uint32_t)(ndv[j][k] == (uint32_t)P.n_dropoffs);      // (:276-279)
+          const uint32_t trunc = ev[j][k] > P.time_limit;
+          tw |= term << (8 * k);
+          trw |= trunc << (8 * k);
+          if constexpr (!ONE) gw |= goal << (8 * k);
+        }
+        fix_done |= ((tw | trw) & 0x01010101u) << j;
+        fix_goal |= (gw & 0x01010101u) << j;
+        *reinterpret_cast<int4*>(buf + lq * 4) = make_int4(ov[0], ov[1], ov[2], ov[3]);
+        *reinterpret_cast<float4*>(buf + 4 * kTmaEnvs + lq * 4) = make_float4(rv[0], rv[1], rv[2], rv[3]);
+        *reinterpret_cast<uint32_t*>(buf + 8 * kTmaEnvs + lq) = tw;
+        *reinterpret_cast<uint32_t*>(buf + 9 * kTmaEnvs + lq) = trw;
+      }
+      if (fix_done | fix_goal) {  // rare: full reset of finished envs, passenger respawn after a delivery (:283-286)
+#pragma unroll 1
+        for (uint32_t m = fix_done | fix_goal; m; m &= m - 1) {
+          const int bit = __ffs(m) - 1, k = bit >> 3, j = bit & 7;   // bit 8k + j <-> quad j, env k
+          const bool full = (fix_done >> bit) & 1u;
+          const int idx = j * 4 + k;
+          uint32_t cur = 0;
+#pragma unroll
+          for (int i = 0; i < 4 * QPT; ++i) cur = i == idx ? off[i >> 2][i & 3] : cur;
+          const uint32_t le = loc + j * kQuadStride + k;
+          const uint32_t fresh = taxi_fix_inline<REPLAY, DEVCTR>(P, alias, tile + le, (uint32_t)t, cur >> kRowShift, full, ctr_dev);
+          reinterpret_cast<int32_t*>(buf)[le] = (int32_t)hobs[fresh];   // observation of the post-reset state (same thread wrote the quad)
+#pragma unroll
+          for (int i = 0; i < 4 * QPT; ++i) {
+            if (i == idx) {
+              off[i >> 2][i & 3] = fresh << kRowShift;
+              ev[i >> 2][i & 3] = full ? 0 : ev[i >> 2][i & 3];
+              if constexpr (!ONE) ndv[i >> 2][i & 3] = full ? 0u : ndv[i >> 2][i & 3];
+            }
+          }
+        }
+      }
+    }
+    fence_proxy_async();   // the staged outputs become visible to the TMA engine
+    // the buffer step t+1 writes was last read by the bulk stores of step t-1
+    if (threadIdx.x == 0) tma_bulk_wait_read<kTmaBufs - 2>();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      // in-place outputs (out_stride 0: every step overwrites the same rows) are written by the LAST step only — bulk
+      // stores of different groups are not ordered against each other
+      if (M.out_stride != 0 || t == n_steps - 1) {
+        const int64_t o = (int64_t)t * M.out_stride + tile;
+        tma_bulk_s2g(P.obs + o, buf, 4 * valid);
+        tma_bulk_s2g(P.reward + o, buf + 4 * kTmaEnvs, 4 * valid);
+        tma_bulk_s2g(P.terminated + o, buf + 8 * kTmaEnvs, valid);
+        tma_bulk_s2g(P.truncated + o, buf + 9 * kTmaEnvs, valid);
+        tma_bulk_commit();
+      }
+      if (t + kTmaActRows < n_steps) {  // every thread has consumed this ring row (barrier above): refill it
+        mbar_expect_tx(&abar[slot], valid);
+        tma_bulk_g2s(acts + slot * kTmaEnvs, P.actions + (int64_t)(t + kTmaActRows) * M.act_stride + tile, valid, &abar[slot]);
+      }
+    }
+  }
+  if (active) {
+#pragma unroll
+    for (int j = 0; j < QPT; ++j) {
+      const int64_t q = base + j * kQuadStride;
+      st_stream(reinterpret_cast<int4*>(P.s + q), make_int4((int)(off[j][0] >> kRowShift), (int)(off[j][1] >> kRowShift),
+                                                            (int)(off[j][2] >> kRowShift), (int)(off[j][3] >> kRowShift)));
+      st_stream(reinterpret_cast<int4*>(P.elapsed + q), make_int4(ev[j][0], ev[j][1], ev[j][2], ev[j][3]));
+      st_stream(reinterpret_cast<uint32_t*>(P.ndrop + q),
+                ONE ? 0u : ((ndv[j][0] & 0xFFu) | ((ndv[j][1] & 0xFFu) << 8) | ((ndv[j][2] & 0xFFu) << 16) | ((ndv[j][3] & 0xFFu) << 24)));
+    }
+  }
+  if (threadIdx.x == 0) tma_bulk_wait_read<0>();   // shared memory must outlive the last bulk stores' reads
+}
+
+
 // ---- single-step kernel (gpt_step, replay mode, reset): compact 16-bit table, rare envs patched in memory ----
 constexpr uint32_t kT16State = 0x1FFFu, kT16Goal = 1u << 13, kT16Bad = 1u << 14;
 constexpr int kT16Cols = 6;  // actions 0..4 + "no-op" column for out-of-range action bytes
@@ -732,6 +918,7 @@ int taxi_launch(gpt_env* env, const LaunchArgs& a) {
   int threads, grid;
   size_t smem = env->blob_bytes;
   TaxiMultiParams M;
+  TaxiTmaParams TP;
   const bool hansen = c.taxi_hansen_obs != 0;
   P.trans16_off = env->taxi_trans16_off;
   P.alias_off = env->taxi_alias_off;
@@ -762,6 +949,37 @@ int taxi_launch(gpt_env* env, const LaunchArgs& a) {
         default: break;
       }
     }
+    // default: the TMA-I/O kernel (bulk-copied action rows and outputs); it needs 16-byte aligned rows in every
+    // stream, i.e. aligned base pointers and a rollout-slot stride that is a multiple of 16 rows.
+    // gpt_set_fused_steps(env, GPT_FUSED_THREADS) or GPT_TAXI_FUSED_LEGACY=1 select the per-thread load/store kernel (A/B runs).
+    static const bool legacy_env = getenv("GPT_TAXI_FUSED_LEGACY") != nullptr;
+    const bool legacy = env->fused_io == 2 || (legacy_env && env->fused_io == 0);
+    const uintptr_t align_or = (uintptr_t)P.actions | (uintptr_t)P.obs | (uintptr_t)P.reward | (uintptr_t)P.terminated | (uintptr_t)P.truncated |
+                               (uintptr_t)env->d_blob | (uintptr_t)(a.out_stride_rows & 15) | (uintptr_t)(env->taxi_hobs_off & 15u);
+    if (!legacy && !c.track_stats && mshape == 0 && (align_or & 15u) == 0) {
+      const uint32_t tab_bytes = env->blob_bytes - env->taxi_hobs_off;   // hobs | alias | trans: what the fused step reads
+      const uint32_t stage_off = (tab_bytes + 127u) & ~127u;
+      const size_t need = (size_t)stage_off + (size_t)kTmaBufs * kTmaStage + (size_t)kTmaActRows * kTmaEnvs;
+      if (need <= 200 * 1024) {
+        TP.m = M;
+        TP.m.p.blob = env->d_blob + env->taxi_hobs_off;
+        TP.m.p.hobs_off = 0;
+        TP.m.p.alias_off = env->taxi_alias_off - env->taxi_hobs_off;
+        TP.m.p.trans_off = env->taxi_trans_off - env->taxi_hobs_off;
+        TP.tab_bytes = tab_bytes;
+        TP.stage_off = stage_off;
+        using KT = void (*)(const TaxiTmaParams);
+        KT kt = devctr_multi ? (one ? (KT)taxi_multi_tma_kernel<true, true> : (KT)taxi_multi_tma_kernel<false, true>)
+                             : (one ? (KT)taxi_multi_tma_kernel<true, false> : (KT)taxi_multi_tma_kernel<false, false>);
+        km = nullptr;
+        kernel = (const void*)kt;
+        args[0] = (void*)&TP;
+        threads = 128;
+        grid = (int)(((int64_t)a.n_tiles * kTileEnvs + kTmaEnvs - 1) / kTmaEnvs);
+        smem = need;
+      }
+    }
+    if (km) {
     const int64_t envs_per_cta = (int64_t)threads * kQuad * qpt;
     grid = (int)(((int64_t)a.n_tiles * kTileEnvs + envs_per_cta - 1) / envs_per_cta);
     kernel = (const void*)km;
@@ -769,6 +987,7 @@ int taxi_launch(gpt_env* env, const LaunchArgs& a) {
     // tuning knob: extra dynamic shared memory per CTA lowers the resident CTAs per SM (wave quantisation experiments)
     static const int pad_kb = getenv("GPT_TAXI_PAD_KB") ? atoi(getenv("GPT_TAXI_PAD_KB")) : 0;
     smem += (size_t)pad_kb * 1024;
+    }
   } else if (env->taxi_use_table) {
     using K = void (*)(const TaxiParams);
     // launch shape: GPT_TAXI_SHAPE = "<quads per thread>x<threads>" (tuning knob; default 2x128)

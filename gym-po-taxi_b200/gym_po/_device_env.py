@@ -223,8 +223,8 @@ class DeviceVecEnv:
 
     def step_many(self, actions, out=None):
         """``T`` consecutive steps from an action stream ``[T, capacity(,cols)]`` (one launch per step,
-        no host round trip).  With ``out`` = dict of rollout tensors ``[T, capacity, ...]`` named like
-        the output arrays the results of step ``t`` land in ``out[name][t]``."""
+        no host round trip).  With ``out`` = dict of rollout tensors ``[T, rows >= capacity, ...]`` named like
+        the output arrays the results of step ``t`` land in ``out[name][t, :capacity]``."""
         t = actions
         if t.device != self.device or t.dtype != self._action_dtype or not t.is_contiguous() or t.shape[1] != self.capacity:
             raise ValueError("step_many needs a contiguous device tensor [T, capacity(,cols)] of the action dtype")
@@ -234,10 +234,12 @@ class DeviceVecEnv:
             for name in names:
                 i, _, dt, cols = self._descs[name]
                 o = out[name]
-                if o.shape[0] < t.shape[0] or o.shape[1] != self.capacity or not o.is_contiguous():
-                    raise ValueError(f"out['{name}'] must be contiguous [T, capacity, ...]")
+                if o.shape[0] < t.shape[0] or o.shape[1] < self.capacity or not o.is_contiguous():
+                    raise ValueError(f"out['{name}'] must be contiguous [T, rows >= capacity, ...]")
+                if stride not in (0, o.shape[1]):
+                    raise ValueError("every out[...] tensor must have the same number of rows per rollout slot")
+                stride = o.shape[1]          # rows between consecutive rollout slots (padded storage is fine)
                 N.check(N.lib.gpt_bind(self._h, i, C.c_void_p(o.data_ptr()), o.shape[0] * o.shape[1]))
-            stride = self.capacity
         try:
             with self._on_device():
                 N.check(N.lib.gpt_step_many(self._h, C.c_void_p(t.data_ptr()), t.shape[0], stride, self._stream()))
@@ -343,9 +345,14 @@ class DeviceVecEnv:
     def rng_counter(self, value: int):
         N.check(N.lib.gpt_set_counter(self._h, int(value)))
 
-    def set_fused_steps(self, enable: bool):
-        """``step_many`` as one fused multi-step launch where the family supports it (Taxi) — on by default."""
-        N.check(N.lib.gpt_set_fused_steps(self._h, int(bool(enable))))
+    def set_fused_steps(self, enable=True):
+        """``step_many`` as one fused multi-step launch where the family supports it (Taxi, ROOMS, MSRooms; Philox mode)
+        — on by default.  ``enable``: False / True, or ``"tma"`` (I/O by TMA bulk copies where the family has it: the
+        Taxi default, opt-in for ROOMS) / ``"threads"`` (per-thread loads and stores) to pick the fused kernel's I/O path."""
+        mode = {"tma": 2, "threads": 3}.get(enable, None) if isinstance(enable, str) else int(bool(enable))
+        if mode is None:
+            raise ValueError("set_fused_steps: True, False, 'tma' or 'threads'")
+        N.check(N.lib.gpt_set_fused_steps(self._h, mode))
 
     def set_graph_mode(self, enable: bool = True):
         """Make ``step()`` capturable into a CUDA graph (Taxi / ROOMS, Philox mode): the Philox step counter moves into

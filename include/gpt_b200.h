@@ -205,10 +205,17 @@ GPT_API int gpt_step_dlpack(gpt_env* env, void* managed_actions, void* stream);
 /* T consecutive steps from an action stream [T, capacity]; outputs of step t go to the bound
  * output arrays offset by t*out_stride_rows rows (0 = overwrite in place every step). */
 GPT_API int gpt_step_many(gpt_env* env, const void* actions, int32_t n_steps, int64_t out_stride_rows, void* stream);
-/* Taxi (table kernel, Philox mode) runs gpt_step_many as ONE fused launch: the state stays in registers for the
- * n_steps steps, only actions are read and outputs written per step; results are bit-identical to n_steps
- * single-step launches.  gpt_set_fused_steps(env, 0) forces one launch per step (A/B measurements). */
-GPT_API int gpt_set_fused_steps(gpt_env* env, int enable);
+/* Taxi (table kernel), ROOMS and MSRooms in Philox mode run gpt_step_many as ONE fused launch: the state stays in
+ * registers for the n_steps steps, only actions are read and outputs written per step; results are bit-identical to
+ * n_steps single-step launches.  gpt_set_fused_steps(env, mode): 0 = one launch per step (A/B measurements),
+ * 1 = fused, the family's default I/O path, 2 = fused with TMA I/O where the family has it (action rows by bulk loads,
+ * outputs staged in shared memory and written by bulk stores: the Taxi default; ROOMS non-window observations opt-in),
+ * 3 = fused with per-thread loads/stores. */
+#define GPT_FUSED_OFF 0
+#define GPT_FUSED_DEFAULT 1
+#define GPT_FUSED_TMA 2
+#define GPT_FUSED_THREADS 3
+GPT_API int gpt_set_fused_steps(gpt_env* env, int mode);
 /* Graph mode (every family; Philox mode, no track_stats; Taxi with the table kernel): the Philox step counter moves from the
  * launch parameters into device memory and the step kernels read AND advance it themselves (the last CTA of a grid to
  * fetch it stores counter + steps), so that gpt_step() / gpt_step_many() calls captured into a CUDA graph draw fresh

@@ -261,3 +261,47 @@ def test_fused_multi_step_launch_equals_single_steps(obs_type, goal_xy, layout):
         for k in sa:
             assert torch.equal(sa[k], sc[k]), k
         assert a.rng_counter == c.rng_counter
+
+
+@pytest.mark.parametrize("obs_type,goal_xy,layout,cardinal", [("hansen8", (0, 0), "4", False), ("vector_hansen8", (0, 0), "4", False),
+                                                              ("vector_goal_hansen4", None, "8", True), ("vector_mdp", (0, 0), "16", False),
+                                                              ("vector_mdp_goal", None, "2", True), ("room_goal", None, "10b", False)])
+def test_fused_tma_launch_partial_cta(obs_type, goal_xy, layout, cardinal):
+    """Fused launches of the non-window observations move their I/O with TMA bulk copies per CTA of 1024 envs: an ODD
+    number of 512-env tiles (half-filled last CTA), more steps than the action ring holds, rollout storage with padded
+    rows, in-place outputs — all equal to single-step launches, for every observation width (2, 4, 8 bytes per env)."""
+    from gym_po.envs import RoomsEnv
+    b, T = 1400, 23
+    kw = dict(layout=layout, obs_type=obs_type, goal_xy=goal_xy, time_limit=9, step_reward=-0.1, wall_reward=-0.5)
+    if cardinal:
+        kw["action_type"] = "cardinal"
+    a = RoomsEnv(b, device=DEV, seed=5, **kw)
+    c = RoomsEnv(b, device=DEV, seed=5, **kw)
+    a.set_fused_steps("tma")        # opt-in for ROOMS (the default fused kernel stores per thread)
+    assert (a.capacity // 512) % 2 == 1
+    a.reset(seed=5); c.reset(seed=5)
+    gen = torch.Generator(device=DEV).manual_seed(8)
+    names = ("obs", "reward", "terminated", "truncated")
+    n_act = 4 if cardinal else 8
+    for pad in (0, 16 * 3):
+        rows = a.capacity + pad
+        acts = torch.randint(0, n_act, (T, a.capacity), dtype=torch.int8, device=DEV, generator=gen)
+        out = {n: torch.full((T, rows) + tuple(a._arrays[n].shape[1:]), 77, dtype=a._arrays[n].dtype, device=DEV) for n in names}
+        l0 = a.launch_count
+        a.step_many(acts, out)
+        assert a.launch_count == l0 + 1
+        for t in range(T):
+            o = c.step(acts[t])
+            for n, x in zip(names, o[:4]):
+                assert torch.equal(out[n][t][:b].reshape(x.shape).view(x.dtype), x), (n, pad, t)
+            for n in names:
+                assert bool((out[n][t][a.capacity:] == 77).all()), (n, t)
+        sa, sc = a.get_state(), c.get_state()
+        for k in sa:
+            assert torch.equal(sa[k], sc[k]), k
+    acts = torch.randint(0, n_act, (7, a.capacity), dtype=torch.int8, device=DEV, generator=gen)
+    a.step_many(acts)                       # in place: the bound arrays hold the last step's results
+    for t in range(7):
+        o = c.step(acts[t])
+    for n, x in zip(names, o[:4]):
+        assert torch.equal(a._arrays[n][:b].reshape(x.shape).view(x.dtype), x), n

@@ -311,9 +311,10 @@ def test_render_draws_device_state_like_the_reference(hansen):
     assert a.shape == b.shape == (176, 132, 3) and (a != b).any() and (b[:, -20:] == 0).all()
 
 
+@pytest.mark.parametrize("io", ["tma", "threads"])
 @pytest.mark.parametrize("kw", [dict(), dict(hansen_obs=True, num_passengers=3, time_limit=17),
                                 dict(map="ext", time_limit=9)])
-def test_fused_multi_step_launch_equals_single_steps(kw):
+def test_fused_multi_step_launch_equals_single_steps(kw, io):
     """gpt_step_many on Taxi runs T steps in ONE launch (state in registers); outputs of every step and the final
     state must be bit-identical to T single-step launches (Philox counters = (global env id, step))."""
     from gym_po.envs import EXTENDED_TAXI_MAP, TaxiVecEnv
@@ -323,6 +324,7 @@ def test_fused_multi_step_launch_equals_single_steps(kw):
     b, T = 3000, 37
     a = TaxiVecEnv(b, device=DEV, seed=9, **kw)
     c = TaxiVecEnv(b, device=DEV, seed=9, **kw)
+    a.set_fused_steps(io)   # the fused kernel's I/O path: TMA bulk copies (default) or per-thread loads / stores
     a.reset(seed=9); c.reset(seed=9)
     gen = torch.Generator(device=DEV).manual_seed(4)
     for rep in range(3):
@@ -349,6 +351,46 @@ def test_fused_multi_step_launch_equals_single_steps(kw):
         o = c.step(acts[t])
     for n, x in zip(("obs", "reward"), o[:2]):
         assert torch.equal(a._arrays[n][:b], x)
+
+
+@pytest.mark.parametrize("b,kw", [(1, dict()), (1500, dict(time_limit=11)), (2500, dict(num_passengers=2, time_limit=13, hansen_obs=True))])
+def test_fused_tma_launch_partial_cta(b, kw):
+    """The default fused kernel moves its I/O with TMA bulk copies per CTA of 1024 envs: capacities with an ODD number of
+    512-env tiles (half-filled last CTA), more steps than the action ring holds, rollout slots with a padded stride and
+    in-place outputs — all equal to single-step launches."""
+    from gym_po.envs import TaxiVecEnv
+    T = 29
+    a = TaxiVecEnv(b, device=DEV, seed=21, **kw)
+    c = TaxiVecEnv(b, device=DEV, seed=21, **kw)
+    a.set_fused_steps("tma")        # (the default for this family)
+    assert (a.capacity // 512) % 2 == 1
+    a.reset(seed=21); c.reset(seed=21)
+    gen = torch.Generator(device=DEV).manual_seed(6)
+    names = ("obs", "reward", "terminated", "truncated")
+    for stride_pad in (0, 16 * 7):
+        acts = torch.randint(0, 5, (T, a.capacity), dtype=torch.int8, device=DEV, generator=gen)
+        rows = a.capacity + stride_pad
+        store = {n: torch.full((T * rows,), 77, dtype=a._arrays[n].dtype, device=DEV) for n in names}
+        l0 = a.launch_count
+        a.step_many(acts, {n: v.view(T, rows) for n, v in store.items()})
+        assert a.launch_count == l0 + 1
+        for t in range(T):
+            o = c.step(acts[t])
+            for n, x in zip(names, o[:4]):
+                got = store[n][t * rows: t * rows + b]
+                assert torch.equal(got.view(x.dtype), x), (n, stride_pad, t)
+            if stride_pad:   # the padding between rollout slots is untouched
+                for n in names:
+                    assert bool((store[n][t * rows + a.capacity:(t + 1) * rows] == 77).all()), (n, t)
+        sa, sc = a.get_state(), c.get_state()
+        for k in sa:
+            assert torch.equal(sa[k], sc[k]), k
+    acts = torch.randint(0, 5, (11, a.capacity), dtype=torch.int8, device=DEV, generator=gen)
+    a.step_many(acts)                       # in place: the bound arrays hold the last step's results
+    for t in range(11):
+        o = c.step(acts[t])
+    for n, x in zip(names, o[:4]):
+        assert torch.equal(a._arrays[n][:b].view(x.dtype), x), n
 
 
 @pytest.mark.parametrize("b", [1, 513, 4096])
