@@ -351,24 +351,7 @@ int rooms_launch(gpt_env* env, const LaunchArgs& a) {
   P.out_stride = a.out_stride_rows;
   const bool devctr = env->graph_mode && !replay && !c.track_stats;   // graph mode: step counter in device memory
   P.ctr_ptr = env->d_counter;
-  int variant = devctr ? (multi ? 4 : 3) : (multi ? 2 : (c.track_stats != 0 ? 1 : 0));
-  // fused launches of the non-window observations can move their I/O with TMA bulk copies (16-byte aligned rows in
-  // every stream needed: aligned base pointers, rollout-slot stride a multiple of 16 rows).  Opt-in for this family
-  // (gpt_set_fused_steps(env, GPT_FUSED_TMA) or GPT_ROOMS_FUSED_TMA=1): the ROOMS step is bound by instruction issue,
-  // and the CTA barrier per step of the staged path costs more than the better write pattern gives (measured, hansen8
-  // at 2^22 envs, 10 steps per launch: 110.1 us against 101.9 us with per-thread stores).
-  static const bool tma_env = getenv("GPT_ROOMS_FUSED_TMA") != nullptr;
-  const bool legacy = !(env->fused_io == 1 || (tma_env && env->fused_io == 0));
-  const uintptr_t align_or = (uintptr_t)P.actions | (uintptr_t)P.obs | (uintptr_t)P.reward | (uintptr_t)P.terminated | (uintptr_t)P.truncated |
-                             (uintptr_t)(a.out_stride_rows & 15);
-  if (multi && !grid && !legacy && (align_or & 15u) == 0) {
-    const size_t need = (size_t)P.stage_off + (size_t)kRoomsTmaBufs * (obs_row + 6) * envs_per_cta + (size_t)kRoomsTmaActRows * envs_per_cta;
-    if (need <= 200 * 1024) {
-      variant = devctr ? 6 : 5;
-      smem = need;
-    }
-  }
-  void* k = pick_kernel(c.rooms_obs_kind, P.grid_n, rgoal, replay, variant);
+  void* k = pick_kernel(c.rooms_obs_kind, P.grid_n, rgoal, replay, devctr ? (multi ? 4 : 3) : (multi ? 2 : (c.track_stats != 0 ? 1 : 0)));
   if (!k) return fail(GPT_E_ARG, "rooms: no kernel for this obs kind");
   if (smem > 40 * 1024) {  // static + dynamic shared memory above 48 KB needs the opt-in
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -232,26 +232,6 @@ __device__ __forceinline__ void store_obs(void* obs, int64_t q, int64_t warp_qua
   }
 }
 
-// The same for a shared-memory staging buffer that mirrors the global layout of a CTA's rows (TMA fused launches):
-// `lq` = index of the quad's first env inside the CTA tile.  Plain (generic) stores.
-template <int OBS>
-__device__ __forceinline__ void store_obs_staged(uint8_t* buf, uint32_t lq, int hansen_n, const uint32_t (&lo)[4], const uint32_t (&hi)[4]) {
-  static_assert(OBS != GPT_OBS_GRID, "window observations keep their own staging");
-  if constexpr (OBS == GPT_OBS_VEC_MDP) {
-    *reinterpret_cast<uint2*>(buf + lq * 2) = make_uint2(lo[0] | (lo[1] << 16), lo[2] | (lo[3] << 16));
-  } else if constexpr (OBS == GPT_OBS_VEC_HANSEN || OBS == GPT_OBS_VEC_HANSEN_GOAL) {
-    if (hansen_n == 8) {
-      int4* o = reinterpret_cast<int4*>(buf + lq * 8);
-      o[0] = make_int4((int)lo[0], (int)hi[0], (int)lo[1], (int)hi[1]);
-      o[1] = make_int4((int)lo[2], (int)hi[2], (int)lo[3], (int)hi[3]);
-    } else {
-      *reinterpret_cast<int4*>(buf + lq * 4) = make_int4((int)lo[0], (int)lo[1], (int)lo[2], (int)lo[3]);
-    }
-  } else {
-    *reinterpret_cast<int4*>(buf + lq * 4) = make_int4((int)lo[0], (int)lo[1], (int)lo[2], (int)lo[3]);
-  }
-}
-
 // Number of quads (4 envs) a thread handles and the CTA size, per observation kind.  Measured on B200
 // (Taxi, same access pattern): 2 quads x 128 threads beats 4 x 256 — more, smaller CTAs backfill better.
 #ifndef GPT_ROOMS_QPT_SCALAR
@@ -306,29 +286,13 @@ __device__ __noinline__ uint32_t rooms_respawn(const RoomsParams& P, const uint1
 // MULTI: gpt_step_many as ONE launch — pos / goal / elapsed are read once, live in registers for P.n_steps steps and
 // are written once; per step only the action byte is read and the outputs are written.  Bit-identical to n_steps
 // single-step launches (Philox counters = (global env / quad id, first step + t)).
-//
-// TMA (fused launches of the non-window observations, the default): the per-step I/O is moved by the TMA engine as in
-// the fused Taxi kernel (gpt_taxi.cu, taxi_multi_tma_kernel) — the CTA's action rows arrive by bulk copies in a ring of
-// kRoomsTmaActRows shared-memory rows, every step's outputs are staged in shared memory (obs | reward | terminated |
-// truncated of the CTA's 1024 envs) and leave with four bulk stores per CTA and step, double-buffered.  One CTA barrier
-// per step; warps past the end of the batch (odd tile count) compute on zeros and store nothing.
-#ifndef GPT_ROOMS_TMA_ACT_ROWS
-#define GPT_ROOMS_TMA_ACT_ROWS 4
-#endif
-#ifndef GPT_ROOMS_MINB_TMA
-#define GPT_ROOMS_MINB_TMA 6
-#endif
-constexpr int kRoomsTmaActRows = GPT_ROOMS_TMA_ACT_ROWS;   // power of two
-constexpr int kRoomsTmaBufs = 2;
-template <int OBS, bool RGOAL, bool REPLAY, int GRID_N, bool STATS, bool MULTI = false, bool DEVCTR = false, bool TMA = false>
+template <int OBS, bool RGOAL, bool REPLAY, int GRID_N, bool STATS, bool MULTI = false, bool DEVCTR = false>
 __global__ void __launch_bounds__(RoomsShape<OBS, GRID_N>::kThreads,
-                                  STATS ? 1 : (TMA ? GPT_ROOMS_MINB_TMA : (MULTI ? (RoomsShape<OBS, GRID_N>::kMinBlocks > 1 ? GPT_ROOMS_MINB_MULTI : 1) : RoomsShape<OBS, GRID_N>::kMinBlocks)))
+                                  STATS ? 1 : (MULTI ? (RoomsShape<OBS, GRID_N>::kMinBlocks > 1 ? GPT_ROOMS_MINB_MULTI : 1) : RoomsShape<OBS, GRID_N>::kMinBlocks))
 rooms_step_kernel(const __grid_constant__ RoomsParams P) {
   static_assert(!MULTI || (!REPLAY && !STATS), "fused launches: Philox mode, no in-kernel statistics");
-  static_assert(!TMA || (MULTI && OBS != GPT_OBS_GRID), "TMA I/O: fused launches of the non-window observations");
   constexpr int QPT = RoomsShape<OBS, GRID_N>::kQpt;
   constexpr int kEnvsPerWarp = kWarp * kQuad * QPT;
-  constexpr int kEnvsPerCta = RoomsShape<OBS, GRID_N>::kThreads * kQuad * QPT;
   // fixed goal + non-window obs: the observation is a pure function of the agent cell -> one table lookup
   constexpr bool kObsTable = !RGOAL && OBS != GPT_OBS_GRID;
   // ... and when it also fits 16 bits it rides in the move-table entry: ONE lookup yields next cell, blocked,
@@ -337,47 +301,21 @@ rooms_step_kernel(const __grid_constant__ RoomsParams P) {
                                          OBS == GPT_OBS_HANSEN || OBS == GPT_OBS_VEC_MDP);
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ uint64_t bar;
-  __shared__ __align__(8) uint64_t abar[TMA ? kRoomsTmaActRows : 1];
   pdl_launch_dependents();
-  if constexpr (TMA) {
-    if (threadIdx.x == 0) {
-#pragma unroll
-      for (int i = 0; i < kRoomsTmaActRows; ++i) mbar_init(&abar[i], 1);
-    }
-  }
   stage_tables_begin(smem, P.blob, P.blob_bytes, &bar);
 
   const uint32_t lane = threadIdx.x & 31u;
   const uint32_t warp = threadIdx.x >> 5;
   const int64_t first = (int64_t)P.first_tile * kTileEnvs, last = first + (int64_t)P.n_tiles * kTileEnvs;
   const int64_t wbase = first + ((int64_t)blockIdx.x * (RoomsShape<OBS, GRID_N>::kThreads / 32) + warp) * kEnvsPerWarp;
-  const bool active = wbase < last;
-  if (!TMA && !active) return;
+  if (wbase >= last) return;
   const int64_t base = wbase + lane * kQuad;
-  // TMA: the CTA's envs are [tile, tile + valid); `lq0` = the thread's first quad inside that tile
-  const int64_t tile = first + (int64_t)blockIdx.x * kEnvsPerCta;
-  const uint32_t valid = (uint32_t)(last - tile < kEnvsPerCta ? last - tile : kEnvsPerCta);
-  const uint32_t lq0 = warp * (uint32_t)kEnvsPerWarp + lane * kQuad;
   const uint32_t n = (uint32_t)P.n_actions;
   const uint32_t dir_shift = n == 4 ? 1u : 0u;   // cardinal action i = ordinal direction 2i
 
   // reset() is not a separate code path: the host poisons `elapsed` so that every env truncates and
   // launches this same kernel (gpt_rooms.cu), which keeps the hot loop free of mode branches.
   pdl_wait();   // the previous step's writes are complete and visible from here on
-  uint8_t* const tma_stage = smem + P.stage_off;                                   // TMA: kRoomsTmaBufs staging buffers ...
-  const size_t obs_row = OBS == GPT_OBS_GRID ? (size_t)((GRID_N > 0 ? GRID_N : P.grid_n) * (GRID_N > 0 ? GRID_N : P.grid_n))
-                         : (OBS == GPT_OBS_VEC_MDP ? 2 : ((OBS == GPT_OBS_VEC_HANSEN || OBS == GPT_OBS_VEC_HANSEN_GOAL) ? (size_t)P.hansen_n : 4));
-  const uint32_t tma_buf_bytes = (uint32_t)(obs_row + 6) * kEnvsPerCta;             // obs | reward | terminated | truncated
-  uint8_t* const tma_acts = tma_stage + kRoomsTmaBufs * tma_buf_bytes;             // ... then the action ring
-  if constexpr (TMA) {
-    if (threadIdx.x == 0) {   // the first action rows
-      const int rows = P.n_steps < kRoomsTmaActRows ? P.n_steps : kRoomsTmaActRows;
-      for (int r = 0; r < rows; ++r) {
-        mbar_expect_tx(&abar[r], valid);
-        tma_bulk_g2s(tma_acts + r * kEnvsPerCta, P.actions + (int64_t)r * P.act_stride + tile, valid, &abar[r]);
-      }
-    }
-  }
   uint2 pos4[QPT], goal4[QPT];
   int4 e4[QPT];
   uint32_t a4[QPT];
@@ -387,15 +325,10 @@ rooms_step_kernel(const __grid_constant__ RoomsParams P) {
   for (int j = 0; j < QPT; ++j) {
     const int64_t q = base + j * kQuadStride;
     goal4[j] = make_uint2(0, 0);
-    pos4[j] = make_uint2(0, 0);
-    e4[j] = make_int4(0, 0, 0, 0);
-    a4[j] = 0u;
-    if (!TMA || active) {
-      pos4[j] = ld_stream(reinterpret_cast<const uint2*>(P.pos + q));
-      if (RGOAL) goal4[j] = ld_stream(reinterpret_cast<const uint2*>(P.goal + q));
-      e4[j] = ld_stream(reinterpret_cast<const int4*>(P.elapsed + q));
-      if constexpr (!TMA) a4[j] = ld_stream(reinterpret_cast<const uint32_t*>(P.actions + q));
-    }
+    pos4[j] = ld_stream(reinterpret_cast<const uint2*>(P.pos + q));
+    if (RGOAL) goal4[j] = ld_stream(reinterpret_cast<const uint2*>(P.goal + q));
+    e4[j] = ld_stream(reinterpret_cast<const int4*>(P.elapsed + q));
+    a4[j] = ld_stream(reinterpret_cast<const uint32_t*>(P.actions + q));
     if constexpr (STATS) ret4[j] = __ldcs(reinterpret_cast<const float4*>(P.ep_return + q));
   }
 
@@ -433,18 +366,16 @@ rooms_step_kernel(const __grid_constant__ RoomsParams P) {
   // DEVCTR (graph mode): the step counter comes from device memory, so that a captured CUDA graph can be replayed
   uint64_t ctr_dev = 0;
   if constexpr (DEVCTR) ctr_dev = devctr_fetch_and_advance(P.ctr_ptr, (uint32_t)n_steps);
+  const size_t obs_row = OBS == GPT_OBS_GRID ? (size_t)(gn * gn)
+                         : (OBS == GPT_OBS_VEC_MDP ? 2 : ((OBS == GPT_OBS_VEC_HANSEN || OBS == GPT_OBS_VEC_HANSEN_GOAL) ? (size_t)P.hansen_n : 4));
 #pragma unroll 1
   for (int32_t t = 0; t < n_steps; ++t) {
   uint32_t a_next[QPT];
-  const bool more = MULTI && !TMA && t + 1 < n_steps;
-  uint8_t* const tma_buf = tma_stage + (uint32_t)(t & (kRoomsTmaBufs - 1)) * tma_buf_bytes;
-  const int tma_slot = t & (kRoomsTmaActRows - 1);
-  if constexpr (TMA) mbar_wait(&abar[tma_slot], (uint32_t)(t / kRoomsTmaActRows) & 1u);   // this step's action row has landed
+  const bool more = MULTI && t + 1 < n_steps;
 #pragma unroll
   for (int j = 0; j < QPT; ++j) {   // prefetch the next step's action bytes (the only per-step read)
     a_next[j] = 0u;
     if (more) a_next[j] = ld_stream(reinterpret_cast<const uint32_t*>(P.actions + (int64_t)(t + 1) * P.act_stride + base + j * kQuadStride));
-    if constexpr (TMA) a4[j] = *reinterpret_cast<const uint32_t*>(tma_acts + tma_slot * kEnvsPerCta + lq0 + j * kQuadStride);
   }
   const int64_t orow = MULTI ? (int64_t)t * P.out_stride : 0;
   const uint64_t ctr = (DEVCTR ? ctr_dev : (((uint64_t)P.rng.step_hi << 32) | P.rng.step_lo)) + (uint32_t)t;   // Philox step counter of this step
@@ -570,41 +501,12 @@ rooms_step_kernel(const __grid_constant__ RoomsParams P) {
       window_quad<GRID_N>(T, OC, cellv, goalv, stage + (uint32_t)(lane * kQuad) * (uint32_t)(GRID_N * GRID_N));
 
     // ---- stores ------------------------------------------------------------------------------
-    if constexpr (TMA) {   // staged in shared memory in the global layout of the CTA's rows
-      const uint32_t lq = lq0 + j * kQuadStride;
-      store_obs_staged<OBS>(tma_buf, lq, P.hansen_n, o32, o32b);
-      *reinterpret_cast<float4*>(tma_buf + obs_row * kEnvsPerCta + lq * 4) = make_float4(rv[0], rv[1], rv[2], rv[3]);
-      *reinterpret_cast<uint32_t*>(tma_buf + (obs_row + 4) * kEnvsPerCta + lq) = tw;
-      *reinterpret_cast<uint32_t*>(tma_buf + (obs_row + 5) * kEnvsPerCta + lq) = trw;
-    } else {
-      st_stream(reinterpret_cast<float4*>(P.reward + orow + q), make_float4(rv[0], rv[1], rv[2], rv[3]));
-      st_stream(reinterpret_cast<uint32_t*>(P.terminated + orow + q), tw);
-      st_stream(reinterpret_cast<uint32_t*>(P.truncated + orow + q), trw);
-      store_obs<OBS>((uint8_t*)P.obs + (size_t)orow * obs_row, q, wbase + j * kQuadStride, P.hansen_n, gn, lane, stage, o32, o32b);
-      if constexpr (STATS) st_stream(reinterpret_cast<float4*>(P.ep_return + q), ret4[j]);
-      a4[j] = a_next[j];
-    }
-  }
-  if constexpr (TMA) {
-    fence_proxy_async();   // the staged outputs become visible to the TMA engine
-    // the buffer step t+1 writes was last read by the bulk stores of step t-1
-    if (threadIdx.x == 0) tma_bulk_wait_read<kRoomsTmaBufs - 2>();
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      // in-place outputs (out_stride 0) are written by the LAST step only: bulk stores of different groups are unordered
-      if (P.out_stride != 0 || t == n_steps - 1) {
-        const int64_t o = orow + tile;
-        tma_bulk_s2g((uint8_t*)P.obs + (size_t)o * obs_row, tma_buf, (uint32_t)obs_row * valid);
-        tma_bulk_s2g(P.reward + o, tma_buf + obs_row * kEnvsPerCta, 4 * valid);
-        tma_bulk_s2g(P.terminated + o, tma_buf + (obs_row + 4) * kEnvsPerCta, valid);
-        tma_bulk_s2g(P.truncated + o, tma_buf + (obs_row + 5) * kEnvsPerCta, valid);
-        tma_bulk_commit();
-      }
-      if (t + kRoomsTmaActRows < n_steps) {  // every thread has consumed this ring row (barrier above): refill it
-        mbar_expect_tx(&abar[tma_slot], valid);
-        tma_bulk_g2s(tma_acts + tma_slot * kEnvsPerCta, P.actions + (int64_t)(t + kRoomsTmaActRows) * P.act_stride + tile, valid, &abar[tma_slot]);
-      }
-    }
+    st_stream(reinterpret_cast<float4*>(P.reward + orow + q), make_float4(rv[0], rv[1], rv[2], rv[3]));
+    st_stream(reinterpret_cast<uint32_t*>(P.terminated + orow + q), tw);
+    st_stream(reinterpret_cast<uint32_t*>(P.truncated + orow + q), trw);
+    store_obs<OBS>((uint8_t*)P.obs + (size_t)orow * obs_row, q, wbase + j * kQuadStride, P.hansen_n, gn, lane, stage, o32, o32b);
+    if constexpr (STATS) st_stream(reinterpret_cast<float4*>(P.ep_return + q), ret4[j]);
+    a4[j] = a_next[j];
   }
   }  // steps of a fused launch
 #pragma unroll
@@ -612,15 +514,11 @@ rooms_step_kernel(const __grid_constant__ RoomsParams P) {
     const int64_t q = base + j * kQuadStride;
     const uint32_t (&cellv)[4] = cellq[j];
     const uint32_t (&goalv)[4] = goalq[j];
-    if (TMA && !active) continue;
     st_stream(reinterpret_cast<uint2*>(P.pos + q), make_uint2(cellv[0] | (cellv[1] << 16), cellv[2] | (cellv[3] << 16)));
     if (RGOAL) st_stream(reinterpret_cast<uint2*>(P.goal + q), make_uint2(goalv[0] | (goalv[1] << 16), goalv[2] | (goalv[3] << 16)));
     st_stream(reinterpret_cast<int4*>(P.elapsed + q), make_int4(evq[j][0], evq[j][1], evq[j][2], evq[j][3]));
   }
   if constexpr (STATS) acc.flush(P.stats);
-  if constexpr (TMA) {
-    if (threadIdx.x == 0) tma_bulk_wait_read<0>();   // shared memory must outlive the last bulk stores' reads
-  }
 }
 
 template <int OBS, int GRID_N, bool STATS>
@@ -632,19 +530,9 @@ static void* pick_rr2(bool rgoal, bool replay) {
 }
 // variant: 0 = plain single step, 1 = single step with in-kernel statistics, 2 = fused multi-step (Philox mode),
 // 3 = single step with the device-resident step counter (graph mode, Philox), 4 = fused multi-step in graph mode
-// 5 / 6 = 2 / 4 with TMA I/O (non-window observations only)
 template <int OBS, int GRID_N>
 static void* pick_rr(bool rgoal, bool replay, int variant) {
   using K = void (*)(const RoomsParams);
-  if constexpr (OBS != GPT_OBS_GRID) {
-    if (variant == 6)
-      return replay ? nullptr
-                    : (void*)(rgoal ? (K)rooms_step_kernel<OBS, true, false, GRID_N, false, true, true, true> : (K)rooms_step_kernel<OBS, false, false, GRID_N, false, true, true, true>);
-    if (variant == 5)
-      return replay ? nullptr
-                    : (void*)(rgoal ? (K)rooms_step_kernel<OBS, true, false, GRID_N, false, true, false, true> : (K)rooms_step_kernel<OBS, false, false, GRID_N, false, true, false, true>);
-  }
-  if (variant >= 5) return nullptr;
   if (variant == 4)
     return replay ? nullptr
                   : (void*)(rgoal ? (K)rooms_step_kernel<OBS, true, false, GRID_N, false, true, true> : (K)rooms_step_kernel<OBS, false, false, GRID_N, false, true, true>);

@@ -347,8 +347,8 @@ class DeviceVecEnv:
 
     def set_fused_steps(self, enable=True):
         """``step_many`` as one fused multi-step launch where the family supports it (Taxi, ROOMS, MSRooms; Philox mode)
-        — on by default.  ``enable``: False / True, or ``"tma"`` (I/O by TMA bulk copies where the family has it: the
-        Taxi default, opt-in for ROOMS) / ``"threads"`` (per-thread loads and stores) to pick the fused kernel's I/O path."""
+        — on by default.  ``enable``: False / True, or ``"tma"`` (I/O by TMA bulk copies where the family has it: Taxi,
+        where it is the default) / ``"threads"`` (per-thread loads and stores) to pick the fused kernel's I/O path."""
         mode = {"tma": 2, "threads": 3}.get(enable, None) if isinstance(enable, str) else int(bool(enable))
         if mode is None:
             raise ValueError("set_fused_steps: True, False, 'tma' or 'threads'")

@@ -208,9 +208,10 @@ GPT_API int gpt_step_many(gpt_env* env, const void* actions, int32_t n_steps, in
 /* Taxi (table kernel), ROOMS and MSRooms in Philox mode run gpt_step_many as ONE fused launch: the state stays in
  * registers for the n_steps steps, only actions are read and outputs written per step; results are bit-identical to
  * n_steps single-step launches.  gpt_set_fused_steps(env, mode): 0 = one launch per step (A/B measurements),
- * 1 = fused, the family's default I/O path, 2 = fused with TMA I/O where the family has it (action rows by bulk loads,
- * outputs staged in shared memory and written by bulk stores: the Taxi default; ROOMS non-window observations opt-in),
- * 3 = fused with per-thread loads/stores. */
+ * 1 = fused, the family's default I/O path, 2 = fused with TMA I/O where the family has it (Taxi, where it is the
+ * default: action rows by bulk loads, outputs staged in shared memory and written by bulk stores), 3 = fused with
+ * per-thread loads/stores.  ROOMS / MSRooms have the per-thread path only: their fused step is bound by instruction
+ * issue, not by its I/O. */
 #define GPT_FUSED_OFF 0
 #define GPT_FUSED_DEFAULT 1
 #define GPT_FUSED_TMA 2

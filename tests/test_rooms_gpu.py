@@ -266,10 +266,9 @@ def test_fused_multi_step_launch_equals_single_steps(obs_type, goal_xy, layout):
 @pytest.mark.parametrize("obs_type,goal_xy,layout,cardinal", [("hansen8", (0, 0), "4", False), ("vector_hansen8", (0, 0), "4", False),
                                                               ("vector_goal_hansen4", None, "8", True), ("vector_mdp", (0, 0), "16", False),
                                                               ("vector_mdp_goal", None, "2", True), ("room_goal", None, "10b", False)])
-def test_fused_tma_launch_partial_cta(obs_type, goal_xy, layout, cardinal):
-    """Fused launches of the non-window observations move their I/O with TMA bulk copies per CTA of 1024 envs: an ODD
-    number of 512-env tiles (half-filled last CTA), more steps than the action ring holds, rollout storage with padded
-    rows, in-place outputs — all equal to single-step launches, for every observation width (2, 4, 8 bytes per env)."""
+def test_fused_launch_odd_tiles_padded_rows_in_place(obs_type, goal_xy, layout, cardinal):
+    """Fused launches at an ODD number of 512-env tiles (half-filled last CTA), rollout storage with padded rows and
+    in-place outputs — all equal to single-step launches, for every observation width (2, 4, 8 bytes per env)."""
     from gym_po.envs import RoomsEnv
     b, T = 1400, 23
     kw = dict(layout=layout, obs_type=obs_type, goal_xy=goal_xy, time_limit=9, step_reward=-0.1, wall_reward=-0.5)
@@ -277,7 +276,6 @@ def test_fused_tma_launch_partial_cta(obs_type, goal_xy, layout, cardinal):
         kw["action_type"] = "cardinal"
     a = RoomsEnv(b, device=DEV, seed=5, **kw)
     c = RoomsEnv(b, device=DEV, seed=5, **kw)
-    a.set_fused_steps("tma")        # opt-in for ROOMS (the default fused kernel stores per thread)
     assert (a.capacity // 512) % 2 == 1
     a.reset(seed=5); c.reset(seed=5)
     gen = torch.Generator(device=DEV).manual_seed(8)
