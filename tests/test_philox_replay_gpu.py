@@ -205,10 +205,10 @@ def test_taxi_baseline_size_replay():
 
 
 def test_taxi_baseline_size_philox_fused():
-    """The timed configuration itself: Taxi, 2^22 envs, Philox mode, fused launches of 10 steps with rollout slots,
-    de-synchronised phases — against the oracle on host-rebuilt draws."""
+    """The timed configuration itself: Taxi, 2^22 envs, Philox mode, fused launches (TMA I/O) of 20 steps — what
+    bench.py times — and of 10 steps with rollout slots, de-synchronised phases — against the oracle on host-rebuilt draws."""
     from gym_po.envs import TaxiVecEnv
-    b, seed, T = 1 << 22, 0, 10
+    b, seed, T = 1 << 22, 0, 20
     env = TaxiVecEnv(b, device=DEV, seed=seed)
     draws = PhiloxDraws(env, seed, "taxi")
     orc = oracle.TaxiOracle(b, draws=draws)
@@ -221,12 +221,12 @@ def test_taxi_baseline_size_philox_fused():
     orc.elapsed[:] = el
     env.elapsed.copy_(torch.as_tensor(el, dtype=torch.int32))
     out = {nm: torch.zeros((T,) + tuple(env._arrays[nm].shape), dtype=env._arrays[nm].dtype, device=DEV) for nm in NAMES}
-    for L in range(2):
+    for L, T in enumerate((T, T // 2)):
         acts = rng.integers(5, size=(T, b)).astype(np.int8)
         c0, l0 = env.rng_counter, env.launch_count
         env.step_many(torch.as_tensor(acts, device=DEV), out)
         assert env.launch_count - l0 == 1
-        host = {nm: out[nm].cpu().numpy() for nm in NAMES}
+        host = {nm: out[nm][:T].cpu().numpy() for nm in NAMES}
         for t in range(T):
             draws.counter = c0 + t
             o = orc.step(acts[t])
