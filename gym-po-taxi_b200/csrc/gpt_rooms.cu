@@ -349,6 +349,11 @@ int rooms_launch(gpt_env* env, const LaunchArgs& a) {
   P.n_steps = a.n_steps;
   P.act_stride = env->capacity;
   P.out_stride = a.out_stride_rows;
+  // window obs: one TMA bulk store per warp tile (128 envs x n^2 bytes) when every tile starts 16-byte aligned; fused
+  // in-place outputs keep the per-lane stores (bulk stores of different steps to the same rows would be unordered).
+  // GPT_ROOMS_OBS_TMA=0 switches it off (A/B runs).
+  static const bool obs_tma_off = getenv("GPT_ROOMS_OBS_TMA") && atoi(getenv("GPT_ROOMS_OBS_TMA")) == 0;
+  P.obs_tma = grid && !obs_tma_off && ((uintptr_t)P.obs & 15u) == 0 && (a.out_stride_rows & 15) == 0 && !(multi && a.out_stride_rows == 0);
   const bool devctr = env->graph_mode && !replay && !c.track_stats;   // graph mode: step counter in device memory
   P.ctr_ptr = env->d_counter;
   void* k = pick_kernel(c.rooms_obs_kind, P.grid_n, rgoal, replay, devctr ? (multi ? 4 : 3) : (multi ? 2 : (c.track_stats != 0 ? 1 : 0)));

@@ -46,6 +46,7 @@ struct RoomsParams {
   int32_t first_tile, n_tiles, mode;
   int32_t w, n_actions, n_valid, n_rooms, time_limit;
   int32_t hansen_n, grid_n, goal_cell, goal_y, goal_x;
+  int32_t obs_tma;   // window obs: the staged tile is written by one TMA bulk store per warp and quad row (16-byte aligned rows)
   FastDiv div_w;
   float r_step, r_wall, r_goal;
   // fused multi-step launch (gpt_step_many, MULTI kernels): n_steps consecutive steps, the state stays in registers
@@ -207,9 +208,11 @@ __device__ __forceinline__ void window_quad(const RoomsTables& T, const ObsCtx& 
 
 // Stores the observations of one quad (4 consecutive envs starting at env index q).  For the window
 // obs the warp's 128 envs x n^2 bytes (contiguous in HBM) are streamed out of shared memory.
+// `tile_tma` (window obs only): the warp's staged tile leaves with ONE TMA bulk store (lane 0) instead of a loop of
+// per-lane 16-byte stores; the caller must call obs_tile_acquire() before the tile is written again and at kernel end.
 template <int OBS>
 __device__ __forceinline__ void store_obs(void* obs, int64_t q, int64_t warp_quad_base, int hansen_n, int gn, uint32_t lane,
-                                          const uint8_t* stage, const uint32_t (&lo)[4], const uint32_t (&hi)[4]) {
+                                          const uint8_t* stage, const uint32_t (&lo)[4], const uint32_t (&hi)[4], bool tile_tma = false) {
   if constexpr (OBS == GPT_OBS_VEC_MDP) {
     st_stream(reinterpret_cast<uint2*>((uint8_t*)obs + q * 2), make_uint2(lo[0] | (lo[1] << 16), lo[2] | (lo[3] << 16)));
   } else if constexpr (OBS == GPT_OBS_VEC_HANSEN || OBS == GPT_OBS_VEC_HANSEN_GOAL) {
@@ -221,15 +224,30 @@ __device__ __forceinline__ void store_obs(void* obs, int64_t q, int64_t warp_qua
       st_stream(reinterpret_cast<int4*>((uint8_t*)obs + q * 4), make_int4((int)lo[0], (int)lo[1], (int)lo[2], (int)lo[3]));
     }
   } else if constexpr (OBS == GPT_OBS_GRID) {
-    __syncwarp();
-    const uint32_t vecs = (uint32_t)(kQuadStride * gn * gn) >> 4;
-    const int4* src = reinterpret_cast<const int4*>(stage);
-    int4* dst = reinterpret_cast<int4*>((uint8_t*)obs + warp_quad_base * (gn * gn));
-    for (uint32_t i = lane; i < vecs; i += 32) st_stream(dst + i, src[i]);
-    __syncwarp();
+    if (tile_tma) {
+      fence_proxy_async();   // the lanes' tile slices become visible to the TMA engine
+      __syncwarp();
+      if (lane == 0) {
+        tma_bulk_s2g((uint8_t*)obs + warp_quad_base * (gn * gn), stage, (uint32_t)(kQuadStride * gn * gn));
+        tma_bulk_commit();
+      }
+    } else {
+      __syncwarp();
+      const uint32_t vecs = (uint32_t)(kQuadStride * gn * gn) >> 4;
+      const int4* src = reinterpret_cast<const int4*>(stage);
+      int4* dst = reinterpret_cast<int4*>((uint8_t*)obs + warp_quad_base * (gn * gn));
+      for (uint32_t i = lane; i < vecs; i += 32) st_stream(dst + i, src[i]);
+      __syncwarp();
+    }
   } else {  // scalar int32 obs, or 4 packed bytes per env (VEC_MDP_GOAL)
     st_stream(reinterpret_cast<int4*>((uint8_t*)obs + q * 4), make_int4((int)lo[0], (int)lo[1], (int)lo[2], (int)lo[3]));
   }
+}
+
+// Window obs with tile_tma: wait until the warp's previous bulk store has finished READING the staged tile.
+__device__ __forceinline__ void obs_tile_acquire(uint32_t lane) {
+  if (lane == 0) tma_bulk_wait_read<0>();
+  __syncwarp();
 }
 
 // Number of quads (4 envs) a thread handles and the CTA size, per observation kind.  Measured on B200
@@ -481,6 +499,9 @@ rooms_step_kernel(const __grid_constant__ RoomsParams P) {
       }
     }
     // ---- observation of the (post-reset) state ------------------------------------------------
+    if constexpr (OBS == GPT_OBS_GRID) {
+      if (P.obs_tma) obs_tile_acquire(lane);   // the previous quad row's bulk store has read the tile
+    }
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       if constexpr (kMerged) {
@@ -504,7 +525,7 @@ rooms_step_kernel(const __grid_constant__ RoomsParams P) {
     st_stream(reinterpret_cast<float4*>(P.reward + orow + q), make_float4(rv[0], rv[1], rv[2], rv[3]));
     st_stream(reinterpret_cast<uint32_t*>(P.terminated + orow + q), tw);
     st_stream(reinterpret_cast<uint32_t*>(P.truncated + orow + q), trw);
-    store_obs<OBS>((uint8_t*)P.obs + (size_t)orow * obs_row, q, wbase + j * kQuadStride, P.hansen_n, gn, lane, stage, o32, o32b);
+    store_obs<OBS>((uint8_t*)P.obs + (size_t)orow * obs_row, q, wbase + j * kQuadStride, P.hansen_n, gn, lane, stage, o32, o32b, P.obs_tma != 0);
     if constexpr (STATS) st_stream(reinterpret_cast<float4*>(P.ep_return + q), ret4[j]);
     a4[j] = a_next[j];
   }
@@ -519,6 +540,9 @@ rooms_step_kernel(const __grid_constant__ RoomsParams P) {
     st_stream(reinterpret_cast<int4*>(P.elapsed + q), make_int4(evq[j][0], evq[j][1], evq[j][2], evq[j][3]));
   }
   if constexpr (STATS) acc.flush(P.stats);
+  if constexpr (OBS == GPT_OBS_GRID) {
+    if (P.obs_tma) obs_tile_acquire(lane);   // shared memory must outlive the last bulk store's read
+  }
 }
 
 template <int OBS, int GRID_N, bool STATS>
