@@ -247,7 +247,10 @@ static void* pick_kernel(int obs, int grid_n, bool rgoal, bool replay, int stats
   return nullptr;
 }
 
-bool rooms_can_fuse(const gpt_env* env) { return env->cfg.rng_mode == GPT_RNG_PHILOX && !env->cfg.track_stats; }
+// (the fused kernels keep the elapsed counters as biased 16-bit pairs: time limits beyond 32766 step one launch at a time)
+bool rooms_can_fuse(const gpt_env* env) {
+  return env->cfg.rng_mode == GPT_RNG_PHILOX && !env->cfg.track_stats && env->cfg.time_limit >= 0 && env->cfg.time_limit <= 32766;
+}
 
 int rooms_launch(gpt_env* env, const LaunchArgs& a) {
   const gpt_config& c = env->cfg;

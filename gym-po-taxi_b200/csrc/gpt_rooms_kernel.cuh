@@ -380,6 +380,23 @@ rooms_step_kernel(const __grid_constant__ RoomsParams P) {
     goalq[j][0] = goal4[j].x & 0xFFFFu; goalq[j][1] = goal4[j].x >> 16; goalq[j][2] = goal4[j].y & 0xFFFFu; goalq[j][3] = goal4[j].y >> 16;
     evq[j][0] = e4[j].x; evq[j][1] = e4[j].y; evq[j][2] = e4[j].z; evq[j][3] = e4[j].w;
   }
+  // MULTI: the four elapsed counters of a quad live in two registers as biased 16-bit pairs, c = elapsed + 0x7FFF -
+  // time_limit ([0] = envs 0 | 2, [1] = envs 1 | 3): one packed add per pair and step, bit 15 of a half = "elapsed >
+  // time_limit" (rooms.py:220), so the truncated bytes are two shifts and masks and nothing is done per env.  The host
+  // fuses only with time_limit <= 32766; an injected counter outside [0, time_limit] behaves like the limit (the env
+  // truncates on its next step either way).
+  const uint32_t cbias = 0x7FFFu - (uint32_t)P.time_limit;
+  uint32_t cntq[MULTI ? QPT : 1][2];
+  if constexpr (MULTI) {
+#pragma unroll
+    for (int j = 0; j < QPT; ++j) {
+      uint32_t c[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) c[k] = (uint32_t)min(max(evq[j][k], 0), P.time_limit) + cbias;
+      cntq[j][0] = c[0] | (c[2] << 16);
+      cntq[j][1] = c[1] | (c[3] << 16);
+    }
+  }
   const int32_t n_steps = MULTI ? P.n_steps : 1;
   // DEVCTR (graph mode): the step counter comes from device memory, so that a captured CUDA graph can be replayed
   uint64_t ctr_dev = 0;
@@ -418,6 +435,7 @@ rooms_step_kernel(const __grid_constant__ RoomsParams P) {
     int32_t (&ev)[4] = evq[j];
     float rv[4];
     uint32_t tw = 0, trw = 0;
+    uint32_t mraw[4] = {0, 0, 0, 0}; // merged move-table entries of the quad (fused launches: flag bytes by byte permutes)
     uint32_t o32[4] = {0, 0, 0, 0};  // scalar obs, or packed bytes of the vector obs (lo)
     uint32_t o32b[4] = {0, 0, 0, 0}; // second word for 8-byte vector obs
 
@@ -430,7 +448,7 @@ rooms_step_kernel(const __grid_constant__ RoomsParams P) {
     for (int k = 0; k < 4; ++k) {
       const int64_t env = q + k;
       const uint32_t gcell = RGOAL ? goalv[k] : (uint32_t)P.goal_cell;
-      ev[k] += 1;
+      if constexpr (!MULTI) ev[k] += 1;
       const uint32_t a = ((a4[j] >> (8 * k)) & 0xFFu) & (n - 1u);   // n is 4 or 8; out-of-range bytes wrap
       // slipped action a' = #{j : cumsum(P[a])_j < u}, clamped to n-1   (action_utils.py:84-90)
       uint32_t a2 = 0;
@@ -451,6 +469,7 @@ rooms_step_kernel(const __grid_constant__ RoomsParams P) {
       bool blocked, at_goal;
       if constexpr (kMerged) {
         const uint32_t m = moveobs[cellv[k] * 8 + d8];
+        mraw[k] = m;
         cellv[k] = m & 0x3FFFu;
         blocked = (m & 0x8000u) != 0;
         at_goal = (m & 0x4000u) != 0;
@@ -462,10 +481,15 @@ rooms_step_kernel(const __grid_constant__ RoomsParams P) {
         at_goal = cellv[k] == gcell;                     // (:216)
       }
       rv[k] = at_goal ? P.r_goal : (blocked ? P.r_wall : P.r_step);
-      const bool trunc = ev[k] > P.time_limit;            // (:220)
-      tw |= (at_goal ? 1u : 0u) << (8 * k);
-      trw |= (trunc ? 1u : 0u) << (8 * k);
-      again |= ((at_goal | trunc) ? 1u : 0u) << k;
+      bool trunc = false;
+      if constexpr (!MULTI) {
+        trunc = ev[k] > P.time_limit;            // (:220)
+        tw |= (at_goal ? 1u : 0u) << (8 * k);
+        trw |= (trunc ? 1u : 0u) << (8 * k);
+        again |= ((at_goal | trunc) ? 1u : 0u) << k;
+      } else if constexpr (!kMerged) {
+        tw |= (at_goal ? 1u : 0u) << (8 * k);
+      }
       goalv[k] = gcell;
       if constexpr (STATS) {
         float& ret = k == 0 ? ret4[j].x : (k == 1 ? ret4[j].y : (k == 2 ? ret4[j].z : ret4[j].w));
@@ -477,11 +501,23 @@ rooms_step_kernel(const __grid_constant__ RoomsParams P) {
         ret = (at_goal | trunc) ? 0.f : ret;
       }
     }
+    if constexpr (MULTI) {
+      // terminated bytes: the on-goal flag (bit 14) of the four merged entries, gathered with byte permutes
+      if constexpr (kMerged) {
+        const uint32_t hi01 = __byte_perm(mraw[0], mraw[1], 0x0051), hi23 = __byte_perm(mraw[2], mraw[3], 0x0051);
+        tw = (__byte_perm(hi01, hi23, 0x5410) >> 6) & 0x01010101u;
+      }
+      // elapsed += 1 for the four envs; truncated bytes = bit 15 of the biased halves
+      cntq[j][0] += 0x00010001u;
+      cntq[j][1] += 0x00010001u;
+      trw = ((cntq[j][0] >> 15) & 0x00010001u) | ((cntq[j][1] >> 7) & 0x01000100u);
+      again = tw | trw;   // one byte per env
+    }
     // ---- rare: respawn finished envs (one divergence point per quad, not per env) ----
     if (again) {
 #pragma unroll 1
       for (uint32_t m = again; m; m &= m - 1) {
-        const int k = __ffs(m) - 1;
+        const int k = MULTI ? (__ffs(m) - 1) >> 3 : __ffs(m) - 1;
         uint32_t g = 0;
 #pragma unroll
         for (int i = 0; i < 4; ++i) g = i == k ? goalv[i] : g;
@@ -495,6 +531,11 @@ rooms_step_kernel(const __grid_constant__ RoomsParams P) {
             ev[i] = 0;
             if constexpr (kMerged) o32[i] = obstab[fresh & 0xFFFFu];
           }
+        }
+        if constexpr (MULTI) {   // elapsed = 0: the env's counter half goes back to the bias
+          const uint32_t half = (k & 2) ? 0xFFFF0000u : 0x0000FFFFu, fresh_c = (cbias | (cbias << 16)) & half;
+          if (k & 1) cntq[j][1] = (cntq[j][1] & ~half) | fresh_c;
+          else cntq[j][0] = (cntq[j][0] & ~half) | fresh_c;
         }
       }
     }
@@ -537,7 +578,11 @@ rooms_step_kernel(const __grid_constant__ RoomsParams P) {
     const uint32_t (&goalv)[4] = goalq[j];
     st_stream(reinterpret_cast<uint2*>(P.pos + q), make_uint2(cellv[0] | (cellv[1] << 16), cellv[2] | (cellv[3] << 16)));
     if (RGOAL) st_stream(reinterpret_cast<uint2*>(P.goal + q), make_uint2(goalv[0] | (goalv[1] << 16), goalv[2] | (goalv[3] << 16)));
-    st_stream(reinterpret_cast<int4*>(P.elapsed + q), make_int4(evq[j][0], evq[j][1], evq[j][2], evq[j][3]));
+    if constexpr (MULTI)
+      st_stream(reinterpret_cast<int4*>(P.elapsed + q), make_int4((int)((cntq[j][0] & 0xFFFFu) - cbias), (int)((cntq[j][1] & 0xFFFFu) - cbias),
+                                                                  (int)((cntq[j][0] >> 16) - cbias), (int)((cntq[j][1] >> 16) - cbias)));
+    else
+      st_stream(reinterpret_cast<int4*>(P.elapsed + q), make_int4(evq[j][0], evq[j][1], evq[j][2], evq[j][3]));
   }
   if constexpr (STATS) acc.flush(P.stats);
   if constexpr (OBS == GPT_OBS_GRID) {
