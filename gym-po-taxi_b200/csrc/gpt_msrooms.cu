@@ -207,6 +207,20 @@ __global__ void __launch_bounds__(kMsThreads, MULTI ? GPT_MS_MINB_MULTI : GPT_MS
     goalq[j][0] = goal4[j].x & 0xFFFFu; goalq[j][1] = goal4[j].x >> 16; goalq[j][2] = goal4[j].y & 0xFFFFu; goalq[j][3] = goal4[j].y >> 16;
     evq[j][0] = e4[j].x; evq[j][1] = e4[j].y; evq[j][2] = e4[j].z; evq[j][3] = e4[j].w;
   }
+  // MULTI: elapsed counters of a quad as biased 16-bit pairs (see rooms_step_kernel): one packed add per pair and step,
+  // bit 15 of a half = "elapsed > time_limit"; the host fuses only with time_limit <= 32766
+  const uint32_t cbias = 0x7FFFu - (uint32_t)P.time_limit;
+  uint32_t cntq[MULTI ? kMsQpt : 1][2];
+  if constexpr (MULTI) {
+#pragma unroll
+    for (int j = 0; j < kMsQpt; ++j) {
+      uint32_t c[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) c[k] = (uint32_t)min(max(evq[j][k], 0), P.time_limit) + cbias;
+      cntq[j][0] = c[0] | (c[2] << 16);
+      cntq[j][1] = c[1] | (c[3] << 16);
+    }
+  }
   const int32_t n_steps = MULTI ? P.n_steps : 1;
   uint64_t ctr_dev = 0;   // graph mode: step counter from device memory
   if constexpr (DEVCTR) ctr_dev = devctr_fetch_and_advance(P.ctr_ptr, (uint32_t)n_steps);
@@ -242,6 +256,7 @@ __global__ void __launch_bounds__(kMsThreads, MULTI ? GPT_MS_MINB_MULTI : GPT_MS
     int32_t (&ev)[4] = evq[j];
     float rv[4];
     uint32_t tw = 0, trw = 0, again = 0;
+    uint32_t mraw[4] = {0, 0, 0, 0};   // merged move-table entries (fused launches: flag bytes by byte permutes)
     uint32_t lo[4] = {0, 0, 0, 0}, hi[4] = {0, 0, 0, 0};
 
     const uint32_t slipv[4] = {REPLAY ? 0u : slipq[j].x, REPLAY ? 0u : slipq[j].y, REPLAY ? 0u : slipq[j].z, REPLAY ? 0u : slipq[j].w};
@@ -249,7 +264,7 @@ __global__ void __launch_bounds__(kMsThreads, MULTI ? GPT_MS_MINB_MULTI : GPT_MS
 #pragma unroll
     for (int k = 0; k < 4; ++k) {  // straight-line transition of the 4 envs
       const uint32_t gcell = RGOAL ? goalv[k] : (uint32_t)P.goal_cell;
-      ev[k] += 1;
+      if constexpr (!MULTI) ev[k] += 1;
       const uint32_t a = ((a4[j] >> (8 * k)) & 0xFFu) & (n - 1u);
       uint32_t d8;
       if (REPLAY) {  // a' = min(#{j : cumsum(P[a])_j < u}, n-1)   (action_utils.py:84-90)
@@ -266,6 +281,7 @@ __global__ void __launch_bounds__(kMsThreads, MULTI ? GPT_MS_MINB_MULTI : GPT_MS
       bool blocked, at_goal;
       if constexpr (MERGED) {
         const uint32_t m = moveobs[cellv[k] * 8 + d8];
+        mraw[k] = m;
         cellv[k] = m & 0x3FFFu;
         blocked = (m & 0x8000u) != 0;
         at_goal = (m & 0x4000u) != 0;
@@ -277,16 +293,30 @@ __global__ void __launch_bounds__(kMsThreads, MULTI ? GPT_MS_MINB_MULTI : GPT_MS
         at_goal = cellv[k] == gcell;
       }
       rv[k] = at_goal ? P.r_goal : (blocked ? P.r_wall : P.r_step);
-      const bool trunc = ev[k] > P.time_limit;
-      tw |= (at_goal ? 1u : 0u) << (8 * k);
-      trw |= (trunc ? 1u : 0u) << (8 * k);
-      again |= ((at_goal | trunc) ? 1u : 0u) << k;
+      if constexpr (!MULTI) {
+        const bool trunc = ev[k] > P.time_limit;
+        tw |= (at_goal ? 1u : 0u) << (8 * k);
+        trw |= (trunc ? 1u : 0u) << (8 * k);
+        again |= ((at_goal | trunc) ? 1u : 0u) << k;
+      } else if constexpr (!MERGED) {
+        tw |= (at_goal ? 1u : 0u) << (8 * k);
+      }
       goalv[k] = gcell;
+    }
+    if constexpr (MULTI) {
+      if constexpr (MERGED) {   // terminated bytes: the on-goal flag (bit 14) of the four merged entries
+        const uint32_t hi01 = __byte_perm(mraw[0], mraw[1], 0x0051), hi23 = __byte_perm(mraw[2], mraw[3], 0x0051);
+        tw = (__byte_perm(hi01, hi23, 0x5410) >> 6) & 0x01010101u;
+      }
+      cntq[j][0] += 0x00010001u;   // elapsed += 1 for the four envs; truncated bytes = bit 15 of the biased halves
+      cntq[j][1] += 0x00010001u;
+      trw = ((cntq[j][0] >> 15) & 0x00010001u) | ((cntq[j][1] >> 7) & 0x01000100u);
+      again = tw | trw;   // one byte per env
     }
     if (again) {  // rare: respawn finished envs, one divergence point per quad
 #pragma unroll 1
       for (uint32_t m = again; m; m &= m - 1) {
-        const int k = __ffs(m) - 1;
+        const int k = MULTI ? (__ffs(m) - 1) >> 3 : __ffs(m) - 1;
         uint32_t g = 0;
 #pragma unroll
         for (int i = 0; i < 4; ++i) g = i == k ? goalv[i] : g;
@@ -300,6 +330,11 @@ __global__ void __launch_bounds__(kMsThreads, MULTI ? GPT_MS_MINB_MULTI : GPT_MS
             ev[i] = 0;
             if constexpr (MERGED) lo[i] = obstab[fresh & 0xFFFFu];
           }
+        }
+        if constexpr (MULTI) {   // elapsed = 0: the env's counter half goes back to the bias
+          const uint32_t half = (k & 2) ? 0xFFFF0000u : 0x0000FFFFu, fresh_c = (cbias | (cbias << 16)) & half;
+          if (k & 1) cntq[j][1] = (cntq[j][1] & ~half) | fresh_c;
+          else cntq[j][0] = (cntq[j][0] & ~half) | fresh_c;
         }
       }
     }
@@ -349,7 +384,11 @@ __global__ void __launch_bounds__(kMsThreads, MULTI ? GPT_MS_MINB_MULTI : GPT_MS
     const uint32_t (&goalv)[4] = goalq[j];
     st_stream(reinterpret_cast<uint2*>(P.pos + q), make_uint2(cellv[0] | (cellv[1] << 16), cellv[2] | (cellv[3] << 16)));
     if (RGOAL) st_stream(reinterpret_cast<uint2*>(P.goal + q), make_uint2(goalv[0] | (goalv[1] << 16), goalv[2] | (goalv[3] << 16)));
-    st_stream(reinterpret_cast<int4*>(P.elapsed + q), make_int4(evq[j][0], evq[j][1], evq[j][2], evq[j][3]));
+    if constexpr (MULTI)
+      st_stream(reinterpret_cast<int4*>(P.elapsed + q), make_int4((int)((cntq[j][0] & 0xFFFFu) - cbias), (int)((cntq[j][1] & 0xFFFFu) - cbias),
+                                                                  (int)((cntq[j][0] >> 16) - cbias), (int)((cntq[j][1] >> 16) - cbias)));
+    else
+      st_stream(reinterpret_cast<int4*>(P.elapsed + q), make_int4(evq[j][0], evq[j][1], evq[j][2], evq[j][3]));
   }
 }
 
@@ -539,7 +578,8 @@ static void* ms_pick(bool rgoal, bool merged, bool replay, bool multi, bool devc
   return (void*)k;
 }
 
-bool msrooms_can_fuse(const gpt_env* env) { return env->cfg.rng_mode == GPT_RNG_PHILOX; }
+// (the fused kernels keep the elapsed counters as biased 16-bit pairs: time limits beyond 32766 step one launch at a time)
+bool msrooms_can_fuse(const gpt_env* env) { return env->cfg.rng_mode == GPT_RNG_PHILOX && env->cfg.time_limit >= 0 && env->cfg.time_limit <= 32766; }
 
 int msrooms_launch(gpt_env* env, const LaunchArgs& a) {
   const gpt_config& c = env->cfg;
