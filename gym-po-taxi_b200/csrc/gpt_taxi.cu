@@ -933,21 +933,12 @@ int taxi_launch(gpt_env* env, const LaunchArgs& a) {
     const bool one = c.taxi_n_dropoffs == 1;
     KM km = c.track_stats ? (one ? (KM)taxi_table_multi_kernel<true, 2, 128, true> : (KM)taxi_table_multi_kernel<true, 2, 128, false>)
                           : (one ? (KM)taxi_table_multi_kernel<false, 2, 128, true> : (KM)taxi_table_multi_kernel<false, 2, 128, false>);
-    int qpt = 2;
+    const int qpt = 2;   // launch shapes 1x128, 1x256, 2x256 measured within 2 % of 2x128 (profiles/README.md) and removed
     threads = 128;
-    // tuning knob GPT_TAXI_MULTI_SHAPE = <quads per thread><threads> (default 2128)
-    static const int mshape = getenv("GPT_TAXI_MULTI_SHAPE") ? atoi(getenv("GPT_TAXI_MULTI_SHAPE")) : 0;
     const bool devctr_multi = env->graph_mode && !c.track_stats;   // graph mode: step counter in device memory
     if (devctr_multi) {
       M.p.ctr_ptr = env->d_counter;
       km = one ? (KM)taxi_table_multi_kernel<false, 2, 128, true, true> : (KM)taxi_table_multi_kernel<false, 2, 128, false, true>;
-    } else if (!c.track_stats && one) {
-      switch (mshape) {
-        case 1128: km = (KM)taxi_table_multi_kernel<false, 1, 128, true>; qpt = 1; threads = 128; break;
-        case 1256: km = (KM)taxi_table_multi_kernel<false, 1, 256, true>; qpt = 1; threads = 256; break;
-        case 2256: km = (KM)taxi_table_multi_kernel<false, 2, 256, true>; qpt = 2; threads = 256; break;
-        default: break;
-      }
     }
     // default: the TMA-I/O kernel (bulk-copied action rows and outputs); it needs 16-byte aligned rows in every
     // stream, i.e. aligned base pointers and a rollout-slot stride that is a multiple of 16 rows.
@@ -956,7 +947,7 @@ int taxi_launch(gpt_env* env, const LaunchArgs& a) {
     const bool legacy = env->fused_io == 2 || (legacy_env && env->fused_io == 0);
     const uintptr_t align_or = (uintptr_t)P.actions | (uintptr_t)P.obs | (uintptr_t)P.reward | (uintptr_t)P.terminated | (uintptr_t)P.truncated |
                                (uintptr_t)env->d_blob | (uintptr_t)(a.out_stride_rows & 15) | (uintptr_t)(env->taxi_hobs_off & 15u);
-    if (!legacy && !c.track_stats && mshape == 0 && (align_or & 15u) == 0) {
+    if (!legacy && !c.track_stats && (align_or & 15u) == 0) {
       const uint32_t tab_bytes = env->blob_bytes - env->taxi_hobs_off;   // hobs | alias | trans: what the fused step reads
       const uint32_t stage_off = (tab_bytes + 127u) & ~127u;
       const size_t need = (size_t)stage_off + (size_t)kTmaBufs * kTmaStage + (size_t)kTmaActRows * kTmaEnvs;
@@ -979,14 +970,11 @@ int taxi_launch(gpt_env* env, const LaunchArgs& a) {
         smem = need;
       }
     }
-    if (km) {
-    const int64_t envs_per_cta = (int64_t)threads * kQuad * qpt;
-    grid = (int)(((int64_t)a.n_tiles * kTileEnvs + envs_per_cta - 1) / envs_per_cta);
-    kernel = (const void*)km;
-    args[0] = (void*)&M;
-    // tuning knob: extra dynamic shared memory per CTA lowers the resident CTAs per SM (wave quantisation experiments)
-    static const int pad_kb = getenv("GPT_TAXI_PAD_KB") ? atoi(getenv("GPT_TAXI_PAD_KB")) : 0;
-    smem += (size_t)pad_kb * 1024;
+    if (km) {   // per-thread I/O kernel
+      const int64_t envs_per_cta = (int64_t)threads * kQuad * qpt;
+      grid = (int)(((int64_t)a.n_tiles * kTileEnvs + envs_per_cta - 1) / envs_per_cta);
+      kernel = (const void*)km;
+      args[0] = (void*)&M;
     }
   } else if (env->taxi_use_table) {
     using K = void (*)(const TaxiParams);

@@ -265,10 +265,12 @@ def test_fused_multi_step_launch_equals_single_steps(obs_type, goal_xy, layout):
 
 @pytest.mark.parametrize("obs_type,goal_xy,layout,cardinal", [("hansen8", (0, 0), "4", False), ("vector_hansen8", (0, 0), "4", False),
                                                               ("vector_goal_hansen4", None, "8", True), ("vector_mdp", (0, 0), "16", False),
-                                                              ("vector_mdp_goal", None, "2", True), ("room_goal", None, "10b", False)])
+                                                              ("vector_mdp_goal", None, "2", True), ("room_goal", None, "10b", False),
+                                                              ("grid", (0, 0), "4", False), ("grid", None, "8", True)])
 def test_fused_launch_odd_tiles_padded_rows_in_place(obs_type, goal_xy, layout, cardinal):
     """Fused launches at an ODD number of 512-env tiles (half-filled last CTA), rollout storage with padded rows and
-    in-place outputs — all equal to single-step launches, for every observation width (2, 4, 8 bytes per env)."""
+    in-place outputs — all equal to single-step launches, for every observation width (2, 4, 8 bytes per env) and the
+    window observation (TMA tile store into rollout slots, per-lane stores for the in-place outputs)."""
     from gym_po.envs import RoomsEnv
     b, T = 1400, 23
     kw = dict(layout=layout, obs_type=obs_type, goal_xy=goal_xy, time_limit=9, step_reward=-0.1, wall_reward=-0.5)
