@@ -54,7 +54,8 @@ struct gpt_env {
   gpt::HostPath host;
 
   // ---- taxi ----
-  uint32_t taxi_rep_shift = 0, taxi_trans_off = 0, taxi_hobs_off = 0, taxi_alias_off = 0, taxi_trans16_off = 0, taxi_single_bytes = 0;
+  uint32_t taxi_rep_shift = 0, taxi_trans_off = 0, taxi_hobs_off = 0, taxi_alias_off = 0, taxi_trans16_off = 0, taxi_single_bytes = 0,
+           taxi_tfused16_off = 0, taxi_t32_end = 0, taxi_s16_off = 0, taxi_s16_alias_off = 0;
   bool taxi_use_table = false;
   int taxi_shape = 0;  // launch-shape tuning knob (GPT_TAXI_SHAPE), 0 = default
   // ---- rooms / crooms ----

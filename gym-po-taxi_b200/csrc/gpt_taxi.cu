@@ -421,27 +421,36 @@ __global__ void __launch_bounds__(THREADS, STATS ? 1 : GPT_TAXI_MINB_MULTI * 128
 // per CTA and step (double-buffered; cp.async.bulk.wait_group.read guards the reuse).  On the rollout access pattern —
 // 86 % writes into 4 output streams x T slots — this moves 6.2 TB/s where per-thread stores reach 5.6 TB/s
 // (scripts/stream_pattern_probe4.cu).  One CTA barrier per step.
+constexpr int kT16RowShift = 4;                // 16-bit table of the TMA kernel: 8 actions x 2 B per state
 constexpr int kTmaEnvs = 1024;                 // envs per CTA: 128 threads x 2 quads x 4 envs
 constexpr int kTmaStage = kTmaEnvs * 10;       // staging bytes per buffer
 #ifndef GPT_TAXI_TMA_BUFS
 #define GPT_TAXI_TMA_BUFS 2
 #endif
 #ifndef GPT_TAXI_TMA_ACT_ROWS
-#define GPT_TAXI_TMA_ACT_ROWS 4   // 43.5 KB per CTA on the 5x5 map = 5 CTAs per SM (measured: 8 rows = 4 CTAs/SM 91.3 us, 4 rows = 5 CTAs/SM 87.1 us per 10-step launch)
+#define GPT_TAXI_TMA_ACT_ROWS 4   // with the 32-bit table (43.5 KB per CTA on the 5x5 map): 8 rows = 4 CTAs/SM 91.3 us, 4 rows = 5 CTAs/SM 87.1 us per 10-step launch
 #endif
 constexpr int kTmaBufs = GPT_TAXI_TMA_BUFS;          // power of two
 constexpr int kTmaActRows = GPT_TAXI_TMA_ACT_ROWS;   // power of two
 #ifndef GPT_TAXI_MINB_TMA
-#define GPT_TAXI_MINB_TMA 4
+#define GPT_TAXI_MINB_TMA 6
 #endif
 struct TaxiTmaParams {
   TaxiMultiParams m;
-  uint32_t tab_bytes;     // bytes of the blob's fused part (hobs | alias | trans), staged at shared offset 0
+  uint32_t tab_bytes;     // bytes of the blob's part this kernel reads (hobs | alias | 16-bit table), staged at shared offset 0
   uint32_t stage_off;     // shared-memory offset of the staging buffers (128-byte aligned), the action ring follows
 };
 
-template <bool ONE, bool DEVCTR = false>
+// 16-bit table: entries [state][8 actions] (16-byte rows; the state is kept as the row's byte offset): next state id << 2 |
+// illegal << 1 | delivered.  The observation is the next state id itself, or — Hansen observations — one more 16-bit
+// lookup.  Half the size of the per-thread kernel's 32-bit table.
+// TAB = 0: the 32-bit table of the per-thread kernel (observation in the entry); 1: the 16-bit table; 2: the 16-bit
+// table + observation lookup (Hansen observations).  The host picks 0 while that leaves five CTAs per SM (the 5x5 map:
+// 87.1 us per 10-step launch against 87.3 with the 16-bit table at six CTAs per SM) and the 16-bit table for larger maps
+// (8x8 map: 108.1 -> 91.4 us).
+template <bool ONE, int TAB, bool DEVCTR = false>
 __global__ void __launch_bounds__(128, GPT_TAXI_MINB_TMA) taxi_multi_tma_kernel(const __grid_constant__ TaxiTmaParams TP) {
+  constexpr int kShift = TAB == 0 ? kRowShift : kT16RowShift;   // log2 of a table row's bytes
   constexpr bool REPLAY = false;
   constexpr int QPT = 2;
   const TaxiMultiParams& M = TP.m;
@@ -483,7 +492,7 @@ __global__ void __launch_bounds__(128, GPT_TAXI_MINB_TMA) taxi_multi_tma_kernel(
   }
   uint64_t ctr_dev = 0;   // graph mode: step counter from device memory, advanced by n_steps for the next launch
   if constexpr (DEVCTR) ctr_dev = devctr_fetch_and_advance(P.ctr_ptr, (uint32_t)n_steps);
-  uint32_t off[QPT][4], ndv[QPT][4];   // off = state id << kRowShift
+  uint32_t off[QPT][4], ndv[QPT][4];   // off = state id << kShift
   int32_t ev[QPT][4];
 #pragma unroll
   for (int j = 0; j < QPT; ++j) {
@@ -494,8 +503,8 @@ __global__ void __launch_bounds__(128, GPT_TAXI_MINB_TMA) taxi_multi_tma_kernel(
       const int4 s4 = ld_stream(reinterpret_cast<const int4*>(P.s + q));
       const int4 e4 = ld_stream(reinterpret_cast<const int4*>(P.elapsed + q));
       const uint32_t nd4 = ONE ? 0u : ld_stream(reinterpret_cast<const uint32_t*>(P.ndrop + q));
-      off[j][0] = (uint32_t)s4.x << kRowShift; off[j][1] = (uint32_t)s4.y << kRowShift;
-      off[j][2] = (uint32_t)s4.z << kRowShift; off[j][3] = (uint32_t)s4.w << kRowShift;
+      off[j][0] = (uint32_t)s4.x << kShift; off[j][1] = (uint32_t)s4.y << kShift;
+      off[j][2] = (uint32_t)s4.z << kShift; off[j][3] = (uint32_t)s4.w << kShift;
       ev[j][0] = e4.x; ev[j][1] = e4.y; ev[j][2] = e4.z; ev[j][3] = e4.w;
 #pragma unroll
       for (int k = 0; k < 4; ++k) ndv[j][k] = (nd4 >> (8 * k)) & 0xFFu;
@@ -519,12 +528,21 @@ __global__ void __launch_bounds__(128, GPT_TAXI_MINB_TMA) taxi_multi_tma_kernel(
         uint32_t tw = 0, trw = 0, gw = 0;   // terminated / truncated / delivered, one byte per env
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-          const uint32_t aoff = (k == 0 ? (a4 << 2) : (a4 >> (8 * k - 2))) & 0x1Cu;   // 4 * (action & 7)
-          const uint32_t ent = *reinterpret_cast<const uint32_t*>(trans + off[j][k] + aoff);
+          uint32_t ent;
+          if constexpr (TAB == 0) {
+            const uint32_t aoff = (k == 0 ? (a4 << 2) : (a4 >> (8 * k - 2))) & 0x1Cu;   // 4 * (action & 7)
+            ent = *reinterpret_cast<const uint32_t*>(trans + off[j][k] + aoff);
+            off[j][k] = ent & kTransRow;
+            ov[k] = (int32_t)(ent >> 16);
+          } else {
+            const uint32_t aoff = (k == 0 ? (a4 << 1) : (a4 >> (8 * k - 1))) & 0xEu;   // 2 * (action & 7)
+            ent = *reinterpret_cast<const uint16_t*>(trans + off[j][k] + aoff);
+            const uint32_t nxt = ent >> 2;
+            off[j][k] = nxt << kShift;
+            ov[k] = TAB == 2 ? (int32_t)hobs[nxt] : (int32_t)nxt;
+          }
           const uint32_t goal = ent & kTransGoal;
           if constexpr (!ONE) ndv[j][k] += goal;
-          off[j][k] = ent & kTransRow;
-          ov[k] = (int32_t)(ent >> 16);
           ev[j][k] += 1;
           rv[k] = goal ? P.r_goal : ((ent & kTransBad) ? P.r_bad : P.r_any);
           const uint32_t term = ONE ? goal : (uint32_t)(ndv[j][k] == (uint32_t)P.n_dropoffs);      // (:276-279)
@@ -550,12 +568,12 @@ __global__ void __launch_bounds__(128, GPT_TAXI_MINB_TMA) taxi_multi_tma_kernel(
 #pragma unroll
           for (int i = 0; i < 4 * QPT; ++i) cur = i == idx ? off[i >> 2][i & 3] : cur;
           const uint32_t le = loc + j * kQuadStride + k;
-          const uint32_t fresh = taxi_fix_inline<REPLAY, DEVCTR>(P, alias, tile + le, (uint32_t)t, cur >> kRowShift, full, ctr_dev);
+          const uint32_t fresh = taxi_fix_inline<REPLAY, DEVCTR>(P, alias, tile + le, (uint32_t)t, cur >> kShift, full, ctr_dev);
           reinterpret_cast<int32_t*>(buf)[le] = (int32_t)hobs[fresh];   // observation of the post-reset state (same thread wrote the quad)
 #pragma unroll
           for (int i = 0; i < 4 * QPT; ++i) {
             if (i == idx) {
-              off[i >> 2][i & 3] = fresh << kRowShift;
+              off[i >> 2][i & 3] = fresh << kShift;
               ev[i >> 2][i & 3] = full ? 0 : ev[i >> 2][i & 3];
               if constexpr (!ONE) ndv[i >> 2][i & 3] = full ? 0u : ndv[i >> 2][i & 3];
             }
@@ -588,8 +606,8 @@ __global__ void __launch_bounds__(128, GPT_TAXI_MINB_TMA) taxi_multi_tma_kernel(
 #pragma unroll
     for (int j = 0; j < QPT; ++j) {
       const int64_t q = base + j * kQuadStride;
-      st_stream(reinterpret_cast<int4*>(P.s + q), make_int4((int)(off[j][0] >> kRowShift), (int)(off[j][1] >> kRowShift),
-                                                            (int)(off[j][2] >> kRowShift), (int)(off[j][3] >> kRowShift)));
+      st_stream(reinterpret_cast<int4*>(P.s + q), make_int4((int)(off[j][0] >> kShift), (int)(off[j][1] >> kShift),
+                                                            (int)(off[j][2] >> kShift), (int)(off[j][3] >> kShift)));
       st_stream(reinterpret_cast<int4*>(P.elapsed + q), make_int4(ev[j][0], ev[j][1], ev[j][2], ev[j][3]));
       st_stream(reinterpret_cast<uint32_t*>(P.ndrop + q),
                 ONE ? 0u : ((ndv[j][0] & 0xFFu) | ((ndv[j][1] & 0xFFu) << 8) | ((ndv[j][2] & 0xFFu) << 16) | ((ndv[j][3] & 0xFFu) << 24)));
@@ -786,7 +804,7 @@ int taxi_create(gpt_env* env, const gpt_config* c) {
     // tabulate the whole step relation with the same rule the arithmetic kernel applies per env
     const int nl = c->taxi_nlocs, cols = c->taxi_cols;
     std::vector<uint32_t> trans((size_t)ns * kTransCols);
-    std::vector<uint16_t> hobs((size_t)ns), trans16((size_t)ns * kT16Cols);
+    std::vector<uint16_t> hobs((size_t)ns), trans16((size_t)ns * kT16Cols), tfused16((size_t)ns * kTransCols);
     for (int64_t st = 0; st < ns; ++st) {   // observation per state: the id itself, or the Hansen re-encoding
       const int d0 = (int)(st % nl), p0 = (int)((st / nl) % (nl + 1)), cell0 = (int)(st / nl / (nl + 1));
       hobs[st] = c->taxi_hansen_obs ? (uint16_t)((((celltab[(size_t)cell0 * rep] & 15) * (nl + 1)) + p0) * nl + d0) : (uint16_t)st;
@@ -810,6 +828,7 @@ int taxi_create(gpt_env* env, const gpt_config* c) {
         const bool bad = act && !goal && !pickup;
         const int64_t s2 = ((int64_t)cell * (nl + 1) + p) * nl + d0;
         trans[(size_t)st * kTransCols + a] = ((uint32_t)hobs[s2] << 16) | ((uint32_t)s2 << kRowShift) | (goal ? kTransGoal : 0u) | (bad ? kTransBad : 0u);
+        tfused16[(size_t)st * kTransCols + a] = (uint16_t)((s2 << 2) | (goal ? kTransGoal : 0u) | (bad ? kTransBad : 0u));   // ns <= 2048: 11 + 2 bits
         if (a < kT16Cols) trans16[(size_t)st * kT16Cols + a] = (uint16_t)(s2 | (goal ? kT16Goal : 0u) | (bad ? kT16Bad : 0u));
       }
     }
@@ -820,6 +839,11 @@ int taxi_create(gpt_env* env, const gpt_config* c) {
     env->taxi_alias_off = blob_append(blob, alias);
     env->taxi_single_bytes = align16((uint32_t)blob.size());
     env->taxi_trans_off = blob_append(blob, trans);
+    env->taxi_t32_end = align16((uint32_t)blob.size());      // fused kernels with the 32-bit table stage hobs .. here
+    // 16-bit section of the TMA fused kernel (larger maps): its own copies of hobs and alias, then the 16-bit table
+    env->taxi_s16_off = blob_append(blob, hobs);
+    env->taxi_s16_alias_off = blob_append(blob, alias);
+    env->taxi_tfused16_off = blob_append(blob, tfused16);
   } else {
     blob_append(blob, celltab);
     env->taxi_alias_off = blob_append(blob, alias);
@@ -885,7 +909,7 @@ int taxi_launch(gpt_env* env, const LaunchArgs& a) {
     if (!P.rp_reset_state || !P.rp_new_p || !P.rp_new_d) return fail(GPT_E_UNBOUND, "taxi: replay arrays must be bound in replay mode");
   }
   P.blob = env->d_blob;
-  P.blob_bytes = env->blob_bytes;
+  P.blob_bytes = env->taxi_use_table ? env->taxi_t32_end : env->blob_bytes;   // (the 16-bit section behind is the TMA kernel's)
   P.rep_shift = env->taxi_rep_shift;
   P.env_offset = c.env_offset;
   P.first_tile = a.first_tile;
@@ -916,7 +940,7 @@ int taxi_launch(gpt_env* env, const LaunchArgs& a) {
   void* args[] = {(void*)&P};
   const void* kernel;
   int threads, grid;
-  size_t smem = env->blob_bytes;
+  size_t smem = P.blob_bytes;
   TaxiMultiParams M;
   TaxiTmaParams TP;
   const bool hansen = c.taxi_hansen_obs != 0;
@@ -946,28 +970,38 @@ int taxi_launch(gpt_env* env, const LaunchArgs& a) {
     static const bool legacy_env = getenv("GPT_TAXI_FUSED_LEGACY") != nullptr;
     const bool legacy = env->fused_io == 2 || (legacy_env && env->fused_io == 0);
     const uintptr_t align_or = (uintptr_t)P.actions | (uintptr_t)P.obs | (uintptr_t)P.reward | (uintptr_t)P.terminated | (uintptr_t)P.truncated |
-                               (uintptr_t)env->d_blob | (uintptr_t)(a.out_stride_rows & 15) | (uintptr_t)(env->taxi_hobs_off & 15u);
+                               (uintptr_t)env->d_blob | (uintptr_t)(a.out_stride_rows & 15) | (uintptr_t)((env->taxi_hobs_off | env->taxi_s16_off) & 15u);
     if (!legacy && !c.track_stats && (align_or & 15u) == 0) {
-      const uint32_t tab_bytes = env->blob_bytes - env->taxi_hobs_off;   // hobs | alias | trans: what the fused step reads
+      // table format: the 32-bit table (hobs | alias | trans) while it leaves five CTAs per SM, else the 16-bit section
+      const size_t io_bytes = (size_t)kTmaBufs * kTmaStage + (size_t)kTmaActRows * kTmaEnvs;
+      const uint32_t t32_bytes = env->taxi_t32_end - env->taxi_hobs_off;
+      const bool t32 = (((size_t)t32_bytes + 127u) & ~(size_t)127u) + io_bytes + 1024 <= 227 * 1024 / 5;
+      const uint32_t sec_off = t32 ? env->taxi_hobs_off : env->taxi_s16_off;
+      const uint32_t tab_bytes = t32 ? t32_bytes : env->blob_bytes - env->taxi_s16_off;
       const uint32_t stage_off = (tab_bytes + 127u) & ~127u;
-      const size_t need = (size_t)stage_off + (size_t)kTmaBufs * kTmaStage + (size_t)kTmaActRows * kTmaEnvs;
+      const size_t need = (size_t)stage_off + io_bytes;
       if (need <= 200 * 1024) {
         TP.m = M;
-        TP.m.p.blob = env->d_blob + env->taxi_hobs_off;
+        TP.m.p.blob = env->d_blob + sec_off;
         TP.m.p.hobs_off = 0;
-        TP.m.p.alias_off = env->taxi_alias_off - env->taxi_hobs_off;
-        TP.m.p.trans_off = env->taxi_trans_off - env->taxi_hobs_off;
+        TP.m.p.alias_off = (t32 ? env->taxi_alias_off : env->taxi_s16_alias_off) - sec_off;
+        TP.m.p.trans_off = (t32 ? env->taxi_trans_off : env->taxi_tfused16_off) - sec_off;
         TP.tab_bytes = tab_bytes;
         TP.stage_off = stage_off;
         using KT = void (*)(const TaxiTmaParams);
-        KT kt = devctr_multi ? (one ? (KT)taxi_multi_tma_kernel<true, true> : (KT)taxi_multi_tma_kernel<false, true>)
-                             : (one ? (KT)taxi_multi_tma_kernel<true, false> : (KT)taxi_multi_tma_kernel<false, false>);
+#define GPT_TAXI_TMA_PICK2(O, D) (t32 ? (KT)taxi_multi_tma_kernel<O, 0, D> : (hansen ? (KT)taxi_multi_tma_kernel<O, 2, D> : (KT)taxi_multi_tma_kernel<O, 1, D>))
+#define GPT_TAXI_TMA_PICK(D) (one ? GPT_TAXI_TMA_PICK2(true, D) : GPT_TAXI_TMA_PICK2(false, D))
+        KT kt = devctr_multi ? GPT_TAXI_TMA_PICK(true) : GPT_TAXI_TMA_PICK(false);
+#undef GPT_TAXI_TMA_PICK
+#undef GPT_TAXI_TMA_PICK2
         km = nullptr;
         kernel = (const void*)kt;
         args[0] = (void*)&TP;
         threads = 128;
         grid = (int)(((int64_t)a.n_tiles * kTileEnvs + kTmaEnvs - 1) / kTmaEnvs);
         smem = need;
+        // five or six CTAs per SM need the largest shared-memory carveout
+        cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
       }
     }
     if (km) {   // per-thread I/O kernel
