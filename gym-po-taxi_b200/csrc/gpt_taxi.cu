@@ -422,7 +422,11 @@ __global__ void __launch_bounds__(THREADS, STATS ? 1 : GPT_TAXI_MINB_MULTI * 128
 // 86 % writes into 4 output streams x T slots — this moves 6.2 TB/s where per-thread stores reach 5.6 TB/s
 // (scripts/stream_pattern_probe4.cu).  One CTA barrier per step.
 constexpr int kT16RowShift = 4;                // 16-bit table of the TMA kernel: 8 actions x 2 B per state
-constexpr int kTmaEnvs = 1024;                 // envs per CTA: 128 threads x 2 quads x 4 envs
+#ifndef GPT_TAXI_TMA_THREADS
+#define GPT_TAXI_TMA_THREADS 128
+#endif
+constexpr int kTmaThreads = GPT_TAXI_TMA_THREADS;
+constexpr int kTmaEnvs = kTmaThreads * 8;      // envs per CTA: threads x 2 quads x 4 envs
 constexpr int kTmaStage = kTmaEnvs * 10;       // staging bytes per buffer
 #ifndef GPT_TAXI_TMA_BUFS
 #define GPT_TAXI_TMA_BUFS 2
@@ -449,7 +453,7 @@ struct TaxiTmaParams {
 // 87.1 us per 10-step launch against 87.3 with the 16-bit table at six CTAs per SM) and the 16-bit table for larger maps
 // (8x8 map: 108.1 -> 91.4 us).
 template <bool ONE, int TAB, bool DEVCTR = false>
-__global__ void __launch_bounds__(128, GPT_TAXI_MINB_TMA) taxi_multi_tma_kernel(const __grid_constant__ TaxiTmaParams TP) {
+__global__ void __launch_bounds__(kTmaThreads, GPT_TAXI_MINB_TMA) taxi_multi_tma_kernel(const __grid_constant__ TaxiTmaParams TP) {
   constexpr int kShift = TAB == 0 ? kRowShift : kT16RowShift;   // log2 of a table row's bytes
   constexpr bool REPLAY = false;
   constexpr int QPT = 2;
@@ -478,7 +482,7 @@ __global__ void __launch_bounds__(128, GPT_TAXI_MINB_TMA) taxi_multi_tma_kernel(
   const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
   const int64_t first = (int64_t)P.first_tile * kTileEnvs, last = first + (int64_t)P.n_tiles * kTileEnvs;
   const int64_t tile = first + (int64_t)blockIdx.x * kTmaEnvs;          // the CTA's envs: [tile, tile + valid)
-  const uint32_t valid = (uint32_t)(last - tile < kTmaEnvs ? last - tile : kTmaEnvs);   // 512 or 1024
+  const uint32_t valid = (uint32_t)(last - tile < kTmaEnvs ? last - tile : kTmaEnvs);   // a multiple of 512
   const uint32_t loc = warp * (kQuadStride * QPT) + lane * kQuad;       // thread's first quad inside the CTA tile (+ j*128)
   const bool active = loc < valid;                                      // whole warps: a warp owns 256 consecutive envs
   const int64_t base = tile + loc;
@@ -997,7 +1001,7 @@ int taxi_launch(gpt_env* env, const LaunchArgs& a) {
         km = nullptr;
         kernel = (const void*)kt;
         args[0] = (void*)&TP;
-        threads = 128;
+        threads = kTmaThreads;
         grid = (int)(((int64_t)a.n_tiles * kTileEnvs + kTmaEnvs - 1) / kTmaEnvs);
         smem = need;
         // five or six CTAs per SM need the largest shared-memory carveout
