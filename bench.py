@@ -29,7 +29,7 @@ METRIC, UNIT = "env_steps_per_sec", "env-steps/s"
 # T = 10 -> 20 -> 40 at 482 -> 523 -> 543 G env-steps/s with the same fraction of the HBM peak on the restated bytes.
 MAX_SLOTS = 20
 # configurations also timed (briefly) after the headline so that the driver-run line carries them
-EXTRA_WORKLOADS = ("rooms_hansen8", "rooms_grid5", "rooms_grid9", "crooms", "tag", "msrooms")
+EXTRA_WORKLOADS = ("rooms_hansen8", "rooms_grid5", "rooms_grid9", "crooms", "tag", "msrooms", "rooms_grid5_l32", "rooms_hansen8_l32")
 
 # algorithmic bytes per env-step (DESIGN.md "Algorithmic bytes")
 WORKLOADS = {
@@ -55,6 +55,10 @@ WORKLOADS = {
                     desc="multistory FourRooms (3 floors, stairs), mdp obs, 1/3 action-slip, cardinal actions, fixed goal, Philox RNG"),
     "rooms_grid9": dict(alg_bytes=19 + 81, state_bytes=12, n_act=8, dtype="u8", cpu_family="rooms_grid9",
                         desc="FourRooms '4', 9x9 egocentric window obs, 0.2 action-slip, fixed goal"),
+    "rooms_grid5_l32": dict(alg_bytes=19 + 25, state_bytes=12, n_act=8, dtype="u8", cpu_family="rooms_grid5",
+                            desc="ROOMS layout '32' (25x49 map, the large-map case), 5x5 egocentric window obs, 0.2 action-slip, fixed goal"),
+    "rooms_hansen8_l32": dict(alg_bytes=23, state_bytes=12, n_act=8, dtype="int32", cpu_family="rooms_hansen8",
+                              desc="ROOMS layout '32' (25x49 map), hansen8 obs, 0.2 action-slip, fixed goal"),
 }
 
 
@@ -210,6 +214,10 @@ def make_env(workload, b, rank, seed=0):
         return RoomsEnv(b, "4", obs_type="grid", obs_n=5, seed=seed, env_offset=rank * b)
     if workload == "rooms_grid9":
         return RoomsEnv(b, "4", obs_type="grid", obs_n=9, seed=seed, env_offset=rank * b)
+    if workload == "rooms_grid5_l32":
+        return RoomsEnv(b, "32", obs_type="grid", obs_n=5, seed=seed, env_offset=rank * b)
+    if workload == "rooms_hansen8_l32":
+        return RoomsEnv(b, "32", obs_type="hansen8", seed=seed, env_offset=rank * b)
     if workload in ("crooms", "crooms_f64"):
         from gym_po.envs import CRoomsEnv
         return CRoomsEnv(b, "4", obs_type="vector_mdp", seed=seed, env_offset=rank * b,
