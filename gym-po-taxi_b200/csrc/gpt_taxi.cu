@@ -11,7 +11,11 @@
 // consecutive envs at tile + j*128 + 4*l (j = 0..3), so every warp-wide access is one fully used
 // 512 B (int32/float32 streams) or 128 B (byte streams) contiguous segment.
 //
-// Two kernels implement the same step:
+// Kernels implementing the same step:
+//   * taxi_multi_tma_kernel / taxi_table_multi_kernel: T consecutive steps in ONE launch (gpt_step_many), state in
+//     registers; the first moves its per-step I/O with the TMA engine (bulk-copied action rows, outputs staged in shared
+//     memory and written by four bulk stores per CTA and step) and is the default, the second loads and stores per thread
+//     (track_stats, unaligned streams, A/B runs).  See the comments at the kernels.
 //   * taxi_table_kernel (used when ns <= 2048, i.e. both reference maps): the complete (state, action) ->
 //     (next state, delivered?, illegal?) relation is tabulated on the host (ns x 6 uint16, 6 KB for the
 //     5x5 map) and lives in shared memory, so the per-env main path is ONE data-dependent LDS plus ~20
