@@ -203,7 +203,8 @@ GPT_API int gpt_reset(gpt_env* env, int has_seed, uint64_t seed, void* stream);
 GPT_API int gpt_step(gpt_env* env, const void* actions, void* stream);
 GPT_API int gpt_step_dlpack(gpt_env* env, void* managed_actions, void* stream);
 /* T consecutive steps from an action stream [T, capacity]; outputs of step t go to the bound
- * output arrays offset by t*out_stride_rows rows (0 = overwrite in place every step). */
+ * output arrays offset by t*out_stride_rows rows (0 = in place: the arrays hold the LAST step's results afterwards;
+ * otherwise >= capacity — rollout slots may be padded). */
 GPT_API int gpt_step_many(gpt_env* env, const void* actions, int32_t n_steps, int64_t out_stride_rows, void* stream);
 /* Taxi (table kernel), ROOMS and MSRooms in Philox mode run gpt_step_many as ONE fused launch: the state stays in
  * registers for the n_steps steps, only actions are read and outputs written per step; results are bit-identical to
@@ -211,7 +212,8 @@ GPT_API int gpt_step_many(gpt_env* env, const void* actions, int32_t n_steps, in
  * 1 = fused, the family's default I/O path, 2 = fused with TMA I/O where the family has it (Taxi, where it is the
  * default: action rows by bulk loads, outputs staged in shared memory and written by bulk stores), 3 = fused with
  * per-thread loads/stores.  ROOMS / MSRooms have the per-thread path only: their fused step is bound by instruction
- * issue, not by its I/O. */
+ * issue, not by its I/O; they fuse with time_limit <= 32766 (16-bit elapsed counters in registers) and
+ * step one launch at a time beyond that.  The window observations leave through one TMA bulk store per warp tile. */
 #define GPT_FUSED_OFF 0
 #define GPT_FUSED_DEFAULT 1
 #define GPT_FUSED_TMA 2
