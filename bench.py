@@ -440,7 +440,7 @@ def run_b200(args):
         host_actions[:] = hrng.integers(0, wl["n_act"], size=(w.slots, b)).astype(np.int8)
     else:
         host_actions[:] = hrng.uniform(-1, 1, size=host_actions.shape).astype(np.float32)
-    e2e_k = args.e2e_steps if args.e2e_steps is not None else k
+    e2e_k = args.e2e_steps if args.e2e_steps is not None else min(k, 100)   # a host-path step takes ~9 ms at 2^22 envs
     e2e_reps = 1 if args.quick else 7
     for i in range(3):
         env.step_host(host_actions[i % w.slots])
