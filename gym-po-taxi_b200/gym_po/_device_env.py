@@ -355,9 +355,10 @@ class DeviceVecEnv:
         N.check(N.lib.gpt_set_fused_steps(self._h, mode))
 
     def set_graph_mode(self, enable: bool = True):
-        """Make ``step()`` capturable into a CUDA graph (Taxi / ROOMS, Philox mode): the Philox step counter moves into
-        device memory and a one-thread tick kernel advances it after every step, so every replay of a captured graph
-        draws fresh random numbers.  Call it outside of stream capture; ``step_host`` is unavailable while it is on."""
+        """Make ``step()`` / ``step_many()`` capturable into a CUDA graph (every family, Philox mode): the Philox step
+        counter moves into device memory and the step kernels read and advance it themselves, so every replay of a
+        captured graph draws fresh random numbers (fused launches and programmatic dependent launch keep working).
+        Call it outside of stream capture; ``step_host`` is unavailable while it is on."""
         with self._on_device():
             N.check(N.lib.gpt_set_graph_mode(self._h, int(bool(enable)), self._stream()))
 

@@ -19,7 +19,7 @@ for name, env, n_act in (("taxi", TaxiVecEnv(512, device="cuda:0", seed=0), 5), 
     t2 = time.perf_counter()
     print(f"{name}: {1e6 * (t1 - t0) / n:.2f} us per step() call issued, {1e6 * (t2 - t0) / n:.2f} us incl. drain")
 
-# graph mode: 32 captured steps replayed (includes the tick kernels); per-step cost without any Python in the loop
+# graph mode: 32 captured steps replayed; per-step cost without any Python in the loop
 for b in (512, 1 << 20):
     env = TaxiVecEnv(b, device="cuda:0", seed=0)
     env.reset(seed=0)
