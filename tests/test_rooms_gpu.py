@@ -305,3 +305,45 @@ def test_fused_launch_odd_tiles_padded_rows_in_place(obs_type, goal_xy, layout, 
         o = c.step(acts[t])
     for n, x in zip(names, o[:4]):
         assert torch.equal(a._arrays[n][:b].reshape(x.shape).view(x.dtype), x), n
+
+
+def test_step_many_with_a_huge_time_limit_steps_one_launch_at_a_time():
+    """The fused kernels keep the elapsed counters as biased 16-bit pairs: a time limit beyond 32766 is not fused —
+    `step_many` then runs T single-step launches with the same results."""
+    from gym_po.envs import RoomsEnv
+    b, T = 2000, 6
+    a = RoomsEnv(b, device=DEV, seed=2, obs_type="hansen8", time_limit=40000)
+    c = RoomsEnv(b, device=DEV, seed=2, obs_type="hansen8", time_limit=40000)
+    a.reset(seed=2); c.reset(seed=2)
+    el = torch.randint(32760, 40001, (b,), device=DEV, dtype=torch.int32)
+    a.elapsed.copy_(el)
+    c.elapsed.copy_(el)
+    acts = torch.randint(0, 8, (T, a.capacity), dtype=torch.int8, device=DEV)
+    out = {n: torch.zeros((T,) + tuple(a._arrays[n].shape), dtype=a._arrays[n].dtype, device=DEV)
+           for n in ("obs", "reward", "terminated", "truncated")}
+    l0 = a.launch_count
+    a.step_many(acts, out)
+    assert a.launch_count == l0 + T
+    for t in range(T):
+        o = c.step(acts[t])
+        for n, x in zip(("obs", "reward", "terminated", "truncated"), o[:4]):
+            assert torch.equal(out[n][t][:b].reshape(x.shape).view(x.dtype), x), (n, t)
+    assert torch.equal(a.elapsed, c.elapsed)
+    # at the largest fused limit the packed counters still truncate exactly at elapsed > time_limit
+    a = RoomsEnv(b, device=DEV, seed=3, obs_type="hansen8", time_limit=32766)
+    c = RoomsEnv(b, device=DEV, seed=3, obs_type="hansen8", time_limit=32766)
+    a.reset(seed=3); c.reset(seed=3)
+    el = torch.randint(32760, 32767, (b,), device=DEV, dtype=torch.int32)
+    a.elapsed.copy_(el)
+    c.elapsed.copy_(el)
+    l0 = a.launch_count
+    a.step_many(acts, out)
+    assert a.launch_count == l0 + 1
+    seen_trunc = False
+    for t in range(T):
+        o = c.step(acts[t])
+        seen_trunc |= bool(o[3].any())
+        for n, x in zip(("obs", "reward", "terminated", "truncated"), o[:4]):
+            assert torch.equal(out[n][t][:b].reshape(x.shape).view(x.dtype), x), (n, t)
+    assert seen_trunc
+    assert torch.equal(a.elapsed, c.elapsed)
